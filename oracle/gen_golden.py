@@ -1,0 +1,279 @@
+"""
+TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference/ART through oracle/refshim) on the scenes of oracle/scenes.py.
+
+    python oracle/gen_golden.py            # all scenes + scale subsets
+    python oracle/gen_golden.py cfg3_2tor  # selected ones
+
+Runs only in the build container (needs /root/reference).  The fixtures it writes are committed;
+nothing at test/bench time on the GPU box reads the reference.
+
+Each fixture holds: the scene spec (JSON), the element poses the reference's OEPlacement +
+misalignment methods produced, derived optic parameters, the source bundle, the bundle after
+EVERY element (number, P, U, sum(path), incidence), the autoplace'd detector and the
+statistics (GetResultSummary, getETransmission, weighted SDs, per-ray centred 2-D points and
+delays).
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "refshim"))
+sys.path.insert(0, HERE)
+
+import load_reference as lr  # noqa: E402
+import scenes as sc  # noqa: E402
+import art_oracle as orc  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(HERE), "tests", "golden")
+REF = None
+
+
+def ref():
+    global REF
+    if REF is None:
+        REF = lr.load()
+    return REF
+
+
+# ------------------------------------------------------------------------------------------
+def build_support(spec):
+    ms = ref().msupp
+    kind, p = spec[0], spec[1:]
+    return {
+        "round": ms.SupportRound, "roundhole": ms.SupportRoundHole, "rect": ms.SupportRectangle,
+        "recthole": ms.SupportRectangleHole, "rectrecthole": ms.SupportRectangleRectHole,
+    }[kind](*p)
+
+
+def build_optic(spec):
+    R = ref()
+    mm = R.mmirror
+    sup = build_support(spec["support"])
+    k = spec["kind"]
+    if k == "mask":
+        return R.mmask.Mask(sup)
+    if k == "plane":
+        m = mm.MirrorPlane(sup)
+    elif k == "spherical":
+        m = mm.MirrorSpherical(spec["radius_signed"], sup)
+    elif k == "cylindrical":
+        m = mm.MirrorCylindrical(spec["radius_signed"], sup)
+    elif k == "parabolic":
+        m = mm.MirrorParabolic(spec["feff"], spec["offaxisangle_deg"], sup)
+    elif k == "toroidal":
+        m = mm.MirrorToroidal(spec["majorradius"], spec["minorradius"], sup)
+    elif k == "ellipsoidal":
+        kw = {a: spec[a] for a in ("SemiMajorAxis", "SemiMinorAxis", "OffAxisAngle", "f_object", "f_image")
+              if a in spec}
+        m = mm.MirrorEllipsoidal(sup, **kw)
+    else:
+        raise ValueError(k)
+    if spec.get("defects"):
+        dl = []
+        for d in spec["defects"]:
+            assert d["kind"] == "zernike"
+            coeffs = {(int(n), int(mm_)): c for n, mm_, c in d["coefficients"]}
+            dl.append(R.mdef.Zernike(sup, coeffs))
+        m = mm.DeformedMirror(m, dl)
+    return m
+
+
+def derived_optic(spec, obj):
+    """Oracle-side description of a reference optic object (derived parameters included)."""
+    k = spec["kind"]
+    base = obj.Mirror if type(obj).__name__ == "DeformedMirror" else obj
+    d = {"kind": k, "support": list(spec["support"]), "type": obj.type}
+    if k in ("spherical", "cylindrical"):
+        d["radius"] = float(base.radius)
+    elif k == "parabolic":
+        d.update(feff=float(base.feff), offaxisangle=float(base.offaxisangle), p=float(base.p))
+    elif k == "toroidal":
+        d.update(majorradius=float(base.majorradius), minorradius=float(base.minorradius))
+    elif k == "ellipsoidal":
+        d.update(a=float(base.a), b=float(base.b), offaxisangle=float(base._offaxisangle))
+    if spec.get("defects"):
+        d["defects"] = []
+        for ds, dobj in zip(spec["defects"], obj.DeformationList):
+            d["defects"].append({"kind": "zernike", "R": float(dobj.R), "max_order": int(dobj.max_order),
+                                 "coefficients": ds["coefficients"]})
+    d["centre"] = [float(v) for v in obj.get_centre()]
+    return d
+
+
+def build_chain(scene):
+    R = ref()
+    optics = [build_optic(s) for s in scene["optics"]]
+    with lr.quiet():
+        chain = R.mp.OEPlacement(dict(scene["source"]), optics, list(scene["distances"]),
+                                 list(scene["incidences"]), list(scene["plane_angles"]), scene["name"])
+    for op in scene.get("post", []):
+        getattr(chain.optical_elements[op["element"]], op["op"])(op["value"])
+    return chain
+
+
+def bundle_arrays(rays):
+    return {
+        "num": np.array([r.number for r in rays], dtype=np.int64),
+        "P": np.array([r.point for r in rays], dtype=np.float64).reshape(-1, 3),
+        "U": np.array([r.vector for r in rays], dtype=np.float64).reshape(-1, 3),
+        "path": np.array([np.sum(r.path) for r in rays], dtype=np.float64),
+        "inc": np.array([np.nan if r.incidence is None else r.incidence for r in rays], dtype=np.float64),
+        "I": np.array([np.nan if r.intensity is None else r.intensity for r in rays], dtype=np.float64),
+    }
+
+
+def run_scene(scene, ignore_defects=True, source_rays=None, extra=None):
+    R = ref()
+    chain = build_chain(scene)
+    if source_rays is not None:
+        chain.source_rays = source_rays
+    t0 = time.time()
+    with lr.quiet():
+        out = R.mp.RayTracingCalculation(chain.source_rays, chain.optical_elements, IgnoreDefects=ignore_defects)
+    dt = time.time() - t0
+    data = {}
+    spec = dict(scene)
+    spec["ignore_defects"] = bool(ignore_defects)
+    spec["derived_optics"] = [derived_optic(s, oe.type) for s, oe in zip(scene["optics"], chain.optical_elements)]
+    src = bundle_arrays(chain.source_rays)
+    data["src_num"], data["src_P"], data["src_U"], data["src_I"] = src["num"], src["P"], src["U"], src["I"]
+    for k, oe in enumerate(chain.optical_elements):
+        data[f"el{k}_position"] = np.asarray(oe.position, dtype=np.float64)
+        data[f"el{k}_normal"] = np.asarray(oe.normal, dtype=np.float64)
+        data[f"el{k}_majoraxis"] = np.asarray(oe.majoraxis, dtype=np.float64)
+        b = bundle_arrays(out[k])
+        for key in ("num", "P", "U", "path", "inc"):
+            data[f"out{k}_{key}"] = b[key]
+    final = out[-1]
+    ninter, entering = 0, len(chain.source_rays)
+    for k in range(len(out)):
+        ninter += entering
+        entering = len(out[k])
+    spec["interactions"] = ninter
+    spec["reference_trace_seconds"] = dt
+    if len(final) > 1:
+        det = R.mdet.Detector(chain.optical_elements[-1].position)
+        det.autoplace(final, scene["detector_distance"])
+        with lr.quiet():
+            sd, dur = R.mplots.GetResultSummary(det, final)
+        xy = np.array(det.get_PointList2DCentre(final))
+        delays = np.array(det.get_Delays(final))
+        w = [r.intensity for r in final]
+        data.update(
+            det_centre=det.centre, det_normal=det.normal, det_refpoint=det.refpoint,
+            det_xy_centre=xy, det_delays=delays,
+            SpotSizeSD=np.float64(sd), DurationSD=np.float64(dur),
+            ETransmission=np.float64(R.mplots.getETransmission(chain.source_rays, final)),
+            SpotSizeSD_w=np.float64(R.mp.WeightedStandardDeviation(xy, w)),
+            DurationSD_w=np.float64(R.mp.WeightedStandardDeviation(delays, w)),
+            NA=np.float64(R.mp.ReturnNumericalAperture(final, 1)),
+            Diameter=np.float64(R.mgeo.DiameterPointList(list(xy))),
+            det_distance=np.float64(det.get_distance()),
+        )
+    if extra:
+        spec.update(extra)
+    data["spec"] = np.array(json.dumps(spec))
+    return data, [len(o) for o in out], dt
+
+
+def save(name, data):
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **data)
+    return path
+
+
+# ------------------------------------------------------------------------------------------
+def subset_source_rays(scene, n_full, idx):
+    """Reference Ray objects for rays `idx` of the n_full-ray synthetic bundle.
+
+    Built with the reference's own constructors / rotation (ART/ModuleSource.py:23-81,135-169),
+    only the Vogel-spiral row is evaluated per index instead of for all n_full rays; intensities
+    take their normalisation from the full bundle (oracle.source_for)."""
+    R = ref()
+    sp = dict(scene["source"])
+    sp["NumberRays"] = n_full
+    first = scene["optics"][0]["support"]
+    _, _, num, inten = orc.source_for(sp, first_support=None, k=idx)
+    ez = np.array([0, 0, 1])
+    axis = np.array([1, 0, 0])
+    rays = []
+    if sp["Divergence"] == 0:
+        radius = sp["SourceSize"] / 2
+        xy = orc.spiral_vogel(n_full, radius, idx)
+        for (x, y), k in zip(xy, idx):
+            rays.append(R.mray.Ray(np.array([x, y, 0]), np.array([0, 0, 1]), Number=int(k),
+                                   Wavelength=sp["Wavelength"]))
+    else:
+        xy = orc.spiral_vogel(n_full, 1 * np.tan(sp["Divergence"]), idx)
+        for (x, y), k in zip(xy, idx):
+            rays.append(R.mray.Ray(np.array([0, 0, 0]), np.array([x, y, 1]), Number=int(k),
+                                   Wavelength=sp["Wavelength"]))
+    rays = R.mgeo.RotationRayList(rays, ez, axis)
+    rays = R.mgeo.TranslationRayList(rays, np.array([0, 0, 0]))
+    for r, i in zip(rays, inten):
+        r.intensity = np.float64(i)
+    return rays
+
+
+def gen_subsets(which):
+    todo = {
+        "cfg2_sub": ("cfg2", 2000, [True]),
+        "cfg3_sub": ("cfg3", 2000, [True]),
+        "cfg4_sub": ("cfg4", 1500, [True, False]),
+        "cfg5_sub": ("cfg5", 1000, [True]),
+    }
+    for name, (wl, m, modes) in todo.items():
+        if which and name not in which:
+            continue
+        w = sc.WORKLOADS[wl]
+        scene = sc.resolve(w["scene"])
+        n_full = w["rays"]
+        n_src = n_full - 1 if scene["source"]["Divergence"] == 0 else n_full  # PlaneWaveDisk off-by-one
+        idx = np.sort(np.random.default_rng(1234).choice(n_src, m, replace=False))
+        variants = [None]
+        if "sweep" in w:
+            sw = w["sweep"]
+            vals = np.linspace(sw["lo"], sw["hi"], sw["n"])
+            variants = [(i, float(vals[i])) for i in (0, 300, 1023)]
+        for var in variants:
+            for ign in modes:
+                scn = dict(scene)
+                tag = name
+                extra = {"subset_of": n_full, "workload": wl}
+                if var is not None:
+                    sw = w["sweep"]
+                    scn["post"] = list(scn.get("post", [])) + [
+                        {"op": f"rotate_{sw['axis']}_by", "element": sw["element"], "value": var[1]}]
+                    tag += f"_v{var[0]}"
+                    extra["variant_index"] = var[0]
+                if len(modes) > 1:
+                    tag += "_ign" if ign else "_def"
+                rays = subset_source_rays(scn, n_full, idx)
+                data, counts, dt = run_scene(scn, ignore_defects=ign, source_rays=rays, extra=extra)
+                p = save(tag, data)
+                print(f"{tag:28s} survivors {counts}  ref trace {dt:.2f}s -> {os.path.relpath(p)}")
+
+
+def main(argv):
+    which = set(argv)
+    for name in sc.SCENES:
+        if which and name not in which:
+            continue
+        scene = sc.resolve(name)
+        has_def = any(o.get("defects") for o in scene["optics"])
+        for ign in ([True, False] if has_def else [True]):
+            tag = name + (("_ign" if ign else "_def") if has_def else "")
+            data, counts, dt = run_scene(scene, ignore_defects=ign)
+            p = save(tag, data)
+            print(f"{tag:28s} survivors {counts}  ref trace {dt:.2f}s -> {os.path.relpath(p)}")
+    gen_subsets(which)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
