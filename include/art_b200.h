@@ -1,0 +1,243 @@
+/*
+ * art_b200.h -- C ABI of libart_b200.so: the B200-native replacement for the ray-bundle hot path
+ * of ART (mightymightys/AttosecondRaytracing v0.93).
+ *
+ * Plain C: pointers, sizes and POD structs only; no torch / C++ types cross this boundary.
+ * Every function returns 0 on success and a negative ART_E_* code on failure; the message of the
+ * last failure on the calling thread is available from art_last_error().  No function
+ * synchronises the device or allocates device memory unless its comment says so.  All ray
+ * columns are DEVICE pointers owned by the caller (in the Python host: torch CUDA tensors) except
+ * in the *_host entry points, where they are host pointers.  `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * repository root).
+ */
+#ifndef ART_B200_H
+#define ART_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ART_B200_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define ART_OK 0
+#define ART_E_INVALID (-1)  /* bad argument */
+#define ART_E_CUDA (-2)     /* CUDA runtime error (message holds cudaGetErrorString) */
+#define ART_E_NOMEM (-3)
+#define ART_E_UNSUPPORTED (-4)
+
+/* limits */
+#define ART_MAX_ELEMENTS 16 /* elements per chain (longer chains: chain the calls) */
+
+/* surface kinds: the `type` of an optic, ART/ModuleMirror.py + ART/ModuleMask.py */
+enum {
+  ART_SURF_PLANE = 0,       /* MirrorPlane       ART/ModuleMirror.py:42   params: -                */
+  ART_SURF_SPHERICAL = 1,   /* MirrorSpherical   ART/ModuleMirror.py:117  params: |Radius|         */
+  ART_SURF_PARABOLIC = 2,   /* MirrorParabolic   ART/ModuleMirror.py:212  params: p (semi latus r.) */
+  ART_SURF_TOROIDAL = 3,    /* MirrorToroidal    ART/ModuleMirror.py:391  params: R major, r minor */
+  ART_SURF_ELLIPSOIDAL = 4, /* MirrorEllipsoidal ART/ModuleMirror.py:565  params: a, b             */
+  ART_SURF_CYLINDRICAL = 5, /* MirrorCylindrical ART/ModuleMirror.py:781  params: |Radius|         */
+  ART_SURF_MASK = 6         /* Mask              ART/ModuleMask.py:21     params: -                */
+};
+
+/* support (aperture) kinds, ART/ModuleSupport.py; params as the reference constructors take them */
+enum {
+  ART_SUPP_ROUND = 0,         /* SupportRound(Radius)                                   :46  */
+  ART_SUPP_ROUND_HOLE = 1,    /* SupportRoundHole(Radius, RadiusHole, cx, cy)           :109 */
+  ART_SUPP_RECT = 2,          /* SupportRectangle(DimX, DimY)                           :200 */
+  ART_SUPP_RECT_HOLE = 3,     /* SupportRectangleHole(DimX, DimY, RadiusHole, cx, cy)   :273 */
+  ART_SUPP_RECT_RECT_HOLE = 4 /* SupportRectangleRectHole(DimX, DimY, HoleX, HoleY, cx, cy) :373 */
+};
+
+/*
+ * One optical element = ART/ModuleOpticalElement.py:23 OpticalElement(Type, Position, Normal,
+ * MajorAxis) plus the numbers the tracer needs from `Type` (the optic): its surface kind and
+ * parameters, `Type.get_centre()`, its support and its Zernike defects.
+ * The lab->element rotation is derived inside the library from (normal, majoraxis) exactly as
+ * ART/ModuleProcessing.py:289-294 + ART/ModuleGeometry.py:333-343 do (Kahan angle, 1e-10
+ * thresholds, the MINUS-identity branch at pi).
+ */
+typedef struct ArtElementDesc {
+  int32_t surface;           /* ART_SURF_*                                              */
+  int32_t support;           /* ART_SUPP_*                                              */
+  double surface_params[4];  /* see ART_SURF_*                                          */
+  double support_params[6];  /* see ART_SUPP_*                                          */
+  double centre[3];          /* Type.get_centre(), element frame                        */
+  double position[3];        /* OpticalElement.position, lab frame                      */
+  double normal[3];          /* OpticalElement.normal                                   */
+  double majoraxis[3];       /* OpticalElement.majoraxis                                */
+  int32_t n_defects;         /* DeformedMirror.DeformationList length (Zernike only)    */
+  int32_t first_defect;      /* index of this element's first defect in the defect list */
+} ArtElementDesc;
+
+/*
+ * One Zernike defect = ART/ModuleDefects.py:149 Zernike(Support, coefficients):
+ * `radius` = Support._CircumCirc(), coefficient c[i] belongs to the reference key (n[i], m[i]),
+ * 0 <= m <= n (ART/recursive_zernike_generator.py index convention: m < n/2 sine-like, m > n/2
+ * cosine-like, (1,0) = y, (1,1) = x).
+ */
+typedef struct ArtZernikeDesc {
+  double radius;
+  int32_t n_coefficients;
+  const int32_t* n;
+  const int32_t* m;
+  const double* c;
+} ArtZernikeDesc;
+
+/*
+ * Structure-of-arrays FP64 ray bundle: the `list[Ray]` of ART/ModuleOpticalRay.py:11.
+ * Ray i has point (px,py,pz)[i], unit vector (ux,uy,uz)[i], path[i] = np.sum(Ray.path),
+ * incidence[i], intensity[i]; Ray.number is the index i (or number[i] on the host side, the
+ * kernels never need it).  alive[i] == 0 marks a ray the reference would have dropped from the
+ * list (ART/ModuleMirror.py:932, ART/ModuleMask.py:132); its other columns are unspecified.
+ * Nullable columns: path (input: 0), incidence (not produced), intensity, alive (input: all alive).
+ * Columns must be 16-byte aligned.
+ */
+typedef struct ArtBundleView {
+  double* px; double* py; double* pz;
+  double* ux; double* uy; double* uz;
+  double* path;
+  double* incidence;
+  double* intensity;
+  uint8_t* alive;
+  int64_t n;
+} ArtBundleView;
+
+/* Detector plane, ART/ModuleDetector.py:25.  `rot` takes lab vectors into the detector frame
+ * (normal -> ez, RotationPoint semantics) as get_PointList2D does (:212-234); `l0` is the pivot
+ * subtracted from optical path lengths before they are squared. */
+typedef struct ArtDetector {
+  double centre[3];
+  double normal[3];
+  double refpoint[3];
+  double rot[9];
+  double l0;
+  double n_rays; /* rays the central ray was averaged over (0: detector undefined) */
+} ArtDetector;
+
+/* central-ray sums over the surviving final rays, one row of ART_CENTRAL_LEN doubles:
+ * sum ux,uy,uz, sum px,py,pz, sum path, count, sum intensity (survivors), sum intensity (all
+ * source rays; the denominator of getETransmission, ART/ModuleAnalysisAndPlots.py:62-77) */
+enum {
+  ART_C_SUX = 0, ART_C_SUY, ART_C_SUZ, ART_C_SPX, ART_C_SPY, ART_C_SPZ, ART_C_SPATH, ART_C_N,
+  ART_C_SW_OUT, ART_C_SW_IN,
+  ART_CENTRAL_LEN = 10
+};
+
+/* detector moments, one row of ART_MOMENTS_LEN doubles (x, y in the detector plane relative to
+ * Detector.centre, d = L - l0 with L the total optical path to the plane, w = intensity) */
+enum {
+  ART_M_N = 0, ART_M_SX, ART_M_SY, ART_M_SXX, ART_M_SYY, ART_M_SD, ART_M_SDD,
+  ART_M_SW, ART_M_SWX, ART_M_SWY, ART_M_SWXX, ART_M_SWYY, ART_M_SWD, ART_M_SWDD,
+  ART_M_XMIN, ART_M_XMAX, ART_M_YMIN, ART_M_YMAX, ART_M_DMIN, ART_M_DMAX,
+  ART_M_TMAX, /* max over rays of tan^2(angle(ray, central vector)/2): ReturnNumericalAperture,
+                 ART/ModuleProcessing.py:536-566, NA = sin(2 atan(sqrt(TMAX))) */
+  ART_MOMENTS_LEN = 24 /* [21..23] reserved, written as 0 */
+};
+
+/* trace flags */
+#define ART_TRACE_IGNORE_DEFECTS 1u /* IgnoreDefects=True of RayTracingCalculation (its default) */
+#define ART_TRACE_NO_INCIDENCE 2u   /* do not compute Ray.incidence (saves an atan2 per ray)      */
+
+typedef struct ArtChain ArtChain;
+
+int32_t art_version(void);
+const char* art_last_error(void);
+
+/* CUDA device count / name of device `dev` (plumbing for the host; no reference counterpart). */
+int32_t art_device_count(int32_t* count);
+
+/*
+ * The lab->element rotation of one element, row-major 3x3 (host arithmetic, no GPU needed).
+ * Replaces the per-ray RotationRayList(..., n, ez) / RotationRayList(..., mPrime, ex) pair of
+ * ART/ModuleProcessing.py:290-294.
+ */
+int32_t art_element_rotation(const double normal[3], const double majoraxis[3], double rot_out[9]);
+
+/*
+ * Build an immutable chain on the current CUDA device: `n_variants` x `n_elements` element
+ * descriptions (variant-major; variants share surface kinds but may differ in pose -- the
+ * OpticalChain lists of ART/ModuleOpticalChain.py:533 get_OE_loop_list) and the Zernike defects
+ * they refer to.  Allocates a few KB of device memory and copies synchronously.
+ * Replaces the `optical_elements` argument of RayTracingCalculation, ART/ModuleProcessing.py:250.
+ */
+int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_elements, int32_t n_variants,
+                         const ArtZernikeDesc* defects, int32_t n_defects, ArtChain** chain_out);
+int32_t art_chain_destroy(ArtChain* chain);
+
+/*
+ * The trace: ART/ModuleProcessing.py:250-313 RayTracingCalculation(source_rays,
+ * optical_elements, IgnoreDefects) for variants [variant_first, variant_first + n_variants).
+ *   in          source bundle (shared by all variants).
+ *   out_final   bundle after the last element; for variant v its rows are [v*in->n, (v+1)*in->n)
+ *               of the columns (v counted from variant_first).  May be NULL.
+ *   out_history NULL, or `n_elements` views: bundle after element k (same row layout).
+ *   central_out NULL, or device pointer to n_variants x ART_CENTRAL_LEN doubles receiving the
+ *               sums over the surviving final rays that FindCentralRay needs
+ *               (ART/ModuleProcessing.py:464-482), reduced in a fixed order (deterministic).
+ * One fused kernel launch; every element of the chain is applied per ray in registers.
+ */
+int32_t art_trace(ArtChain* chain, int32_t variant_first, int32_t n_variants, const ArtBundleView* in,
+                  const ArtBundleView* out_final, const ArtBundleView* out_history, uint32_t flags,
+                  double* central_out, void* stream);
+
+/*
+ * Detector.autoplace, ART/ModuleDetector.py:109-137, for n_variants detectors at once, entirely
+ * on the device: central (device, n_variants x ART_CENTRAL_LEN) -> det_out (device, n_variants ArtDetector).
+ */
+int32_t art_detector_autoplace(const double* central, double distance, int32_t n_variants,
+                               ArtDetector* det_out, void* stream);
+
+/* Fill an ArtDetector (host struct) from centre / normal / refpoint: computes rot; l0 as given.
+ * For manually placed detectors (ARTmain.py:113 setup_detector, ManualDetector branch). */
+int32_t art_detector_make(const double centre[3], const double normal[3], const double refpoint[3],
+                          double l0, ArtDetector* det_out);
+
+/*
+ * Detector response + statistics sums: Detector.get_PointList3D/2D, get_Delays
+ * (ART/ModuleDetector.py:191-279) and the sums behind StandardDeviation /
+ * WeightedStandardDeviation / getETransmission / DiameterPointList
+ * (ART/ModuleProcessing.py:485-532, ART/ModuleAnalysisAndPlots.py:62, ART/ModuleGeometry.py:164).
+ *   bundle   n_variants x n rays (row layout as art_trace's out_final; intensity, if non-NULL,
+ *            has n entries shared by all variants).
+ *   det      device, n_variants detectors.
+ *   x_out, y_out, l_out  NULL or device columns (n_variants x n): in-plane coordinates relative
+ *            to Detector.centre and total optical path length L (mm) of each alive ray.
+ *   moments_out  device, n_variants x ART_MOMENTS_LEN.
+ */
+int32_t art_detector_moments(const ArtBundleView* bundle, int32_t n_variants, const ArtDetector* det,
+                             double* x_out, double* y_out, double* l_out, double* moments_out,
+                             void* stream);
+
+/*
+ * End-to-end convenience with HOST buffers: copies the source bundle to the device, traces
+ * variant 0, autoplaces the detector at `distance` (or uses *manual_det if non-NULL), reduces the
+ * moments and copies back moments (ART_MOMENTS_LEN), central sums (ART_CENTRAL_LEN), the detector
+ * and -- where the corresponding host pointers are non-NULL -- the final bundle.  Synchronises.
+ * Uses an internal device workspace that grows to the largest n seen (allocates on growth).
+ * This is the call a host without device buffers makes in place of
+ * OpticalChain.get_output_rays() + GetResultSummary (ARTmain.py:248-290 run_ART).
+ */
+int32_t art_run_host(ArtChain* chain, const ArtBundleView* in_host, const ArtBundleView* out_final_host,
+                     uint32_t flags, double distance, const ArtDetector* manual_det,
+                     double* moments_host, double* central_host, ArtDetector* det_host);
+
+/* FP64 FMA throughput probe for the roofline denominator: runs a register-resident DFMA loop on
+ * the whole device and returns measured FLOP/s (2 per FMA).  Synchronises. */
+int32_t art_probe_fp64(double* flops_per_second);
+/* HBM copy-bandwidth probe (read+write bytes per second of a device-to-device stream copy kernel). */
+int32_t art_probe_hbm(double* bytes_per_second);
+
+/* Number of kernel launches issued by this library on this process so far (for bench.py's
+ * `gpu_launches`). */
+int64_t art_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ART_B200_H */
