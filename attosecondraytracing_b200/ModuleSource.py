@@ -1,0 +1,113 @@
+"""Light sources -- the ray-bundle generators of ART/ModuleSource.py, producing RayBundles.
+
+The reference builds `list[Ray]` in Python loops; here the Vogel-spiral bundles are evaluated in
+closed form by a CUDA kernel (art_source_generate) straight into the device columns, so a 10^8-ray
+bundle (or one rank's slice of it) never exists on the host.  Ray numbers are the spiral indices.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import ModuleGeometry as mgeo
+from . import _cabi
+from .engine import _ptr, _stream, require_cuda
+from .ModuleOpticalRay import RayBundle
+
+_SRC_COLUMNS = ("px", "py", "pz", "ux", "uy", "uz", "intensity")
+
+
+def _generate(kind, n_total, first, count, rho, axis, origin, wavelength, device):
+    device = require_cuda(device)
+    b = RayBundle(count, device=device, columns=_SRC_COLUMNS, wavelength=wavelength)
+    if first != 0:
+        b.number = torch.arange(first, first + count, device=device, dtype=torch.int64)
+    v = b.view()
+    v.intensity = None
+    with torch.cuda.device(device):
+        _cabi.check(_cabi.lib().art_source_generate(kind, n_total, first, count, float(rho), _cabi.vec3(axis),
+                                                    _cabi.vec3(origin), C.byref(v), _stream()))
+    b.col("intensity").fill_(1.0)
+    return b
+
+
+def PointSource(S, Axis, Divergence, NbRays, Wavelength=None, device=None, first=0, count=None):
+    """Rays from the point S filling a cone of half-angle Divergence (rad) about Axis on Vogel's
+    spiral (ART/ModuleSource.py:54-81).  `first`/`count` select a slice of the NbRays-ray bundle."""
+    count = NbRays - first if count is None else count
+    return _generate(0, NbRays, first, count, np.tan(Divergence), Axis, S, Wavelength, device)
+
+
+def PlaneWaveDisk(Centre, Axis, Radius, NbRays, Wavelength=None, device=None, first=0, count=None):
+    """Collimated rays from a disk (ART/ModuleSource.py:135-169).  As in the reference the bundle
+    holds NbRays-1 rays: points 0 .. NbRays-2 of the NbRays-point spiral."""
+    count = NbRays - 1 - first if count is None else count
+    if first + count > NbRays - 1:
+        raise ValueError("PlaneWaveDisk(NbRays) has NbRays-1 rays")
+    return _generate(1, NbRays, first, count, Radius, Axis, Centre, Wavelength, device)
+
+
+def ApplyGaussianIntensityToRayList(RayList, IntensityFraction=1 / np.e**2, group=None, axis=None, scale=None):
+    """Gaussian intensity profile, 1 on the axis falling to IntensityFraction at the edge of the
+    bundle (ART/ModuleSource.py:219-261): by angle for a diverging bundle (max angle > 1e-12),
+    by distance of the ray origin from the lab origin otherwise.
+
+    RayList: RayBundle on the device (filled in place and returned).  With a torch.distributed
+    `group` (or the default group when initialised and group=True) the axis and the extent are
+    all-reduced so that every rank normalises by the FULL bundle."""
+    b = RayList
+    require_cuda(b.device)
+    import torch.distributed as dist
+    use_dist = group is not None and dist.is_available() and dist.is_initialized()
+    grp = None if group is True else group
+    if axis is None:
+        su = torch.stack([b.col("ux").sum(), b.col("uy").sum(), b.col("uz").sum(),
+                          torch.tensor(float(b.n), dtype=torch.float64, device=b.device)])
+        if use_dist:
+            dist.all_reduce(su, op=dist.ReduceOp.SUM, group=grp)
+        su = su.cpu().numpy()
+        axis = mgeo.Normalize(su[:3] / su[3])  # FindCentralRay(...).vector, ART/ModuleProcessing.py:464-482
+    v = b.view()
+    ext = torch.zeros(2, dtype=torch.float64, device=b.device)
+    with torch.cuda.device(b.device):
+        _cabi.check(_cabi.lib().art_source_extents(C.byref(v), _cabi.vec3(axis), _ptr(ext), _stream()))
+    if use_dist:
+        dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=grp)
+    max_angle, max_dist = (float(x) for x in ext.cpu().numpy())
+    mode = 0 if max_angle > 1e-12 else 1
+    if scale is None:
+        scale = max_angle if mode == 0 else max_dist
+    with torch.cuda.device(b.device):
+        _cabi.check(_cabi.lib().art_source_intensity(C.byref(v), _cabi.vec3(axis), mode, float(scale),
+                                                     float(IntensityFraction), _stream()))
+    return b
+
+
+def synthetic_source(SourceProperties, first_optic_support=None, device=None, first=0, count=None, group=None,
+                     intensity=True):
+    """The source bundle `OEPlacement` launches (ART/ModuleProcessing.py:55-79): from the origin along
+    +x; a plane-wave disk when Divergence == 0 (radius SourceSize/2, or from the first optic's
+    support when SourceSize == 0), else a point source; Gaussian intensities down to 1/e^2 at the edge.
+    ExtendedSource (Divergence and SourceSize both non-zero) is not part of the synthetic bundles."""
+    div = SourceProperties["Divergence"]
+    size = SourceProperties["SourceSize"]
+    n = int(SourceProperties["NumberRays"])
+    wl = SourceProperties.get("Wavelength")
+    origin = np.zeros(3)
+    axis = np.array([1.0, 0.0, 0.0])
+    if div == 0:
+        if size == 0:
+            sup = first_optic_support
+            radius = 0.5 * min(sup.dimX, sup.dimY) if hasattr(sup, "dimX") else sup.radius
+        else:
+            radius = size / 2
+        b = PlaneWaveDisk(origin, axis, radius, n, Wavelength=wl, device=device, first=first, count=count)
+    else:
+        if size != 0:
+            raise NotImplementedError("ExtendedSource bundles are not generated on the device")
+        b = PointSource(origin, axis, div, n, Wavelength=wl, device=device, first=first, count=count)
+    if intensity:
+        ApplyGaussianIntensityToRayList(b, 1 / np.e**2, group=group)
+    return b

@@ -1,0 +1,687 @@
+// art_b200.cu -- the C ABI of libart_b200.so (include/art_b200.h): argument checking, the
+// host-side lowering of scene descriptions, launch configuration and the host-buffer entry point.
+// All ray arithmetic happens in the kernels of art_kernels.cuh; there is no CPU ray path here.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "art_kernels.cuh"
+#include "art_lowering.h"
+
+using namespace art;
+
+// -------------------------------------------------------------------------------------------------
+// error plumbing
+// -------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int32_t fail(int32_t code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define ART_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return fail(ART_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+  } while (0)
+#define ART_LAUNCHED()                                                                       \
+  do {                                                                                       \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess) return fail(ART_E_CUDA, std::string("launch: ") + cudaGetErrorString(e__)); \
+  } while (0)
+
+// -------------------------------------------------------------------------------------------------
+// the chain object
+// -------------------------------------------------------------------------------------------------
+struct HostWorkspace {
+  double* cols = nullptr;     // 7 input + 8 output columns of cap_n doubles each
+  uint8_t* alive = nullptr;
+  size_t cap_n = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  double* pinned = nullptr;   // results staging: moments | central | detector
+};
+
+struct ArtChain {
+  int device = 0;
+  int sm_count = 148;
+  int n_elements = 0, n_variants = 0, n_defects = 0;
+  ElemDev* d_elems = nullptr;
+  double* d_ztab = nullptr;
+  int* d_zoff = nullptr;
+  int ztab_len = 0;
+  size_t smem_bytes = 0;
+  bool has_defects = false;
+  double* d_partials = nullptr;
+  size_t partial_rows = 0;
+  double* d_central = nullptr;   // n_variants x ART_CENTRAL_LEN scratch (sweep, host run)
+  double* d_moments = nullptr;   // n_variants x ART_MOMENTS_LEN scratch
+  ArtDetector* d_det = nullptr;  // n_variants scratch
+  HostWorkspace ws;
+};
+
+static const int kTargetBlocks = 148 * 8;
+
+static int blocks_per_variant(const ArtChain* c, long long n, int n_variants) {
+  const long long npairs = (n + 1) / 2;
+  long long maxb = (npairs + TPB - 1) / TPB;
+  if (maxb < 1) maxb = 1;
+  long long target = (long long)c->sm_count * 8;
+  long long bpv = (target + n_variants - 1) / n_variants;
+  if (bpv > maxb) bpv = maxb;
+  if (bpv < 1) bpv = 1;
+  return (int)bpv;
+}
+
+static BundleDev to_dev(const ArtBundleView* b) {
+  BundleDev d;
+  if (!b) {
+    d.px = d.py = d.pz = d.ux = d.uy = d.uz = d.path = d.inc = d.inten = nullptr;
+    d.alive = nullptr;
+    return d;
+  }
+  d.px = b->px; d.py = b->py; d.pz = b->pz;
+  d.ux = b->ux; d.uy = b->uy; d.uz = b->uz;
+  d.path = b->path; d.inc = b->incidence; d.inten = b->intensity;
+  d.alive = b->alive;
+  return d;
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static const char* check_columns(const ArtBundleView* b, bool need_pu) {
+  const double* cols[9] = {b->px, b->py, b->pz, b->ux, b->uy, b->uz, b->path, b->incidence, b->intensity};
+  int have = 0;
+  for (int i = 0; i < 6; ++i) have += cols[i] != nullptr;
+  if (need_pu && have != 6) return "the point and vector columns (px..uz) are required";
+  if (have != 0 && have != 6) return "point / vector columns must be given all six or not at all";
+  for (int i = 0; i < 9; ++i)
+    if (cols[i] && !aligned16(cols[i])) return "ray columns must be 16-byte aligned";
+  return nullptr;
+}
+
+// -------------------------------------------------------------------------------------------------
+// plain queries
+// -------------------------------------------------------------------------------------------------
+extern "C" int32_t art_version(void) { return ART_B200_VERSION; }
+extern "C" const char* art_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t art_launch_count(void) { return g_launches.load(); }
+
+extern "C" int32_t art_device_count(int32_t* count) {
+  if (!count) return fail(ART_E_INVALID, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(ART_E_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *count = n;
+  return ART_OK;
+}
+
+extern "C" int32_t art_element_rotation(const double normal[3], const double majoraxis[3], double rot_out[9]) {
+  if (!normal || !majoraxis || !rot_out) return fail(ART_E_INVALID, "NULL argument");
+  element_rotation(normal, majoraxis, rot_out);
+  return ART_OK;
+}
+
+extern "C" int32_t art_detector_make(const double centre[3], const double normal[3], const double refpoint[3],
+                                     double l0, ArtDetector* det_out) {
+  if (!centre || !normal || !refpoint || !det_out) return fail(ART_E_INVALID, "NULL argument");
+  const double nn = std::sqrt(normal[0] * normal[0] + normal[1] * normal[1] + normal[2] * normal[2]);
+  if (!(nn > 0.0)) return fail(ART_E_INVALID, "detector normal must be non-zero");
+  // Detector.normal setter normalises (ART/ModuleDetector.py:62-70)
+  const double nrm[3] = {normal[0] / nn, normal[1] / nn, normal[2] / nn};
+  const double cv[3] = {-nrm[0], -nrm[1], -nrm[2]};
+  detector_fill(centre, nrm, refpoint, cv, l0, 0.0, det_out);
+  return ART_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// chain construction
+// -------------------------------------------------------------------------------------------------
+extern "C" int32_t art_chain_destroy(ArtChain* c) {
+  if (!c) return ART_OK;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_elems);
+  cudaFree(c->d_ztab);
+  cudaFree(c->d_zoff);
+  cudaFree(c->d_partials);
+  cudaFree(c->d_central);
+  cudaFree(c->d_moments);
+  cudaFree(c->d_det);
+  cudaFree(c->ws.cols);
+  cudaFree(c->ws.alive);
+  if (c->ws.pinned) cudaFreeHost(c->ws.pinned);
+  for (auto& e : c->ws.ev)
+    if (e) cudaEventDestroy(e);
+  if (c->ws.stream) cudaStreamDestroy(c->ws.stream);
+  if (c->ws.copy_stream) cudaStreamDestroy(c->ws.copy_stream);
+  delete c;
+  return ART_OK;
+}
+
+template <typename K>
+static cudaError_t allow_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_elements, int32_t n_variants,
+                                    const ArtZernikeDesc* defects, int32_t n_defects, ArtChain** chain_out) {
+  if (!chain_out) return fail(ART_E_INVALID, "chain_out is NULL");
+  *chain_out = nullptr;
+  if (!elements || n_elements < 1 || n_elements > ART_MAX_ELEMENTS)
+    return fail(ART_E_INVALID, "n_elements must be in [1, " + std::to_string(ART_MAX_ELEMENTS) + "]");
+  if (n_variants < 1) return fail(ART_E_INVALID, "n_variants must be >= 1");
+  if (n_defects < 0 || (n_defects > 0 && !defects)) return fail(ART_E_INVALID, "bad defect list");
+
+  std::vector<ElemDev> h((size_t)n_elements * n_variants);
+  bool any_def = false;
+  for (int v = 0; v < n_variants; ++v)
+    for (int k = 0; k < n_elements; ++k) {
+      const ArtElementDesc& d = elements[(size_t)v * n_elements + k];
+      std::string why = lower_element(d, h[(size_t)v * n_elements + k]);
+      if (!why.empty())
+        return fail(ART_E_INVALID, "variant " + std::to_string(v) + " element " + std::to_string(k) + ": " + why);
+      if (d.n_defects > 0) {
+        any_def = true;
+        if (d.first_defect + d.n_defects > n_defects)
+          return fail(ART_E_INVALID, "element " + std::to_string(k) + " refers to defects beyond the list");
+      }
+      if (v > 0) {
+        const ArtElementDesc& d0 = elements[k];
+        if (d0.surface != d.surface || d0.support != d.support || d0.n_defects != d.n_defects ||
+            d0.first_defect != d.first_defect)
+          return fail(ART_E_INVALID, "variants must share surface / support kinds and defects");
+      }
+    }
+  std::vector<double> ztab;
+  std::vector<int> zoff;
+  for (int i = 0; i < n_defects; ++i) {
+    std::vector<double> t;
+    std::string why = build_zernike_table(defects[i], t);
+    if (!why.empty()) return fail(ART_E_INVALID, "defect " + std::to_string(i) + ": " + why);
+    zoff.push_back((int)ztab.size());
+    ztab.insert(ztab.end(), t.begin(), t.end());
+  }
+
+  ArtChain* c = new (std::nothrow) ArtChain();
+  if (!c) return fail(ART_E_NOMEM, "out of host memory");
+  auto bail = [&](int32_t code, const std::string& msg) {
+    art_chain_destroy(c);
+    return fail(code, msg);
+  };
+  cudaError_t e;
+#define CK(call)                                                                  \
+  if ((e = (call)) != cudaSuccess) return bail(ART_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e))
+  CK(cudaGetDevice(&c->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  if (prop.major < 10)
+    return bail(ART_E_UNSUPPORTED, std::string("libart_b200 is built for sm_100a only; device is ") + prop.name);
+  c->sm_count = prop.multiProcessorCount;
+  c->n_elements = n_elements;
+  c->n_variants = n_variants;
+  c->n_defects = n_defects;
+  c->has_defects = any_def;
+  c->ztab_len = (int)ztab.size();
+  c->smem_bytes = sizeof(ElemDev) * ART_MAX_ELEMENTS + sizeof(double) * ztab.size() + sizeof(int) * zoff.size();
+  c->smem_bytes = (c->smem_bytes + 15) & ~size_t(15);
+  if (c->smem_bytes > 200 * 1024) return bail(ART_E_UNSUPPORTED, "Zernike tables exceed 200 KB of shared memory");
+  CK(allow_smem(trace_kernel<true, false>, c->smem_bytes));
+  CK(allow_smem(trace_kernel<false, false>, c->smem_bytes));
+  CK(allow_smem(trace_kernel<true, true>, c->smem_bytes));
+  CK(allow_smem(trace_kernel<false, true>, c->smem_bytes));
+
+  CK(cudaMalloc(&c->d_elems, h.size() * sizeof(ElemDev)));
+  CK(cudaMemcpy(c->d_elems, h.data(), h.size() * sizeof(ElemDev), cudaMemcpyHostToDevice));
+  if (!ztab.empty()) {
+    CK(cudaMalloc(&c->d_ztab, ztab.size() * sizeof(double)));
+    CK(cudaMemcpy(c->d_ztab, ztab.data(), ztab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&c->d_zoff, zoff.size() * sizeof(int)));
+    CK(cudaMemcpy(c->d_zoff, zoff.data(), zoff.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  c->partial_rows = (size_t)c->sm_count * 8 + (size_t)n_variants + 8;
+  CK(cudaMalloc(&c->d_partials, c->partial_rows * PLEN_FUSED * sizeof(double)));
+  CK(cudaMalloc(&c->d_central, (size_t)n_variants * ART_CENTRAL_LEN * sizeof(double)));
+  CK(cudaMalloc(&c->d_moments, (size_t)n_variants * ART_MOMENTS_LEN * sizeof(double)));
+  CK(cudaMalloc(&c->d_det, (size_t)n_variants * sizeof(ArtDetector)));
+#undef CK
+  *chain_out = c;
+  return ART_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// trace launches
+// -------------------------------------------------------------------------------------------------
+static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, const ArtBundleView* in,
+                            const ArtBundleView* out_final, const ArtBundleView* out_history, uint32_t flags,
+                            const ArtDetector* det, double* x_out, double* y_out, double* l_out,
+                            double* central_out, double* moments_out, cudaStream_t st) {
+  if (!c) return fail(ART_E_INVALID, "chain is NULL");
+  if (!in) return fail(ART_E_INVALID, "input bundle is NULL");
+  if (variant_first < 0 || n_variants < 1 || variant_first + n_variants > c->n_variants)
+    return fail(ART_E_INVALID, "variant range outside the chain's variants");
+  if (in->n < 0) return fail(ART_E_INVALID, "negative ray count");
+  if (const char* why = check_columns(in, true)) return fail(ART_E_INVALID, std::string("input bundle: ") + why);
+  if (out_final) {
+    if (const char* why = check_columns(out_final, false))
+      return fail(ART_E_INVALID, std::string("output bundle: ") + why);
+    if (out_final->n != in->n * (int64_t)n_variants)
+      return fail(ART_E_INVALID, "output bundle must hold n_variants * n rays");
+  }
+  if (det && !moments_out) return fail(ART_E_INVALID, "moments_out is NULL");
+
+  TraceArgs a;
+  a.elems = c->d_elems;
+  a.n_elements = c->n_elements;
+  a.variant_first = variant_first;
+  a.ztab = c->d_ztab;
+  a.zoff = c->d_zoff;
+  a.ztab_len = c->ztab_len;
+  a.n_defects = c->n_defects;
+  a.in = to_dev(in);
+  a.out = to_dev(out_final);
+  a.has_out = out_final != nullptr;
+  a.has_hist = out_history != nullptr;
+  bool want_inc = false;
+  for (int k = 0; k < ART_MAX_ELEMENTS; ++k) {
+    if (out_history && k < c->n_elements) {
+      if (const char* why = check_columns(&out_history[k], false))
+        return fail(ART_E_INVALID, std::string("history bundle: ") + why);
+      if (out_history[k].n != in->n * (int64_t)n_variants)
+        return fail(ART_E_INVALID, "history bundles must hold n_variants * n rays");
+      a.hist[k] = to_dev(&out_history[k]);
+      want_inc = want_inc || out_history[k].incidence != nullptr;
+    } else {
+      a.hist[k] = to_dev(nullptr);
+    }
+  }
+  want_inc = want_inc || (out_final && out_final->incidence);
+  if (flags & ART_TRACE_NO_INCIDENCE) want_inc = false;
+  a.n = in->n;
+  a.flags = flags;
+  a.partials = c->d_partials;
+  a.det = det;
+  a.x_out = x_out;
+  a.y_out = y_out;
+  a.l_out = l_out;
+
+  const int bpv = blocks_per_variant(c, in->n, n_variants);
+  if ((size_t)bpv * n_variants > c->partial_rows) return fail(ART_E_INVALID, "internal: partial buffer too small");
+  const dim3 grid(bpv, n_variants);
+  if (det) {
+    if (want_inc) trace_kernel<true, true><<<grid, TPB, c->smem_bytes, st>>>(a);
+    else trace_kernel<false, true><<<grid, TPB, c->smem_bytes, st>>>(a);
+    ART_LAUNCHED();
+    fold_kernel<<<n_variants, TPB, 0, st>>>(c->d_partials, bpv, 1, central_out, moments_out);
+    ART_LAUNCHED();
+  } else {
+    if (want_inc) trace_kernel<true, false><<<grid, TPB, c->smem_bytes, st>>>(a);
+    else trace_kernel<false, false><<<grid, TPB, c->smem_bytes, st>>>(a);
+    ART_LAUNCHED();
+    if (central_out) {
+      fold_kernel<<<n_variants, TPB, 0, st>>>(c->d_partials, bpv, 0, central_out, nullptr);
+      ART_LAUNCHED();
+    }
+  }
+  return ART_OK;
+}
+
+extern "C" int32_t art_trace(ArtChain* chain, int32_t variant_first, int32_t n_variants, const ArtBundleView* in,
+                             const ArtBundleView* out_final, const ArtBundleView* out_history, uint32_t flags,
+                             double* central_out, void* stream) {
+  return launch_trace(chain, variant_first, n_variants, in, out_final, out_history, flags, nullptr, nullptr,
+                      nullptr, nullptr, central_out, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int32_t art_trace_detect(ArtChain* chain, int32_t variant_first, int32_t n_variants,
+                                    const ArtBundleView* in, const ArtBundleView* out_final, uint32_t flags,
+                                    const ArtDetector* det, double* x_out, double* y_out, double* l_out,
+                                    double* central_out, double* moments_out, void* stream) {
+  if (!det) return fail(ART_E_INVALID, "det is NULL");
+  return launch_trace(chain, variant_first, n_variants, in, out_final, nullptr, flags, det, x_out, y_out, l_out,
+                      central_out, moments_out, (cudaStream_t)stream);
+}
+
+extern "C" int32_t art_detector_autoplace(const double* central, double distance, int32_t n_variants,
+                                          ArtDetector* det_out, void* stream) {
+  if (!central || !det_out || n_variants < 1) return fail(ART_E_INVALID, "bad argument");
+  autoplace_kernel<<<(n_variants + 63) / 64, 64, 0, (cudaStream_t)stream>>>(central, distance, n_variants, det_out);
+  ART_LAUNCHED();
+  return ART_OK;
+}
+
+// reduction scratch for calls that come without a chain (stand-alone Detector objects): one
+// lazily grown buffer per device
+static double* g_scratch[64] = {};
+static size_t g_scratch_rows[64] = {};
+static int32_t global_scratch(size_t rows, double** out) {
+  int dev = 0;
+  ART_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(ART_E_UNSUPPORTED, "device index above 63");
+  if (g_scratch_rows[dev] < rows) {
+    if (g_scratch[dev]) ART_CUDA(cudaFree(g_scratch[dev]));
+    g_scratch[dev] = nullptr;
+    g_scratch_rows[dev] = 0;
+    ART_CUDA(cudaMalloc(&g_scratch[dev], rows * PLEN_FUSED * sizeof(double)));
+    g_scratch_rows[dev] = rows;
+  }
+  *out = g_scratch[dev];
+  return ART_OK;
+}
+
+extern "C" int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bundle, int32_t n_variants,
+                                        const ArtDetector* det, double* x_out, double* y_out, double* l_out,
+                                        double* moments_out, void* stream) {
+  if (!bundle || !det || !moments_out || n_variants < 1) return fail(ART_E_INVALID, "bad argument");
+  ArtChain tmp;  // launch-shape defaults when no chain lends its scratch
+  if (!chain) {
+    int dev = 0;
+    ART_CUDA(cudaGetDevice(&dev));
+    int sms = 148;
+    ART_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    tmp.sm_count = sms;
+    tmp.partial_rows = (size_t)sms * 8 + (size_t)n_variants + 8;
+    int32_t rc = global_scratch(tmp.partial_rows, &tmp.d_partials);
+    if (rc) return rc;
+    chain = &tmp;
+  }
+  if (const char* why = check_columns(bundle, true)) return fail(ART_E_INVALID, std::string("bundle: ") + why);
+  if (bundle->n < 0 || bundle->n % n_variants != 0)
+    return fail(ART_E_INVALID, "bundle must hold n_variants * n rays");
+  DetArgs a;
+  a.b = to_dev(bundle);
+  a.n = bundle->n / n_variants;
+  a.det = det;
+  a.x_out = x_out;
+  a.y_out = y_out;
+  a.l_out = l_out;
+  a.partials = chain->d_partials;
+  const int bpv = blocks_per_variant(chain, a.n, n_variants);
+  if ((size_t)bpv * n_variants > chain->partial_rows)
+    return fail(ART_E_INVALID, "n_variants exceeds the chain's variant count");
+  cudaStream_t st = (cudaStream_t)stream;
+  detector_kernel<<<dim3(bpv, n_variants), TPB, 0, st>>>(a);
+  ART_LAUNCHED();
+  fold_kernel<<<n_variants, TPB, 0, st>>>(chain->d_partials, bpv, 2, nullptr, moments_out);
+  ART_LAUNCHED();
+  return ART_OK;
+}
+
+extern "C" int32_t art_sweep(ArtChain* chain, int32_t variant_first, int32_t n_variants, const ArtBundleView* in,
+                             uint32_t flags, double distance, double* central_out, ArtDetector* det_out,
+                             double* moments_out, void* stream) {
+  if (!chain || !det_out || !moments_out) return fail(ART_E_INVALID, "bad argument");
+  double* central = central_out ? central_out : chain->d_central;
+  const uint32_t f = flags | ART_TRACE_NO_INCIDENCE;
+  int32_t rc = launch_trace(chain, variant_first, n_variants, in, nullptr, nullptr, f, nullptr, nullptr, nullptr,
+                            nullptr, central, nullptr, (cudaStream_t)stream);
+  if (rc) return rc;
+  rc = art_detector_autoplace(central, distance, n_variants, det_out, stream);
+  if (rc) return rc;
+  return launch_trace(chain, variant_first, n_variants, in, nullptr, nullptr, f, det_out, nullptr, nullptr, nullptr,
+                      nullptr, moments_out, (cudaStream_t)stream);
+}
+
+extern "C" int32_t art_delays(const double* l, const uint8_t* alive, int64_t n, int32_t n_variants,
+                              const ArtDetector* det, const double* moments, double* delays_out, void* stream) {
+  if (!l || !det || !moments || !delays_out || n < 0 || n_variants < 1) return fail(ART_E_INVALID, "bad argument");
+  long long bx = (n + TPB - 1) / TPB;
+  if (bx < 1) bx = 1;
+  if (bx > 148 * 16) bx = 148 * 16;
+  delays_kernel<<<dim3((unsigned)bx, n_variants), TPB, 0, (cudaStream_t)stream>>>(l, alive, n, det, moments,
+                                                                                 delays_out);
+  ART_LAUNCHED();
+  return ART_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// sources
+// -------------------------------------------------------------------------------------------------
+extern "C" int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t first, int64_t count, double rho,
+                                       const double axis[3], const double origin[3], const ArtBundleView* bundle,
+                                       void* stream) {
+  if (!bundle || !axis || !origin) return fail(ART_E_INVALID, "NULL argument");
+  if (kind != 0 && kind != 1) return fail(ART_E_INVALID, "kind must be 0 (point source) or 1 (plane wave)");
+  if (n_total < 1 || first < 0 || count < 0 || first + count > n_total || bundle->n < count)
+    return fail(ART_E_INVALID, "bad index range");
+  if (const char* why = check_columns(bundle, true)) return fail(ART_E_INVALID, std::string("bundle: ") + why);
+  SourceArgs a;
+  a.kind = kind;
+  a.n_total = n_total;
+  a.first = first;
+  a.count = count;
+  a.rho = rho;
+  const double ez[3] = {0.0, 0.0, 1.0};
+  rotation_from_to(ez, axis, a.rot);  // RotationRayList(RayList, ez, Axis), ART/ModuleSource.py:79,167
+  for (int i = 0; i < 3; ++i) a.origin[i] = origin[i];
+  a.b = to_dev(bundle);
+  long long bx = (count + TPB - 1) / TPB;
+  if (bx < 1) bx = 1;
+  if (bx > 148 * 16) bx = 148 * 16;
+  source_kernel<<<(unsigned)bx, TPB, 0, (cudaStream_t)stream>>>(a);
+  ART_LAUNCHED();
+  return ART_OK;
+}
+
+static const int kIntensityBlocks = 148 * 4;
+static double* g_ext_partials[64] = {};  // per device scratch of kIntensityBlocks x 2 doubles
+
+extern "C" int32_t art_source_extents(const ArtBundleView* bundle, const double axis[3], double* extents_out,
+                                      void* stream) {
+  if (!bundle || !axis || !extents_out) return fail(ART_E_INVALID, "NULL argument");
+  if (const char* why = check_columns(bundle, true)) return fail(ART_E_INVALID, std::string("bundle: ") + why);
+  int dev = 0;
+  ART_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(ART_E_UNSUPPORTED, "device index above 63");
+  if (!g_ext_partials[dev]) ART_CUDA(cudaMalloc(&g_ext_partials[dev], sizeof(double) * 2 * kIntensityBlocks));
+  IntensityArgs a;
+  a.b = to_dev(bundle);
+  a.n = bundle->n;
+  for (int i = 0; i < 3; ++i) a.axis[i] = axis[i];
+  a.pass = 0;
+  a.mode = 0;
+  a.scale = 1.0;
+  a.lnf = 0.0;
+  a.partials = g_ext_partials[dev];
+  cudaStream_t st = (cudaStream_t)stream;
+  intensity_kernel<<<kIntensityBlocks, TPB, 0, st>>>(a);
+  ART_LAUNCHED();
+  extents_fold_kernel<<<1, 32, 0, st>>>(g_ext_partials[dev], kIntensityBlocks, extents_out);
+  ART_LAUNCHED();
+  return ART_OK;
+}
+
+extern "C" int32_t art_source_intensity(const ArtBundleView* bundle, const double axis[3], int32_t mode,
+                                        double scale, double fraction, void* stream) {
+  if (!bundle || !axis) return fail(ART_E_INVALID, "NULL argument");
+  if (!bundle->intensity) return fail(ART_E_INVALID, "bundle has no intensity column");
+  if (const char* why = check_columns(bundle, true)) return fail(ART_E_INVALID, std::string("bundle: ") + why);
+  if (mode != 0 && mode != 1) return fail(ART_E_INVALID, "mode must be 0 or 1");
+  if (!(fraction > 0.0 && fraction < 1.0)) fraction = 0.1353352832366127;  // 1/e^2, ART/ModuleSource.py:233-238
+  IntensityArgs a;
+  a.b = to_dev(bundle);
+  a.n = bundle->n;
+  for (int i = 0; i < 3; ++i) a.axis[i] = axis[i];
+  a.pass = 1;
+  a.mode = mode;
+  a.scale = scale;
+  a.lnf = -0.5 * std::log(fraction);
+  a.partials = nullptr;
+  intensity_kernel<<<kIntensityBlocks, TPB, 0, (cudaStream_t)stream>>>(a);
+  ART_LAUNCHED();
+  return ART_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// host-buffer end-to-end entry point
+// -------------------------------------------------------------------------------------------------
+static int32_t ensure_workspace(ArtChain* c, size_t n) {
+  HostWorkspace& w = c->ws;
+  if (!w.stream) {
+    ART_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    ART_CUDA(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
+    for (auto& e : w.ev) ART_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ART_CUDA(cudaMallocHost(&w.pinned, sizeof(double) * (ART_MOMENTS_LEN + ART_CENTRAL_LEN) + sizeof(ArtDetector)));
+  }
+  if (n > w.cap_n) {
+    cudaFree(w.cols);
+    cudaFree(w.alive);
+    w.cols = nullptr;
+    w.alive = nullptr;
+    w.cap_n = 0;
+    const size_t cap = (n + 1023) & ~size_t(1023);
+    ART_CUDA(cudaMalloc(&w.cols, sizeof(double) * 15 * cap));
+    ART_CUDA(cudaMalloc(&w.alive, cap));
+    w.cap_n = cap;
+  }
+  return ART_OK;
+}
+
+extern "C" int32_t art_run_host(ArtChain* c, const ArtBundleView* in_host, const ArtBundleView* out_final_host,
+                                uint32_t flags, double distance, const ArtDetector* manual_det,
+                                double* moments_host, double* central_host, ArtDetector* det_host) {
+  if (!c || !in_host) return fail(ART_E_INVALID, "NULL argument");
+  if (in_host->n < 0) return fail(ART_E_INVALID, "negative ray count");
+  if (!in_host->px || !in_host->py || !in_host->pz || !in_host->ux || !in_host->uy || !in_host->uz)
+    return fail(ART_E_INVALID, "the point and vector columns (px..uz) are required");
+  if (out_final_host && out_final_host->n != in_host->n)
+    return fail(ART_E_INVALID, "output bundle must hold n rays");
+  ART_CUDA(cudaSetDevice(c->device));
+  const size_t n = (size_t)in_host->n;
+  int32_t rc = ensure_workspace(c, n);
+  if (rc) return rc;
+  HostWorkspace& w = c->ws;
+  const size_t cap = w.cap_n;
+  auto col = [&](int j) { return w.cols + (size_t)j * cap; };
+  cudaStream_t st = w.stream;
+
+  ArtBundleView din = {};
+  din.n = (int64_t)n;
+  const double* src[7] = {in_host->px, in_host->py, in_host->pz, in_host->ux,
+                          in_host->uy, in_host->uz, in_host->intensity};
+  double** dst[7] = {&din.px, &din.py, &din.pz, &din.ux, &din.uy, &din.uz, &din.intensity};
+  for (int j = 0; j < 7; ++j) {
+    if (!src[j]) continue;
+    *dst[j] = col(j);
+    if (n) ART_CUDA(cudaMemcpyAsync(col(j), src[j], sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  }
+  if (in_host->path || in_host->alive)
+    return fail(ART_E_UNSUPPORTED, "art_run_host starts from a fresh source bundle (no path / alive columns)");
+
+  ArtBundleView dout = {};
+  dout.n = (int64_t)n;
+  dout.px = col(7); dout.py = col(8); dout.pz = col(9);
+  dout.ux = col(10); dout.uy = col(11); dout.uz = col(12);
+  dout.path = col(13);
+  const bool want_inc = out_final_host && out_final_host->incidence && !(flags & ART_TRACE_NO_INCIDENCE);
+  dout.incidence = want_inc ? col(14) : nullptr;
+  dout.alive = w.alive;
+  dout.intensity = din.intensity;
+
+  rc = launch_trace(c, 0, 1, &din, &dout, nullptr, flags, nullptr, nullptr, nullptr, nullptr, c->d_central,
+                    nullptr, st);
+  if (rc) return rc;
+  if (manual_det) {
+    ART_CUDA(cudaMemcpyAsync(c->d_det, manual_det, sizeof(ArtDetector), cudaMemcpyHostToDevice, st));
+  } else {
+    rc = art_detector_autoplace(c->d_central, distance, 1, c->d_det, st);
+    if (rc) return rc;
+  }
+  rc = art_detector_moments(c, &dout, 1, c->d_det, nullptr, nullptr, nullptr, c->d_moments, st);
+  if (rc) return rc;
+
+  double* pm = w.pinned;
+  double* pc = pm + ART_MOMENTS_LEN;
+  ArtDetector* pd = reinterpret_cast<ArtDetector*>(pc + ART_CENTRAL_LEN);
+  ART_CUDA(cudaMemcpyAsync(pm, c->d_moments, sizeof(double) * ART_MOMENTS_LEN, cudaMemcpyDeviceToHost, st));
+  ART_CUDA(cudaMemcpyAsync(pc, c->d_central, sizeof(double) * ART_CENTRAL_LEN, cudaMemcpyDeviceToHost, st));
+  ART_CUDA(cudaMemcpyAsync(pd, c->d_det, sizeof(ArtDetector), cudaMemcpyDeviceToHost, st));
+  if (out_final_host && n) {
+    double* hdst[8] = {out_final_host->px, out_final_host->py, out_final_host->pz, out_final_host->ux,
+                       out_final_host->uy, out_final_host->uz, out_final_host->path,
+                       want_inc ? out_final_host->incidence : nullptr};
+    for (int j = 0; j < 8; ++j)
+      if (hdst[j]) ART_CUDA(cudaMemcpyAsync(hdst[j], col(7 + j), sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (out_final_host->alive)
+      ART_CUDA(cudaMemcpyAsync(out_final_host->alive, w.alive, n, cudaMemcpyDeviceToHost, st));
+  }
+  ART_CUDA(cudaStreamSynchronize(st));
+  if (moments_host)
+    for (int j = 0; j < ART_MOMENTS_LEN; ++j) moments_host[j] = pm[j];
+  if (central_host)
+    for (int j = 0; j < ART_CENTRAL_LEN; ++j) central_host[j] = pc[j];
+  if (det_host) *det_host = *pd;
+  return ART_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// probes
+// -------------------------------------------------------------------------------------------------
+extern "C" int32_t art_probe_fp64(double* flops_per_second) {
+  if (!flops_per_second) return fail(ART_E_INVALID, "NULL argument");
+  int dev = 0;
+  ART_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  ART_CUDA(cudaGetDeviceProperties(&prop, dev));
+  double* d = nullptr;
+  ART_CUDA(cudaMalloc(&d, 64));
+  cudaEvent_t e0, e1;
+  ART_CUDA(cudaEventCreate(&e0));
+  ART_CUDA(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    ART_CUDA(cudaEventRecord(e0));
+    probe_fp64_kernel<<<blocks, TPB>>>(d, iters, 1.0 + rep);
+    ART_LAUNCHED();
+    ART_CUDA(cudaEventRecord(e1));
+    ART_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    ART_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * TPB / (ms * 1e-3);
+    if (rep > 0 && fl > best) best = fl;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *flops_per_second = best;
+  return ART_OK;
+}
+
+extern "C" int32_t art_probe_hbm(double* bytes_per_second) {
+  if (!bytes_per_second) return fail(ART_E_INVALID, "NULL argument");
+  const long long n2 = 1ll << 26;  // 64 Mi double2 = 1 GiB per buffer
+  double2 *a = nullptr, *b = nullptr;
+  ART_CUDA(cudaMalloc(&a, sizeof(double2) * n2));
+  ART_CUDA(cudaMalloc(&b, sizeof(double2) * n2));
+  ART_CUDA(cudaMemset(a, 0, sizeof(double2) * n2));
+  cudaEvent_t e0, e1;
+  ART_CUDA(cudaEventCreate(&e0));
+  ART_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    ART_CUDA(cudaEventRecord(e0));
+    probe_copy_kernel<<<148 * 16, TPB>>>(a, b, n2);
+    ART_LAUNCHED();
+    ART_CUDA(cudaEventRecord(e1));
+    ART_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    ART_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double bw = 2.0 * sizeof(double2) * (double)n2 / (ms * 1e-3);
+    if (rep > 0 && bw > best) best = bw;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(a);
+  cudaFree(b);
+  *bytes_per_second = best;
+  return ART_OK;
+}

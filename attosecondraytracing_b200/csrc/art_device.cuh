@@ -201,26 +201,29 @@ ART_HD TorEval tor_eval(const Ray& r, double t, double R, double r2) {
   return e;
 }
 
+// Newton stops once the NEXT correction would be below rounding level: F is convex with
+// F'' <= 2 |u|^2 = 2, so the step after dt is at most dt^2 / |F'|; at the noise floor of F
+// (~ eps r^2) dt itself is ~1e-13 mm and the test holds as well.
 // largest zero of F, Newton from the right of it; NaN if the line misses the solid
-ART_HD double tor_root_right(const Ray& r, double t, double R, double r2) {
+ART_HD double tor_root_right(const Ray& r, double t, double R, double r2, double scale) {
   for (int it = 0; it < 64; ++it) {
     TorEval e = tor_eval(r, t, R, r2);
     if (!(e.dF > 0.0)) return ART_NAN;  // walked past the minimum of F without meeting a zero
-    double dt = e.F / e.dF;
+    const double dt = e.F / e.dF;
     t -= dt;
-    if (it > 0 && dt <= 4e-16 * fabs(t)) return t;  // monotone until rounding level
+    if (dt * dt <= 2e-16 * (fabs(t) + scale) * e.dF) return t;
   }
   return ART_NAN;
 }
 // smallest zero of F, Newton from the left of it (start t = 0 with F > 0, dF < 0)
-ART_HD double tor_root_left(const Ray& r, double R, double r2) {
+ART_HD double tor_root_left(const Ray& r, double R, double r2, double scale) {
   double t = 0.0;
   for (int it = 0; it < 64; ++it) {
     TorEval e = tor_eval(r, t, R, r2);
     if (!(e.dF < 0.0)) return ART_NAN;
-    double dt = e.F / e.dF;
+    const double dt = e.F / e.dF;
     t -= dt;
-    if (it > 0 && dt >= -4e-16 * fabs(t)) return t;
+    if (dt * dt <= 2e-16 * (fabs(t) + scale) * -e.dF) return t;
   }
   return ART_NAN;
 }
@@ -235,12 +238,12 @@ ART_HD double intersect_toroid(const ElemDev& E, const Ray& r) {
     double tc = -(r.px * r.ux + r.py * r.uy + r.pz * r.uz);
     t0 = tc + 1.0009765625 * (R + rr);
   }
-  double tb = tor_root_right(r, t0, R, r2);
+  double tb = tor_root_right(r, t0, R, r2, rr);
   double ta = ART_NAN;
   TorEval o = tor_eval(r, 0.0, R, r2);
   if (o.F > 0.0) {
     if (!(o.dF < 0.0)) return ART_NAN;  // moving away from the solid: no forward root
-    ta = tor_root_left(r, R, r2);
+    ta = tor_root_left(r, R, r2, rr);
   }
   return pick_candidate<true>(E, r, ta, tb, -R);
 }

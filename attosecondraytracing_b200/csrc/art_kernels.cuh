@@ -1,0 +1,589 @@
+// art_kernels.cuh -- the kernels of libart_b200 (sm_100a): fused chain trace (K1), detector
+// response + moments (K2), fixed-order reductions, detector autoplace, source bundles (K0),
+// and the two roofline probes.  Per-ray optics live in art_device.cuh.
+#pragma once
+#include "art_device.cuh"
+
+namespace art {
+
+constexpr int TPB = 256;       // threads per block
+constexpr int RPT = 2;         // rays per thread: adjacent rays -> 128-bit column accesses
+constexpr int NWARP = TPB / 32;
+
+// partial-row layout written by the trace / detector kernels, one row per (variant, block)
+constexpr int PL_CENTRAL = 0;                      // ART_CENTRAL_LEN sums
+constexpr int PL_MOMENTS = ART_CENTRAL_LEN;        // ART_MOMENTS_LEN entries (sum / min / max)
+constexpr int PLEN_TRACE = ART_CENTRAL_LEN;
+constexpr int PLEN_FUSED = ART_CENTRAL_LEN + ART_MOMENTS_LEN;
+constexpr int PLEN_DET = ART_MOMENTS_LEN;
+
+// reduction operator of moments entry j: 0 sum, 1 min, 2 max
+__host__ __device__ inline int moment_op(int j) {
+  if (j < ART_M_XMIN) return 0;
+  if (j == ART_M_XMIN || j == ART_M_YMIN || j == ART_M_DMIN) return 1;
+  if (j <= ART_M_TMAX) return 2;
+  return 0;
+}
+
+struct TraceArgs {
+  const ElemDev* elems;  // [n_variants_total][n_elements]
+  int n_elements;
+  int variant_first;
+  const double* ztab;    // concatenated Zernike tables
+  const int* zoff;       // offset (in doubles) of each defect's table
+  int ztab_len;          // doubles
+  int n_defects;
+  BundleDev in;
+  BundleDev out;         // final bundle (rows v*n + i), pointers may be null
+  BundleDev hist[ART_MAX_ELEMENTS];
+  int has_out, has_hist;
+  long long n;           // rays per variant
+  unsigned flags;
+  double* partials;      // [variant][block][plen]
+  const ArtDetector* det;  // fused detector (device, per variant) or null
+  double *x_out, *y_out, *l_out;
+};
+
+// ---------------------------------------------------------------------------------------------
+// 128-bit column access for a pair of adjacent rays (i even); scalar at the ragged end or when the
+// variant row offset breaks the 16-byte alignment.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_pair(const double* __restrict__ col, long long i, bool two, double& a,
+                                          double& b) {
+  if (two) {
+    const double2 v = *reinterpret_cast<const double2*>(col + i);
+    a = v.x;
+    b = v.y;
+  } else {
+    a = col[i];
+    b = 0.0;
+  }
+}
+__device__ __forceinline__ void store_pair(double* __restrict__ col, long long i, bool vec, bool w0, bool w1,
+                                           double a, double b) {
+  if (vec && w0 && w1) {
+    __stcs(reinterpret_cast<double2*>(col + i), make_double2(a, b));
+  } else {
+    if (w0) __stcs(col + i, a);
+    if (w1) __stcs(col + i + 1, b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// block reduction of NV per-thread values with a per-entry operator; thread 0 writes the row.
+// Fixed shuffle tree + fixed warp order => bit-reproducible for a given launch shape.
+// ---------------------------------------------------------------------------------------------
+template <int OP>
+__device__ __forceinline__ double red_op(double a, double b) {
+  if (OP == 0) return a + b;
+  if (OP == 1) return fmin(a, b);
+  return fmax(a, b);
+}
+__device__ __forceinline__ double red_any(int op, double a, double b) {
+  return op == 0 ? a + b : (op == 1 ? fmin(a, b) : fmax(a, b));
+}
+
+template <int NV, typename OPF>
+__device__ __forceinline__ void block_reduce_row(double (&v)[NV], OPF opf, double* smem /* NWARP*NV */,
+                                                 double* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int op = opf(j);
+    double x = v[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = red_any(op, x, __shfl_xor_sync(0xffffffffu, x, o));
+    if (lane == 0) smem[warp * NV + j] = x;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < NV; j += TPB) {
+    const int op = opf(j);
+    double x = smem[j];
+    for (int w = 1; w < NWARP; ++w) x = red_any(op, x, smem[w * NV + j]);
+    out[j] = x;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// detector response of one ray: Detector.get_PointList3D / get_PointList2D / get_Delays,
+// ART/ModuleDetector.py:191-279 + IntersectionLinePlane ART/ModuleGeometry.py:48-57.
+//   t = n.(C - P) / (u.n) (sign unchecked); hit = P + u t; (x, y) = first two rows of rot (hit - C);
+//   L = |P - hit| + sum(path) = |t| + path  (|u| = 1).
+// ---------------------------------------------------------------------------------------------
+struct DetHit {
+  double x, y, L, tan2;
+};
+__device__ __forceinline__ DetHit detector_ray(const ArtDetector& D, const Ray& r) {
+  const double nx = D.normal[0], ny = D.normal[1], nz = D.normal[2];
+  const double num = fma(nx, D.centre[0] - r.px, fma(ny, D.centre[1] - r.py, nz * (D.centre[2] - r.pz)));
+  const double den = fma(nx, r.ux, fma(ny, r.uy, nz * r.uz));
+  const double t = num / den;
+  const double hx = fma(t, r.ux, r.px) - D.centre[0];
+  const double hy = fma(t, r.uy, r.py) - D.centre[1];
+  const double hz = fma(t, r.uz, r.pz) - D.centre[2];
+  DetHit h;
+  h.x = fma(D.rot[0], hx, fma(D.rot[1], hy, D.rot[2] * hz));
+  h.y = fma(D.rot[3], hx, fma(D.rot[4], hy, D.rot[5] * hz));
+  h.L = fabs(t) + r.path;
+  // tan^2(angle(u, central vector)/2) from Kahan's form (ART/ModuleGeometry.py:40-44) with unit vectors
+  const double dx = r.ux - D.cvec[0], dy = r.uy - D.cvec[1], dz = r.uz - D.cvec[2];
+  const double sx = r.ux + D.cvec[0], sy = r.uy + D.cvec[1], sz = r.uz + D.cvec[2];
+  h.tan2 = fma(dx, dx, fma(dy, dy, dz * dz)) / fma(sx, sx, fma(sy, sy, sz * sz));
+  return h;
+}
+
+__device__ __forceinline__ void moments_init(double (&m)[ART_MOMENTS_LEN]) {
+#pragma unroll
+  for (int j = 0; j < ART_MOMENTS_LEN; ++j) {
+    const int op = moment_op(j);
+    m[j] = op == 0 ? 0.0 : (op == 1 ? CUDART_INF : -CUDART_INF);
+  }
+}
+__device__ __forceinline__ void moments_add(double (&m)[ART_MOMENTS_LEN], const DetHit& h, double l0, double w) {
+  const double d = h.L - l0;
+  m[ART_M_N] += 1.0;
+  m[ART_M_SX] += h.x;
+  m[ART_M_SY] += h.y;
+  m[ART_M_SXX] = fma(h.x, h.x, m[ART_M_SXX]);
+  m[ART_M_SYY] = fma(h.y, h.y, m[ART_M_SYY]);
+  m[ART_M_SD] += d;
+  m[ART_M_SDD] = fma(d, d, m[ART_M_SDD]);
+  m[ART_M_SW] += w;
+  const double wx = w * h.x, wy = w * h.y, wd = w * d;
+  m[ART_M_SWX] += wx;
+  m[ART_M_SWY] += wy;
+  m[ART_M_SWXX] = fma(wx, h.x, m[ART_M_SWXX]);
+  m[ART_M_SWYY] = fma(wy, h.y, m[ART_M_SWYY]);
+  m[ART_M_SWD] += wd;
+  m[ART_M_SWDD] = fma(wd, d, m[ART_M_SWDD]);
+  m[ART_M_XMIN] = fmin(m[ART_M_XMIN], h.x);
+  m[ART_M_XMAX] = fmax(m[ART_M_XMAX], h.x);
+  m[ART_M_YMIN] = fmin(m[ART_M_YMIN], h.y);
+  m[ART_M_YMAX] = fmax(m[ART_M_YMAX], h.y);
+  m[ART_M_DMIN] = fmin(m[ART_M_DMIN], d);
+  m[ART_M_DMAX] = fmax(m[ART_M_DMAX], d);
+  m[ART_M_TMAX] = fmax(m[ART_M_TMAX], h.tan2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: the fused chain trace.  RayTracingCalculation, ART/ModuleProcessing.py:250-313, for
+// gridDim.y variants of the chain over the same source bundle.  One thread owns RPT adjacent rays
+// and walks every element with the ray in registers; the element table (and the Zernike tables)
+// of the block's variant sit in shared memory and are read at warp-uniform addresses.
+//   WANT_INC  compute Ray.incidence
+//   WITH_DET  also evaluate the detector of this variant and accumulate its moments (K2 fused)
+// ---------------------------------------------------------------------------------------------
+template <bool WANT_INC, bool WITH_DET>
+__global__ void __launch_bounds__(TPB, 2) trace_kernel(const TraceArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ElemDev* sE = reinterpret_cast<ElemDev*>(smem_raw);
+  double* sZ = reinterpret_cast<double*>(smem_raw + sizeof(ElemDev) * ART_MAX_ELEMENTS);
+  int* sZoff = reinterpret_cast<int*>(sZ + a.ztab_len);
+  constexpr int PLEN = WITH_DET ? PLEN_FUSED : PLEN_TRACE;
+  __shared__ double sRed[NWARP * PLEN];
+  __shared__ ArtDetector sDet;
+
+  const int v = blockIdx.y;
+  {
+    const double* src = reinterpret_cast<const double*>(a.elems + (size_t)(a.variant_first + v) * a.n_elements);
+    double* dst = reinterpret_cast<double*>(sE);
+    const int nd = a.n_elements * (int)(sizeof(ElemDev) / sizeof(double));
+    for (int i = threadIdx.x; i < nd; i += TPB) dst[i] = src[i];
+    for (int i = threadIdx.x; i < a.ztab_len; i += TPB) sZ[i] = a.ztab[i];
+    for (int i = threadIdx.x; i < a.n_defects; i += TPB) sZoff[i] = a.zoff[i];
+    if (WITH_DET) {
+      const double* ds = reinterpret_cast<const double*>(a.det + v);
+      double* dd = reinterpret_cast<double*>(&sDet);
+      for (int i = threadIdx.x; i < (int)(sizeof(ArtDetector) / sizeof(double)); i += TPB) dd[i] = ds[i];
+    }
+  }
+  __syncthreads();
+
+  const bool ignore_defects = (a.flags & ART_TRACE_IGNORE_DEFECTS) != 0;
+  const long long n = a.n;
+  const long long row = (long long)v * n;     // first output row of this variant
+  const bool out_vec = (row & 1) == 0;
+  const long long npairs = (n + 1) >> 1;
+
+  double c[ART_CENTRAL_LEN];
+#pragma unroll
+  for (int j = 0; j < ART_CENTRAL_LEN; ++j) c[j] = 0.0;
+  double m[WITH_DET ? ART_MOMENTS_LEN : 1];
+  if constexpr (WITH_DET) moments_init(m);
+
+  for (long long pair = (long long)blockIdx.x * TPB + threadIdx.x; pair < npairs;
+       pair += (long long)gridDim.x * TPB) {
+    const long long i = pair << 1;
+    const bool two = i + 1 < n;
+    Ray r[RPT];
+    double w[RPT];
+    load_pair(a.in.px, i, two, r[0].px, r[1].px);
+    load_pair(a.in.py, i, two, r[0].py, r[1].py);
+    load_pair(a.in.pz, i, two, r[0].pz, r[1].pz);
+    load_pair(a.in.ux, i, two, r[0].ux, r[1].ux);
+    load_pair(a.in.uy, i, two, r[0].uy, r[1].uy);
+    load_pair(a.in.uz, i, two, r[0].uz, r[1].uz);
+    if (a.in.path) load_pair(a.in.path, i, two, r[0].path, r[1].path);
+    else r[0].path = r[1].path = 0.0;
+    if (a.in.inten) load_pair(a.in.inten, i, two, w[0], w[1]);
+    else w[0] = w[1] = 1.0;
+    r[0].alive = true;
+    r[1].alive = two;
+    if (a.in.alive) {
+      r[0].alive = a.in.alive[i] != 0;
+      if (two) r[1].alive = a.in.alive[i + 1] != 0;
+    }
+    r[0].inc = r[1].inc = ART_NAN;
+#pragma unroll
+    for (int q = 0; q < RPT; ++q)
+      if (r[q].alive) c[ART_C_SW_IN] += w[q];
+
+    for (int k = 0; k < a.n_elements; ++k) {
+#pragma unroll
+      for (int q = 0; q < RPT; ++q)
+        if (r[q].alive) apply_element<WANT_INC>(sE[k], r[q], sZ, sZoff, ignore_defects);
+      if (a.has_hist) {
+        const BundleDev& H = a.hist[k];
+        const bool w0 = r[0].alive, w1 = r[1].alive;
+        if (H.px) {
+          store_pair(H.px, row + i, out_vec, w0, w1, r[0].px, r[1].px);
+          store_pair(H.py, row + i, out_vec, w0, w1, r[0].py, r[1].py);
+          store_pair(H.pz, row + i, out_vec, w0, w1, r[0].pz, r[1].pz);
+          store_pair(H.ux, row + i, out_vec, w0, w1, r[0].ux, r[1].ux);
+          store_pair(H.uy, row + i, out_vec, w0, w1, r[0].uy, r[1].uy);
+          store_pair(H.uz, row + i, out_vec, w0, w1, r[0].uz, r[1].uz);
+        }
+        if (H.path) store_pair(H.path, row + i, out_vec, w0, w1, r[0].path, r[1].path);
+        if (WANT_INC && H.inc) store_pair(H.inc, row + i, out_vec, w0, w1, r[0].inc, r[1].inc);
+        if (H.alive) {
+          H.alive[row + i] = w0;
+          if (two) H.alive[row + i + 1] = w1;
+        }
+      }
+    }
+
+    const bool w0 = r[0].alive, w1 = r[1].alive;
+    if (a.has_out) {
+      const BundleDev& O = a.out;
+      if (O.px) {
+        store_pair(O.px, row + i, out_vec, w0, w1, r[0].px, r[1].px);
+        store_pair(O.py, row + i, out_vec, w0, w1, r[0].py, r[1].py);
+        store_pair(O.pz, row + i, out_vec, w0, w1, r[0].pz, r[1].pz);
+        store_pair(O.ux, row + i, out_vec, w0, w1, r[0].ux, r[1].ux);
+        store_pair(O.uy, row + i, out_vec, w0, w1, r[0].uy, r[1].uy);
+        store_pair(O.uz, row + i, out_vec, w0, w1, r[0].uz, r[1].uz);
+      }
+      if (O.path) store_pair(O.path, row + i, out_vec, w0, w1, r[0].path, r[1].path);
+      if (WANT_INC && O.inc) store_pair(O.inc, row + i, out_vec, w0, w1, r[0].inc, r[1].inc);
+      if (O.alive) {
+        if (two && out_vec) {
+          *reinterpret_cast<uchar2*>(O.alive + row + i) = make_uchar2(w0, w1);
+        } else {
+          O.alive[row + i] = w0;
+          if (two) O.alive[row + i + 1] = w1;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      if (!r[q].alive) continue;
+      c[ART_C_SUX] += r[q].ux; c[ART_C_SUY] += r[q].uy; c[ART_C_SUZ] += r[q].uz;
+      c[ART_C_SPX] += r[q].px; c[ART_C_SPY] += r[q].py; c[ART_C_SPZ] += r[q].pz;
+      c[ART_C_SPATH] += r[q].path;
+      c[ART_C_N] += 1.0;
+      c[ART_C_SW_OUT] += w[q];
+      if constexpr (WITH_DET) {
+        const DetHit h = detector_ray(sDet, r[q]);
+        moments_add(m, h, sDet.l0, w[q]);
+        if (a.x_out) a.x_out[row + i + q] = h.x;
+        if (a.y_out) a.y_out[row + i + q] = h.y;
+        if (a.l_out) a.l_out[row + i + q] = h.L;
+      }
+    }
+  }
+
+  double* prow = a.partials + ((size_t)v * gridDim.x + blockIdx.x) * PLEN;
+  if constexpr (WITH_DET) {
+    double all[PLEN_FUSED];
+#pragma unroll
+    for (int j = 0; j < ART_CENTRAL_LEN; ++j) all[j] = c[j];
+#pragma unroll
+    for (int j = 0; j < ART_MOMENTS_LEN; ++j) all[ART_CENTRAL_LEN + j] = m[j];
+    block_reduce_row<PLEN_FUSED>(all, [](int j) { return j < ART_CENTRAL_LEN ? 0 : moment_op(j - ART_CENTRAL_LEN); },
+                                 sRed, prow);
+  } else {
+    block_reduce_row<PLEN_TRACE>(c, [](int) { return 0; }, sRed, prow);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 (stand-alone): detector response + moments of a stored bundle.
+// ---------------------------------------------------------------------------------------------
+struct DetArgs {
+  BundleDev b;       // n_variants x n rows; inten has n entries shared by all variants
+  long long n;
+  const ArtDetector* det;
+  double *x_out, *y_out, *l_out;
+  double* partials;  // [variant][block][PLEN_DET]
+};
+
+__global__ void __launch_bounds__(TPB, 2) detector_kernel(const DetArgs a) {
+  __shared__ double sRed[NWARP * PLEN_DET];
+  __shared__ ArtDetector sDet;
+  const int v = blockIdx.y;
+  {
+    const double* ds = reinterpret_cast<const double*>(a.det + v);
+    double* dd = reinterpret_cast<double*>(&sDet);
+    for (int i = threadIdx.x; i < (int)(sizeof(ArtDetector) / sizeof(double)); i += TPB) dd[i] = ds[i];
+  }
+  __syncthreads();
+  const long long n = a.n, row = (long long)v * n;
+  const bool vec = (row & 1) == 0;
+  const long long npairs = (n + 1) >> 1;
+  double m[ART_MOMENTS_LEN];
+  moments_init(m);
+  for (long long pair = (long long)blockIdx.x * TPB + threadIdx.x; pair < npairs;
+       pair += (long long)gridDim.x * TPB) {
+    const long long i = pair << 1;
+    const bool two = i + 1 < n;
+    bool al[RPT] = {true, two};
+    if (a.b.alive) {
+      al[0] = a.b.alive[row + i] != 0;
+      al[1] = two && a.b.alive[row + i + 1] != 0;
+    }
+    if (!al[0] && !al[1]) continue;
+    Ray r[RPT];
+    double w[RPT];
+    const bool v2 = two && vec;
+    load_pair(a.b.px + row, i, v2, r[0].px, r[1].px);
+    load_pair(a.b.py + row, i, v2, r[0].py, r[1].py);
+    load_pair(a.b.pz + row, i, v2, r[0].pz, r[1].pz);
+    load_pair(a.b.ux + row, i, v2, r[0].ux, r[1].ux);
+    load_pair(a.b.uy + row, i, v2, r[0].uy, r[1].uy);
+    load_pair(a.b.uz + row, i, v2, r[0].uz, r[1].uz);
+    if (a.b.path) load_pair(a.b.path + row, i, v2, r[0].path, r[1].path);
+    else r[0].path = r[1].path = 0.0;
+    if (two && !vec) {
+      r[1].px = a.b.px[row + i + 1]; r[1].py = a.b.py[row + i + 1]; r[1].pz = a.b.pz[row + i + 1];
+      r[1].ux = a.b.ux[row + i + 1]; r[1].uy = a.b.uy[row + i + 1]; r[1].uz = a.b.uz[row + i + 1];
+      if (a.b.path) r[1].path = a.b.path[row + i + 1];
+    }
+    if (a.b.inten) load_pair(a.b.inten, i, two, w[0], w[1]);
+    else w[0] = w[1] = 1.0;
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      if (!al[q]) continue;
+      const DetHit h = detector_ray(sDet, r[q]);
+      moments_add(m, h, sDet.l0, w[q]);
+      if (a.x_out) a.x_out[row + i + q] = h.x;
+      if (a.y_out) a.y_out[row + i + q] = h.y;
+      if (a.l_out) a.l_out[row + i + q] = h.L;
+    }
+  }
+  block_reduce_row<PLEN_DET>(m, [](int j) { return moment_op(j); }, sRed,
+                             a.partials + ((size_t)v * gridDim.x + blockIdx.x) * PLEN_DET);
+}
+
+// ---------------------------------------------------------------------------------------------
+// second reduction stage: one block per variant folds that variant's block rows in a fixed order.
+//   mode 0: row = central            -> central_out
+//   mode 1: row = central | moments  -> central_out (nullable), moments_out
+//   mode 2: row = moments            -> moments_out
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) fold_kernel(const double* __restrict__ partials, int nblocks, int mode,
+                                                   double* __restrict__ central_out,
+                                                   double* __restrict__ moments_out) {
+  __shared__ double sRed[NWARP * PLEN_FUSED];
+  const int v = blockIdx.x;
+  const int plen = mode == 0 ? PLEN_TRACE : (mode == 1 ? PLEN_FUSED : PLEN_DET);
+  const int moff = mode == 1 ? ART_CENTRAL_LEN : 0;  // where the moments start in a row
+  const double* base = partials + (size_t)v * nblocks * plen;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = 0; j < plen; ++j) {
+    const int op = (mode == 0 || (mode == 1 && j < ART_CENTRAL_LEN)) ? 0 : moment_op(j - moff);
+    double x = op == 0 ? 0.0 : (op == 1 ? CUDART_INF : -CUDART_INF);
+    for (int b = threadIdx.x; b < nblocks; b += TPB) x = red_any(op, x, base[(size_t)b * plen + j]);
+    for (int o = 16; o > 0; o >>= 1) x = red_any(op, x, __shfl_xor_sync(0xffffffffu, x, o));
+    if (lane == 0) sRed[warp * plen + j] = x;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < plen; j += TPB) {
+    const int op = (mode == 0 || (mode == 1 && j < ART_CENTRAL_LEN)) ? 0 : moment_op(j - moff);
+    double x = sRed[j];
+    for (int w = 1; w < NWARP; ++w) x = red_any(op, x, sRed[w * plen + j]);
+    if (mode == 0) {
+      central_out[(size_t)v * ART_CENTRAL_LEN + j] = x;
+    } else if (mode == 1) {
+      if (j < ART_CENTRAL_LEN) {
+        if (central_out) central_out[(size_t)v * ART_CENTRAL_LEN + j] = x;
+      } else {
+        moments_out[(size_t)v * ART_MOMENTS_LEN + (j - ART_CENTRAL_LEN)] = x;
+      }
+    } else {
+      moments_out[(size_t)v * ART_MOMENTS_LEN + j] = x;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Detector.autoplace, ART/ModuleDetector.py:109-137 with FindCentralRay ART/ModuleProcessing.py:464-482:
+// central vector = normalised mean direction, central point = mean point of the surviving rays;
+// normal = -central vector, centre = central point - normal * distance, refpoint = central point.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline void detector_fill(const double* centre, const double* normal, const double* refpoint,
+                                              const double* cvec, double l0, double n_rays, ArtDetector* D) {
+  const double ez[3] = {0.0, 0.0, 1.0};
+  for (int i = 0; i < 3; ++i) {
+    D->centre[i] = centre[i];
+    D->normal[i] = normal[i];
+    D->refpoint[i] = refpoint[i];
+    D->cvec[i] = cvec[i];
+  }
+  rotation_from_to(normal, ez, D->rot);  // get_PointList2D, ART/ModuleDetector.py:229
+  D->l0 = l0;
+  D->n_rays = n_rays;
+}
+
+__global__ void autoplace_kernel(const double* __restrict__ central, double distance, int n_variants,
+                                 ArtDetector* __restrict__ det) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_variants) return;
+  const double* c = central + (size_t)v * ART_CENTRAL_LEN;
+  const double N = c[ART_C_N];
+  double cv[3] = {c[ART_C_SUX] / N, c[ART_C_SUY] / N, c[ART_C_SUZ] / N};
+  const double cn = sqrt(cv[0] * cv[0] + cv[1] * cv[1] + cv[2] * cv[2]);
+  for (int i = 0; i < 3; ++i) cv[i] /= cn;  // Ray.vector setter normalises, ART/ModuleOpticalRay.py:85-90
+  const double cp[3] = {c[ART_C_SPX] / N, c[ART_C_SPY] / N, c[ART_C_SPZ] / N};
+  const double nrm[3] = {-cv[0], -cv[1], -cv[2]};
+  const double ctr[3] = {cp[0] - nrm[0] * distance, cp[1] - nrm[1] * distance, cp[2] - nrm[2] * distance};
+  detector_fill(ctr, nrm, cp, cv, c[ART_C_SPATH] / N + distance, N, det + v);
+}
+
+// delays in fs relative to the unweighted mean path, ART/ModuleDetector.py:277-278
+__global__ void delays_kernel(const double* __restrict__ l, const uint8_t* __restrict__ alive, long long n,
+                              const ArtDetector* __restrict__ det, const double* __restrict__ moments,
+                              double* __restrict__ out) {
+  const int v = blockIdx.y;
+  const double* mo = moments + (size_t)v * ART_MOMENTS_LEN;
+  const double mean = det[v].l0 + mo[ART_M_SD] / mo[ART_M_N];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long g = (long long)v * n + i;
+    if (!alive || alive[g]) out[g] = (l[g] - mean) / 299792458000.0 * 1e15;  // LightSpeed, ModuleDetector.py:21
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0: synthetic source bundles -- the reference's Vogel-spiral generators in closed form.
+// SpiralVogel ART/ModuleGeometry.py:61-76; _Cone / PointSource ART/ModuleSource.py:23-81;
+// PlaneWaveDisk :135-169.  Ray k of n_total: (x,y) = sqrt(k/n_total) rho (cos k phi, sin k phi).
+//   kind 0 point source: direction normalise(x, y, 1) rotated by rot, point = origin
+//   kind 1 plane wave : point = rot (x, y, 0) + origin, direction = rot ez
+// ---------------------------------------------------------------------------------------------
+struct SourceArgs {
+  int kind;
+  long long n_total, first, count;
+  double rho;
+  double rot[9];
+  double origin[3];
+  BundleDev b;
+};
+__global__ void source_kernel(const SourceArgs a) {
+  const double golden = 3.141592653589793 * (3.0 - sqrt(5.0));
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.count;
+       j += (long long)gridDim.x * blockDim.x) {
+    const double k = (double)(a.first + j);
+    const double rad = sqrt(k / (double)a.n_total) * a.rho;
+    double s, c;
+    sincos(golden * k, &s, &c);
+    const double x = c * rad, y = s * rad;
+    double px, py, pz, ux, uy, uz;
+    if (a.kind == 0) {
+      const double inv = 1.0 / sqrt(fma(x, x, fma(y, y, 1.0)));
+      const double vx = x * inv, vy = y * inv, vz = inv;
+      ux = a.rot[0] * vx + a.rot[1] * vy + a.rot[2] * vz;
+      uy = a.rot[3] * vx + a.rot[4] * vy + a.rot[5] * vz;
+      uz = a.rot[6] * vx + a.rot[7] * vy + a.rot[8] * vz;
+      px = a.origin[0]; py = a.origin[1]; pz = a.origin[2];
+    } else {
+      px = a.rot[0] * x + a.rot[1] * y + a.origin[0];
+      py = a.rot[3] * x + a.rot[4] * y + a.origin[1];
+      pz = a.rot[6] * x + a.rot[7] * y + a.origin[2];
+      ux = a.rot[2]; uy = a.rot[5]; uz = a.rot[8];
+    }
+    const double un = 1.0 / sqrt(fma(ux, ux, fma(uy, uy, uz * uz)));
+    a.b.px[j] = px; a.b.py[j] = py; a.b.pz[j] = pz;
+    a.b.ux[j] = ux * un; a.b.uy[j] = uy * un; a.b.uz[j] = uz * un;
+    if (a.b.path) a.b.path[j] = 0.0;
+    if (a.b.alive) a.b.alive[j] = 1;
+  }
+}
+
+// ApplyGaussianIntensityToRayList, ART/ModuleSource.py:219-261.
+//   pass 0: per-block max of angle(axis, u) and of |P| -> partials[block][2]
+//   pass 1: mode 0 (point source): I = exp(-2 (tan(angle)/div)^2 * (-0.5 ln f));
+//           mode 1 (plane wave):   I = exp(-2 (|P|/maxdist)^2 * (-0.5 ln f))
+struct IntensityArgs {
+  BundleDev b;
+  long long n;
+  double axis[3];
+  int pass, mode;
+  double scale;    // divergence or max distance
+  double lnf;      // -0.5 * ln(fraction)
+  double* partials;
+};
+__global__ void __launch_bounds__(TPB) intensity_kernel(const IntensityArgs a) {
+  __shared__ double sRed[NWARP * 2];
+  double mx[2] = {0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < a.n; i += (long long)gridDim.x * TPB) {
+    const double ang = unit_angle(a.axis[0], a.axis[1], a.axis[2], a.b.ux[i], a.b.uy[i], a.b.uz[i]);
+    const double px = a.b.px[i], py = a.b.py[i], pz = a.b.pz[i];
+    const double dist = sqrt(fma(px, px, fma(py, py, pz * pz)));
+    if (a.pass == 0) {
+      mx[0] = fmax(mx[0], ang);
+      mx[1] = fmax(mx[1], dist);
+    } else {
+      const double q = (a.mode == 0 ? tan(ang) : dist) / a.scale;
+      a.b.inten[i] = exp(-2.0 * q * q * a.lnf);
+    }
+  }
+  if (a.pass == 0) block_reduce_row<2>(mx, [](int) { return 2; }, sRed, a.partials + (size_t)blockIdx.x * 2);
+}
+
+__global__ void extents_fold_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out) {
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 32) {
+    a = fmax(a, partials[2 * i]);
+    b = fmax(b, partials[2 * i + 1]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+    b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+  }
+  if (threadIdx.x == 0) {
+    out[0] = a;
+    out[1] = b;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// roofline probes
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) probe_fp64_kernel(double* out, int iters, double seed) {
+  double x0 = seed + threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+         x7 = x0 + 7;
+  const double a = 0.9999999, b = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456) out[0] = s;  // never true; keeps the loop alive
+}
+__global__ void __launch_bounds__(TPB) probe_copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
+                                                         long long n2) {
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n2; i += (long long)gridDim.x * TPB)
+    dst[i] = src[i];
+}
+
+}  // namespace art

@@ -1,0 +1,257 @@
+"""Device-side engine: a thin, typed wrapper over the C ABI of libart_b200.so.
+
+`DeviceChain` owns one `ArtChain*` (the packed element table of one or more chain variants on the
+current CUDA device) and exposes the entry points with torch tensors as buffers:
+
+    trace()     RayTracingCalculation            ART/ModuleProcessing.py:250
+    autoplace() Detector.autoplace               ART/ModuleDetector.py:109
+    moments()   Detector response + statistics   ART/ModuleDetector.py:191-279, ModuleProcessing.py:485-532
+    sweep()     the loop over misaligned chains  ARTmain.py:326-332
+    run_host()  host buffers in, statistics out  ARTmain.py:248 run_ART
+
+Everything runs on `torch.cuda.current_stream()`.  There is no CPU path: without a CUDA device
+(or without the built library) these calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._lowering import LoweredChain
+from .ModuleOpticalRay import RayBundle
+
+OUT_COLUMNS = ("px", "py", "pz", "ux", "uy", "uz", "path", "incidence")
+OUT_COLUMNS_NO_INC = OUT_COLUMNS[:-1]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("attosecondraytracing_b200 traces rays on a CUDA device (B200, sm_100a) only; "
+                           "no CUDA device is available and there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+class DeviceChain:
+    """Immutable packed chain (possibly many pose variants) resident on one CUDA device."""
+
+    def __init__(self, variants, device=None):
+        """variants: list of OpticalElement lists (one per variant), or a single OpticalElement list."""
+        if variants and not isinstance(variants[0], (list, tuple)):
+            variants = [variants]
+        self.device = require_cuda(device)
+        self.lowered = LoweredChain(variants)
+        self.n_elements = self.lowered.n_elements
+        self.n_variants = self.lowered.n_variants
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().art_chain_create(self.lowered.elements, self.n_elements, self.n_variants,
+                                                     self.lowered.defects, self.lowered.n_defects,
+                                                     C.byref(self._handle)))
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            _cabi.lib().art_chain_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def _check_bundle(self, bundle):
+        if bundle.device.type != "cuda":
+            raise RuntimeError("the ray bundle must live on the CUDA device (RayBundle.to('cuda'))")
+
+    def _new_out(self, src, n_variants, want_incidence):
+        out = RayBundle(src.n * n_variants, device=self.device,
+                        columns=OUT_COLUMNS if want_incidence else OUT_COLUMNS_NO_INC, with_alive=True,
+                        wavelength=src.wavelength)
+        return out
+
+    def trace(self, bundle, ignore_defects=True, history=False, want_incidence=True, want_central=True,
+              variant_first=0, n_variants=None, store_final=True):
+        """Trace `bundle` through the chain.  Returns (bundles, central):
+        bundles = list of RayBundle after each element (history=True) or [final bundle];
+        for several variants the rows of variant v are [v*n, (v+1)*n).  central = tensor
+        (n_variants, 10) of the central-ray sums, or None."""
+        self._check_bundle(bundle)
+        nv = self.n_variants - variant_first if n_variants is None else n_variants
+        flags = (_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0) | (0 if want_incidence else _cabi.TRACE_NO_INCIDENCE)
+        outs = []
+        hist_arr = None
+        final_view = None
+        if history:
+            outs = [self._new_out(bundle, nv, want_incidence) for _ in range(self.n_elements)]
+            hist_arr = (_cabi.ArtBundleView * self.n_elements)(*[o.view() for o in outs])
+        elif store_final:
+            outs = [self._new_out(bundle, nv, want_incidence)]
+            final_view = C.byref(outs[0].view())
+        central = torch.empty((nv, _cabi.CENTRAL_LEN), dtype=torch.float64, device=self.device) if want_central else None
+        vin = bundle.view()
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().art_trace(self._handle, variant_first, nv, C.byref(vin), final_view, hist_arr,
+                                              flags, _ptr(central), _stream()))
+        for o in outs:
+            if bundle.has("intensity") and nv == 1:
+                o.shared_intensity = bundle.col("intensity")
+            if bundle.number is not None and nv == 1:
+                o.number = bundle.number
+            o.invalidate()
+        return outs, central
+
+    def autoplace(self, central, distance):
+        """Detector.autoplace for every variant row of `central`; returns an (n_variants, 23) tensor of ArtDetector."""
+        nv = central.shape[0]
+        det = torch.empty((nv, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().art_detector_autoplace(_ptr(central), float(distance), nv, _ptr(det), _stream()))
+        return det
+
+    def moments(self, bundle, det, intensity=None, want_points=False):
+        """Detector moments of a stored bundle (n_variants x n rows).  Returns (moments, x, y, l)."""
+        self._check_bundle(bundle)
+        nv = det.shape[0]
+        mom = torch.empty((nv, _cabi.MOMENTS_LEN), dtype=torch.float64, device=self.device)
+        x = y = l = None
+        if want_points:
+            x = torch.full((bundle.n,), float("nan"), dtype=torch.float64, device=self.device)
+            y = torch.full_like(x, float("nan"))
+            l = torch.full_like(x, float("nan"))
+        v = bundle.view()
+        if intensity is not None:
+            v.intensity = intensity.data_ptr()
+        elif not bundle.has("intensity"):
+            shared = getattr(bundle, "shared_intensity", None)
+            v.intensity = shared.data_ptr() if shared is not None else None
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().art_detector_moments(self._handle, C.byref(v), nv, _ptr(det), _ptr(x), _ptr(y),
+                                                         _ptr(l), _ptr(mom), _stream()))
+        return mom, x, y, l
+
+    def delays(self, l, alive, det, moments, n_variants=1):
+        """Per-ray delays (fs) relative to the unweighted mean path; NaN for dead rays."""
+        out = torch.full_like(l, float("nan"))
+        n = l.numel() // n_variants
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().art_delays(_ptr(l), _ptr(alive), n, n_variants, _ptr(det), _ptr(moments),
+                                               _ptr(out), _stream()))
+        return out
+
+    def trace_detect(self, bundle, det, ignore_defects=True, variant_first=0, want_points=False):
+        """Fused trace + detector for known detectors; returns (moments, central, x, y, l)."""
+        self._check_bundle(bundle)
+        nv = det.shape[0]
+        flags = (_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0) | _cabi.TRACE_NO_INCIDENCE
+        mom = torch.empty((nv, _cabi.MOMENTS_LEN), dtype=torch.float64, device=self.device)
+        central = torch.empty((nv, _cabi.CENTRAL_LEN), dtype=torch.float64, device=self.device)
+        x = y = l = None
+        if want_points:
+            x = torch.full((bundle.n * nv,), float("nan"), dtype=torch.float64, device=self.device)
+            y = torch.full_like(x, float("nan"))
+            l = torch.full_like(x, float("nan"))
+        vin = bundle.view()
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().art_trace_detect(self._handle, variant_first, nv, C.byref(vin), None, flags,
+                                                     _ptr(det), _ptr(x), _ptr(y), _ptr(l), _ptr(central), _ptr(mom),
+                                                     _stream()))
+        return mom, central, x, y, l
+
+    def sweep(self, bundle, distance, ignore_defects=True, variant_first=0, n_variants=None):
+        """Trace every variant, autoplace its detector at `distance`, reduce its moments.
+        Returns (moments (nv,24), central (nv,10), det (nv,23)) device tensors."""
+        self._check_bundle(bundle)
+        nv = self.n_variants - variant_first if n_variants is None else n_variants
+        flags = _cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0
+        mom = torch.empty((nv, _cabi.MOMENTS_LEN), dtype=torch.float64, device=self.device)
+        central = torch.empty((nv, _cabi.CENTRAL_LEN), dtype=torch.float64, device=self.device)
+        det = torch.empty((nv, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=self.device)
+        vin = bundle.view()
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().art_sweep(self._handle, variant_first, nv, C.byref(vin), flags, float(distance),
+                                              _ptr(central), _ptr(det), _ptr(mom), _stream()))
+        return mom, central, det
+
+    def run_host(self, host_bundle, distance, ignore_defects=True, out_host=None, manual_det=None):
+        """Host buffers in (pinned or pageable torch CPU tensors), statistics out: H2D, trace,
+        autoplace, moments, D2H inside one synchronous C call.  Returns (moments, central, det) numpy."""
+        if host_bundle.device.type != "cpu":
+            raise RuntimeError("run_host takes a host-resident bundle")
+        flags = (_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0)
+        if out_host is None or not out_host.has("incidence"):
+            flags |= _cabi.TRACE_NO_INCIDENCE
+        mom = np.empty(_cabi.MOMENTS_LEN)
+        cen = np.empty(_cabi.CENTRAL_LEN)
+        det = _cabi.ArtDetector()
+        vin = host_bundle.view()
+        vout = C.byref(out_host.view()) if out_host is not None else None
+        dp = _cabi.c_double_p
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().art_run_host(self._handle, C.byref(vin), vout, flags, float(distance),
+                                                 C.byref(manual_det) if manual_det is not None else None,
+                                                 mom.ctypes.data_as(dp), cen.ctypes.data_as(dp), C.byref(det)))
+        if out_host is not None:
+            out_host.invalidate()
+        return mom, cen, det
+
+
+# ----------------------------------------------------------------------------------------------
+# statistics from a moments row (host arithmetic on ~24 numbers)
+# ----------------------------------------------------------------------------------------------
+LIGHTSPEED = 299792458000  # mm/s, ART/ModuleDetector.py:21
+
+
+def summary_from_moments(m, central=None):
+    """Dict of the bundle statistics the reference computes with StandardDeviation /
+    WeightedStandardDeviation / GetResultSummary / getETransmission / DiameterPointList /
+    ReturnNumericalAperture, from one moments row (and optionally the central-sum row)."""
+    m = np.asarray(m, dtype=np.float64)
+    n = m[_cabi.M_N]
+    out = {"n_rays": int(n)}
+    if not n > 0:
+        for k in ("SpotSizeSD", "DurationSD", "SpotSizeSD_w", "DurationSD_w", "Diameter", "NA", "mean_path_offset"):
+            out[k] = float("nan")
+        return out
+    fs_per_mm = 1e15 / LIGHTSPEED
+
+    def var(s1, s2, w):
+        return max(s2 / w - (s1 / w) ** 2, 0.0)
+
+    vx, vy = var(m[_cabi.M_SX], m[_cabi.M_SXX], n), var(m[_cabi.M_SY], m[_cabi.M_SYY], n)
+    out["SpotSizeSD"] = float(np.sqrt(vx + vy))                                    # ModuleProcessing.py:485-507
+    out["DurationSD"] = float(np.sqrt(var(m[_cabi.M_SD], m[_cabi.M_SDD], n)) * fs_per_mm)
+    sw = m[_cabi.M_SW]
+    wvx, wvy = var(m[_cabi.M_SWX], m[_cabi.M_SWXX], sw), var(m[_cabi.M_SWY], m[_cabi.M_SWYY], sw)
+    out["SpotSizeSD_w"] = float(np.sqrt(wvx + wvy))                                # ModuleProcessing.py:510-532
+    # weighted SD of the delays: the delays are referenced to the UNWEIGHTED mean but the
+    # weighted variance is taken about the weighted mean, so the reference point drops out
+    out["DurationSD_w"] = float(np.sqrt(var(m[_cabi.M_SWD], m[_cabi.M_SWDD], sw)) * fs_per_mm)
+    out["Diameter"] = float(max(abs(m[_cabi.M_XMAX] - m[_cabi.M_XMIN]), abs(m[_cabi.M_YMAX] - m[_cabi.M_YMIN])))
+    out["bbox_centre"] = (0.5 * (m[_cabi.M_XMAX] + m[_cabi.M_XMIN]), 0.5 * (m[_cabi.M_YMAX] + m[_cabi.M_YMIN]))
+    out["NA"] = float(np.sin(2 * np.arctan(np.sqrt(m[_cabi.M_TMAX]))))             # ModuleProcessing.py:536-566
+    out["mean_path_offset"] = float(m[_cabi.M_SD] / n)
+    out["delay_min_fs"] = float((m[_cabi.M_DMIN] - m[_cabi.M_SD] / n) * fs_per_mm)
+    out["delay_max_fs"] = float((m[_cabi.M_DMAX] - m[_cabi.M_SD] / n) * fs_per_mm)
+    if central is not None:
+        c = np.asarray(central, dtype=np.float64)
+        out["ETransmission"] = float(100 * c[_cabi.C_SW_OUT] / c[_cabi.C_SW_IN])   # ModuleAnalysisAndPlots.py:62-77
+    return out
+
+
+def detector_from_row(row):
+    """numpy view of one ArtDetector row (23 doubles) as a dict."""
+    r = np.asarray(row, dtype=np.float64)
+    return {"centre": r[0:3], "normal": r[3:6], "refpoint": r[6:9], "cvec": r[9:12], "rot": r[12:21].reshape(3, 3),
+            "l0": r[21], "n_rays": r[22]}

@@ -115,6 +115,8 @@ typedef struct ArtDetector {
   double centre[3];
   double normal[3];
   double refpoint[3];
+  double cvec[3]; /* central unit vector of the bundle (autoplace: -normal), the reference axis of
+                     ReturnNumericalAperture, ART/ModuleProcessing.py:536-566 */
   double rot[9];
   double l0;
   double n_rays; /* rays the central ray was averaged over (0: detector undefined) */
@@ -193,8 +195,9 @@ int32_t art_trace(ArtChain* chain, int32_t variant_first, int32_t n_variants, co
 int32_t art_detector_autoplace(const double* central, double distance, int32_t n_variants,
                                ArtDetector* det_out, void* stream);
 
-/* Fill an ArtDetector (host struct) from centre / normal / refpoint: computes rot; l0 as given.
- * For manually placed detectors (ARTmain.py:113 setup_detector, ManualDetector branch). */
+/* Fill an ArtDetector (host struct) from centre / normal / refpoint: computes rot, cvec = -normal;
+ * l0 as given.  For manually placed detectors (ARTmain.py:113 setup_detector, ManualDetector
+ * branch).  Host arithmetic only. */
 int32_t art_detector_make(const double centre[3], const double normal[3], const double refpoint[3],
                           double l0, ArtDetector* det_out);
 
@@ -209,10 +212,62 @@ int32_t art_detector_make(const double centre[3], const double normal[3], const 
  *   x_out, y_out, l_out  NULL or device columns (n_variants x n): in-plane coordinates relative
  *            to Detector.centre and total optical path length L (mm) of each alive ray.
  *   moments_out  device, n_variants x ART_MOMENTS_LEN.
+ *   chain    lends its reduction scratch (a chain serves one stream at a time); NULL: a
+ *            per-device scratch inside the library is used (allocated on first use / growth).
  */
-int32_t art_detector_moments(const ArtBundleView* bundle, int32_t n_variants, const ArtDetector* det,
-                             double* x_out, double* y_out, double* l_out, double* moments_out,
-                             void* stream);
+int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bundle, int32_t n_variants,
+                             const ArtDetector* det, double* x_out, double* y_out, double* l_out,
+                             double* moments_out, void* stream);
+
+/*
+ * Trace and detector in ONE kernel (K1 with K2 as its epilogue), for detectors that are known
+ * before the trace (manual detectors, the second pass of a sweep): as art_trace, and in addition
+ * every surviving final ray is intersected with det[v] and the moments are reduced; no per-ray
+ * bundle has to be stored (out_final may be NULL).  det: device, n_variants detectors.
+ */
+int32_t art_trace_detect(ArtChain* chain, int32_t variant_first, int32_t n_variants, const ArtBundleView* in,
+                         const ArtBundleView* out_final, uint32_t flags, const ArtDetector* det,
+                         double* x_out, double* y_out, double* l_out, double* central_out,
+                         double* moments_out, void* stream);
+
+/*
+ * The batched misalignment sweep: the loop of ARTmain.py:326-332 main() over the chains that
+ * ART/ModuleOpticalChain.py:533 get_OE_loop_list builds, each followed by Detector.autoplace at
+ * `distance` and GetResultSummary.  Two passes over the (L2-resident) source bundle -- trace +
+ * central sums, autoplace on the device, trace + detector moments -- and no per-ray output.
+ *   central_out  device, n_variants x ART_CENTRAL_LEN   (nullable)
+ *   det_out      device, n_variants ArtDetector
+ *   moments_out  device, n_variants x ART_MOMENTS_LEN
+ */
+int32_t art_sweep(ArtChain* chain, int32_t variant_first, int32_t n_variants, const ArtBundleView* in,
+                  uint32_t flags, double distance, double* central_out, ArtDetector* det_out,
+                  double* moments_out, void* stream);
+
+/* Per-ray delays in fs relative to the unweighted mean path, Detector.get_Delays
+ * ART/ModuleDetector.py:254-279: delay = (l - (l0 + SD/N)) / c * 1e15 for the alive rays.
+ * l, alive (nullable), delays_out: n_variants x n device columns; det / moments as returned by
+ * art_detector_moments (moments may have been all-reduced over ranks in between). */
+int32_t art_delays(const double* l, const uint8_t* alive, int64_t n, int32_t n_variants, const ArtDetector* det,
+                   const double* moments, double* delays_out, void* stream);
+
+/*
+ * Synthetic source bundles in closed form (device): rows [first, first + count) of the n_total-ray
+ * Vogel-spiral bundle written to bundle[0 .. count).
+ *   kind 0  PointSource(origin, axis, Divergence, n_total)  ART/ModuleSource.py:54-81, rho = tan(Divergence)
+ *   kind 1  PlaneWaveDisk(origin, axis, Radius, n_total)    ART/ModuleSource.py:135-169, rho = Radius
+ *           (the reference emits rays 0 .. n_total-2 of the n_total-point spiral)
+ * axis: the bundle is rotated ez -> axis with RotationPoint semantics.
+ */
+int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t first, int64_t count, double rho,
+                            const double axis[3], const double origin[3], const ArtBundleView* bundle,
+                            void* stream);
+/* ApplyGaussianIntensityToRayList, ART/ModuleSource.py:219-261, in two calls so that sharded
+ * bundles can all-reduce in between: art_source_extents writes {max angle(axis, u), max |P|} of
+ * the bundle to extents_out (device, 2 doubles); art_source_intensity then fills bundle->intensity
+ * with exp(-2 (q/scale)^2 * (-0.5 ln fraction)), q = tan(angle) (mode 0) or |P| (mode 1). */
+int32_t art_source_extents(const ArtBundleView* bundle, const double axis[3], double* extents_out, void* stream);
+int32_t art_source_intensity(const ArtBundleView* bundle, const double axis[3], int32_t mode, double scale,
+                             double fraction, void* stream);
 
 /*
  * End-to-end convenience with HOST buffers: copies the source bundle to the device, traces

@@ -72,3 +72,71 @@ def dir_tol(name):
 
 
 DELAY_TOL_FS = 1e-5  # 0.01 as
+
+
+# ----------------------------------------------------------------------------------------------
+# fixture -> objects of the package under test (attosecondraytracing_b200)
+# ----------------------------------------------------------------------------------------------
+def build_support(spec):
+    import attosecondraytracing_b200.ModuleSupport as msupp
+    kind, p = spec[0], spec[1:]
+    return {"round": msupp.SupportRound, "roundhole": msupp.SupportRoundHole, "rect": msupp.SupportRectangle,
+            "recthole": msupp.SupportRectangleHole, "rectrecthole": msupp.SupportRectangleRectHole}[kind](*p)
+
+
+def build_optic(spec):
+    """The package's optic object for a scene-catalogue optic spec (oracle/scenes.py)."""
+    import attosecondraytracing_b200.ModuleDefects as mdef
+    import attosecondraytracing_b200.ModuleMask as mmask
+    import attosecondraytracing_b200.ModuleMirror as mmirror
+    sup = build_support(spec["support"])
+    k = spec["kind"]
+    if k == "mask":
+        return mmask.Mask(sup)
+    if k == "plane":
+        m = mmirror.MirrorPlane(sup)
+    elif k == "spherical":
+        m = mmirror.MirrorSpherical(spec["radius_signed"], sup)
+    elif k == "cylindrical":
+        m = mmirror.MirrorCylindrical(spec["radius_signed"], sup)
+    elif k == "parabolic":
+        m = mmirror.MirrorParabolic(spec["feff"], spec["offaxisangle_deg"], sup)
+    elif k == "toroidal":
+        m = mmirror.MirrorToroidal(spec["majorradius"], spec["minorradius"], sup)
+    elif k == "ellipsoidal":
+        kw = {a: spec[a] for a in ("SemiMajorAxis", "SemiMinorAxis", "OffAxisAngle", "f_object", "f_image")
+              if a in spec}
+        m = mmirror.MirrorEllipsoidal(sup, **kw)
+    else:
+        raise ValueError(k)
+    if spec.get("defects"):
+        dl = [mdef.Zernike(sup, {(int(n), int(mm_)): c for n, mm_, c in d["coefficients"]}) for d in spec["defects"]]
+        m = mmirror.DeformedMirror(m, dl)
+    return m
+
+
+def golden_optical_elements(g):
+    """OpticalElement list of the package for fixture `g`, with the poses the reference produced."""
+    import attosecondraytracing_b200.ModuleOpticalElement as moe
+    out = []
+    for k, spec in enumerate(g.spec["optics"]):
+        out.append(moe.OpticalElement(build_optic(spec), g[f"el{k}_position"].copy(), g[f"el{k}_normal"].copy(),
+                                      g[f"el{k}_majoraxis"].copy()))
+    return out
+
+
+def compare_bundle(name, k, ref, number, P, U, path, inc, check_inc=True):
+    """The parity bars of the north star for the bundle after element k; returns the max deviations."""
+    assert np.array_equal(number, ref["num"]), f"{name}: survivors differ after element {k}"
+    if ref["num"].size == 0:
+        return {}
+    tol = point_tol(name)
+    dev = {"P": float(np.max(np.abs(P - ref["P"]))), "U": float(np.max(np.abs(U - ref["U"]))),
+           "path": float(np.max(np.abs(path - ref["path"])))}
+    assert dev["P"] <= tol, (name, k, dev)
+    assert dev["U"] <= dir_tol(name), (name, k, dev)
+    assert dev["path"] <= 2 * tol, (name, k, dev)
+    if check_inc:
+        dev["inc"] = float(np.max(np.abs(inc - ref["inc"])))
+        assert dev["inc"] <= 1e-9, (name, k, dev)
+    return dev

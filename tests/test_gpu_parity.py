@@ -1,0 +1,204 @@
+"""GPU parity: the CUDA path (through the C ABI of libart_b200.so) against the golden fixtures that
+the unmodified reference produced (tests/golden, oracle/gen_golden.py) and against the oracle.
+
+Bars (north star): ray numbering and survival bit-exact; points <= 1e-9 mm (3e-8 on the 5 m
+telescope whose reference output is itself that noisy, golden_util.point_tol); per-ray delays
+<= 0.01 as = 1e-5 fs.
+"""
+import numpy as np
+import pytest
+import torch
+
+import art_oracle as orc
+from golden_util import DELAY_TOL_FS, Golden, compare_bundle, golden_names, golden_optical_elements
+
+pytestmark = pytest.mark.gpu
+
+NAMES = golden_names()
+
+
+def _engine():
+    from attosecondraytracing_b200 import engine
+    return engine
+
+
+def _source_bundle(g, device="cuda"):
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
+    return RayBundle.from_numpy(g["src_P"], g["src_U"], intensity=g["src_I"], number=g["src_num"], device=device)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_trace_history_matches_reference(name):
+    eng = _engine()
+    g = Golden(name)
+    chain = eng.DeviceChain(golden_optical_elements(g))
+    src = _source_bundle(g)
+    outs, central = chain.trace(src, ignore_defects=g.ignore_defects, history=True)
+    torch.cuda.synchronize()
+    assert len(outs) == g.n_elements
+    for k, b in enumerate(outs):
+        d = b.to_numpy()
+        compare_bundle(name, k, g.out(k), d["number"], d["P"], d["U"], d["path"], d["incidence"])
+    # final-only trace gives the same final bundle bit for bit
+    outs2, central2 = chain.trace(src, ignore_defects=g.ignore_defects, history=False)
+    a, b = outs[-1].to_numpy(), outs2[0].to_numpy()
+    for key in ("number", "P", "U", "path", "incidence"):
+        assert np.array_equal(a[key], b[key], equal_nan=True), key
+    assert torch.equal(central, central2)
+    c = central.cpu().numpy()[0]
+    assert c[7] == g.out(g.n_elements - 1)["num"].size
+    chain.close()
+
+
+@pytest.mark.parametrize("name", [n for n in NAMES if "det_centre" in Golden(n)])
+def test_detector_and_statistics_match_reference(name):
+    eng = _engine()
+    g = Golden(name)
+    chain = eng.DeviceChain(golden_optical_elements(g))
+    src = _source_bundle(g)
+    outs, central = chain.trace(src, ignore_defects=g.ignore_defects, history=False)
+    final = outs[0]
+    det = chain.autoplace(central, g.spec["detector_distance"])
+    mom, x, y, l = chain.moments(final, det, intensity=src.col("intensity"), want_points=True)
+    delays = chain.delays(l, final.alive, det, mom)
+    torch.cuda.synchronize()
+    D = eng.detector_from_row(det.cpu().numpy()[0])
+    assert np.max(np.abs(D["centre"] - g["det_centre"])) <= 1e-9
+    assert np.max(np.abs(D["normal"] - g["det_normal"])) <= 1e-13
+    assert np.max(np.abs(D["refpoint"] - g["det_refpoint"])) <= 1e-9
+    m = mom.cpu().numpy()[0]
+    s = eng.summary_from_moments(m, central.cpu().numpy()[0])
+    idx = final.alive_index()
+    assert s["n_rays"] == idx.numel() == g["det_delays"].size
+    # per-ray detector response
+    xy = torch.stack([x[idx], y[idx]], dim=1).cpu().numpy() - np.array(s["bbox_centre"])
+    assert np.max(np.abs(xy - g["det_xy_centre"])) <= 1e-9
+    dl = delays[idx].cpu().numpy()
+    assert np.max(np.abs(dl - g["det_delays"])) <= DELAY_TOL_FS, np.max(np.abs(dl - g["det_delays"]))
+    # statistics
+    assert abs(s["SpotSizeSD"] - g["SpotSizeSD"]) <= 1e-9
+    assert abs(s["DurationSD"] - g["DurationSD"]) <= DELAY_TOL_FS
+    assert abs(s["ETransmission"] - g["ETransmission"]) <= 1e-9
+    assert abs(s["SpotSizeSD_w"] - g["SpotSizeSD_w"]) <= 1e-9
+    assert abs(s["DurationSD_w"] - g["DurationSD_w"]) <= DELAY_TOL_FS
+    assert abs(s["NA"] - g["NA"]) <= 1e-12
+    assert abs(s["Diameter"] - g["Diameter"]) <= 1e-9
+    # the fused trace+detector kernel and the sweep entry point give the same moments
+    mom2, central2, _, _, _ = chain.trace_detect(src, det, ignore_defects=g.ignore_defects)
+    mom3, central3, det3 = chain.sweep(src, g.spec["detector_distance"], ignore_defects=g.ignore_defects)
+    torch.cuda.synchronize()
+    for other in (mom2, mom3):
+        o = other.cpu().numpy()[0]
+        assert np.allclose(o[:14], m[:14], rtol=1e-12, atol=1e-12)
+        assert np.array_equal(o[14:21], m[14:21])
+    assert torch.equal(det3, det)
+    chain.close()
+
+
+@pytest.mark.parametrize("name", ["cfg3_2tor", "cfg1_par", "cfg4_zern_def"])
+def test_host_buffer_entry_point(name):
+    """art_run_host: host columns in, statistics and final bundle out (what a ctypes caller without
+    device buffers uses)."""
+    eng = _engine()
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
+    g = Golden(name)
+    chain = eng.DeviceChain(golden_optical_elements(g))
+    src = _source_bundle(g, device="cpu")
+    out = RayBundle(src.n, device="cpu", columns=eng.OUT_COLUMNS, with_alive=True)
+    mom, cen, det = chain.run_host(src, g.spec["detector_distance"], ignore_defects=g.ignore_defects, out_host=out)
+    out.number = src.number
+    d = out.to_numpy()
+    k = g.n_elements - 1
+    compare_bundle(name, k, g.out(k), d["number"], d["P"], d["U"], d["path"], d["incidence"])
+    s = eng.summary_from_moments(mom, cen)
+    assert abs(s["SpotSizeSD"] - g["SpotSizeSD"]) <= 1e-9
+    assert abs(s["DurationSD"] - g["DurationSD"]) <= DELAY_TOL_FS
+    assert abs(s["ETransmission"] - g["ETransmission"]) <= 1e-9
+    assert np.max(np.abs(np.array(det.centre[:]) - g["det_centre"])) <= 1e-9
+    chain.close()
+
+
+def test_edge_cases_empty_ragged_and_all_blocked():
+    """n = 0, n = 1, odd n (ragged 128-bit tail), and a bundle that loses every ray."""
+    eng = _engine()
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
+    g = Golden("cfg3_2tor")
+    chain = eng.DeviceChain(golden_optical_elements(g))
+    P, U = g["src_P"], g["src_U"]
+    full, _ = chain.trace(RayBundle.from_numpy(P, U, device="cuda"), history=False)
+    ref = full[0].to_numpy()
+    for n in (0, 1, 2, 3, 255, 257, 513):
+        outs, central = chain.trace(RayBundle.from_numpy(P[:n], U[:n], device="cuda"), history=False)
+        d = outs[0].to_numpy()
+        keep = ref["number"] < n
+        assert np.array_equal(d["number"], ref["number"][keep])
+        assert np.array_equal(d["P"], ref["P"][keep])
+        assert central.cpu().numpy()[0][7] == keep.sum()
+    # every ray blocked: rays 600.. of this bundle all miss the mask's hole
+    outs, central = chain.trace(RayBundle.from_numpy(P[600:], U[600:], device="cuda"), history=False)
+    assert len(outs[0]) == 0
+    det = chain.autoplace(central, 100.0)
+    mom, _, _, _ = chain.moments(outs[0], det)
+    s = eng.summary_from_moments(mom.cpu().numpy()[0])
+    assert s["n_rays"] == 0 and np.isnan(s["SpotSizeSD"])
+    chain.close()
+
+
+def test_variants_share_one_launch():
+    """Several pose variants in one chain: every variant's rows equal a single-variant trace."""
+    eng = _engine()
+    import copy
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
+    g = Golden("cfg5_tele")
+    base = golden_optical_elements(g)
+    variants = []
+    for ang in (-0.05, 0.0, 0.013, 0.05, 0.02):
+        oes = copy.deepcopy(base)
+        oes[2].rotate_pitch_by(ang)
+        variants.append(oes)
+    src = RayBundle.from_numpy(g["src_P"][:999], g["src_U"][:999], intensity=g["src_I"][:999], device="cuda")  # odd n
+    multi = eng.DeviceChain(variants)
+    outs, central = multi.trace(src, history=False)
+    mom_s, central_s, det_s = multi.sweep(src, 100.0)
+    n = src.n
+    for v, oes in enumerate(variants):
+        single = eng.DeviceChain(oes)
+        o1, c1 = single.trace(src, history=False)
+        for name in ("px", "py", "pz", "ux", "uy", "uz", "path", "incidence"):
+            a = outs[0].col(name)[v * n:(v + 1) * n]
+            assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(o1[0].col(name))), (v, name)
+        assert torch.equal(outs[0].alive[v * n:(v + 1) * n], o1[0].alive)
+        assert torch.equal(central[v], c1[0])
+        m1, cc1, d1 = single.sweep(src, 100.0)
+        assert torch.equal(mom_s[v], m1[0]) and torch.equal(det_s[v], d1[0])
+        single.close()
+    # the tele_pitch fixture is variant pitch=0.02 of element 2
+    gp = Golden("tele_pitch")
+    s = eng.summary_from_moments(mom_s[4].cpu().numpy())
+    if gp["src_P"].shape[0] == 1000:
+        full = eng.DeviceChain(variants[4])
+        srcf = RayBundle.from_numpy(gp["src_P"], gp["src_U"], intensity=gp["src_I"], device="cuda")
+        m, c, d = full.sweep(srcf, gp.spec["detector_distance"])
+        sf = eng.summary_from_moments(m.cpu().numpy()[0], c.cpu().numpy()[0])
+        assert abs(sf["SpotSizeSD"] - gp["SpotSizeSD"]) <= 1e-9
+        assert abs(sf["DurationSD"] - gp["DurationSD"]) <= DELAY_TOL_FS
+        full.close()
+    multi.close()
+
+
+def test_device_sources_match_oracle():
+    """K0: the closed-form Vogel-spiral bundles generated on the device equal the oracle's sources."""
+    from attosecondraytracing_b200 import ModuleSource as msrc
+    for sp in ({"Divergence": 0.025, "SourceSize": 0, "NumberRays": 5000, "Wavelength": 80e-6},
+               {"Divergence": 0, "SourceSize": 50, "NumberRays": 4001, "Wavelength": 800e-6}):
+        P, U, num, inten = orc.source_for(sp)
+        b = msrc.synthetic_source(sp, device="cuda")
+        d = b.to_numpy()
+        assert np.array_equal(d["number"], num)
+        assert np.max(np.abs(d["P"] - P)) <= 1e-12
+        assert np.max(np.abs(d["U"] - U)) <= 1e-14
+        assert np.max(np.abs(d["intensity"] - inten)) <= 1e-12
+        # a slice generated on its own equals the rows of the full bundle
+        part = msrc.synthetic_source(sp, device="cuda", first=1000, count=512)
+        pd = part.to_numpy()
+        assert np.array_equal(pd["P"], d["P"][1000:1512]) and np.array_equal(pd["U"], d["U"][1000:1512])
