@@ -145,9 +145,10 @@ class RayBundle:
     def view(self):
         """ArtBundleView over the tensors (pointers stay valid while this bundle lives)."""
         v = _cabi.ArtBundleView()
-        for name in _COLUMNS:
-            setattr(v, name, self.col(name).data_ptr() if self.has(name) else None)
-        v.alive = self.alive.data_ptr() if self.alive is not None else None
+        base, stride = self._storage.data_ptr(), self._storage.stride(0) * 8
+        for name in _COLUMNS:  # row pointers from the base: an empty slice has no data_ptr of its own
+            setattr(v, name, base + self._names.index(name) * stride if self.has(name) else None)
+        v.alive = self.alive.untyped_storage().data_ptr() if self.alive is not None else None
         v.n = self.n
         return v
 

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libart_b200.so")
+# ART_B200_LIB points the loader at another build of the same library (kernel tuning variants)
+LIB_PATH = os.environ.get("ART_B200_LIB") or os.path.join(HERE, "libart_b200.so")
 
 ART_MAX_ELEMENTS = 16
 

@@ -67,10 +67,8 @@ struct ArtChain {
   HostWorkspace ws;
 };
 
-static const int kTargetBlocks = 148 * 8;
-
-static int blocks_per_variant(const ArtChain* c, long long n, int n_variants) {
-  const long long npairs = (n + 1) / 2;
+static int blocks_per_variant(const ArtChain* c, long long n, int n_variants, int per_thread = RPT) {
+  const long long npairs = (n + per_thread - 1) / per_thread;
   long long maxb = (npairs + TPB - 1) / TPB;
   if (maxb < 1) maxb = 1;
   long long target = (long long)c->sm_count * 8;
@@ -234,10 +232,10 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
   c->smem_bytes = sizeof(ElemDev) * ART_MAX_ELEMENTS + sizeof(double) * ztab.size() + sizeof(int) * zoff.size();
   c->smem_bytes = (c->smem_bytes + 15) & ~size_t(15);
   if (c->smem_bytes > 200 * 1024) return bail(ART_E_UNSUPPORTED, "Zernike tables exceed 200 KB of shared memory");
-  CK(allow_smem(trace_kernel<true, false>, c->smem_bytes));
-  CK(allow_smem(trace_kernel<false, false>, c->smem_bytes));
-  CK(allow_smem(trace_kernel<true, true>, c->smem_bytes));
-  CK(allow_smem(trace_kernel<false, true>, c->smem_bytes));
+  CK(allow_smem(trace_kernel<true, false, true>, c->smem_bytes));
+  CK(allow_smem(trace_kernel<false, false, true>, c->smem_bytes));
+  CK(allow_smem(trace_kernel<true, true, true>, c->smem_bytes));
+  CK(allow_smem(trace_kernel<false, true, true>, c->smem_bytes));
 
   CK(cudaMalloc(&c->d_elems, h.size() * sizeof(ElemDev)));
   CK(cudaMemcpy(c->d_elems, h.data(), h.size() * sizeof(ElemDev), cudaMemcpyHostToDevice));
@@ -313,24 +311,31 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
   a.y_out = y_out;
   a.l_out = l_out;
 
-  const int bpv = blocks_per_variant(c, in->n, n_variants);
+  const int bpv = blocks_per_variant(c, in->n, n_variants, ART_RPT);
   if ((size_t)bpv * n_variants > c->partial_rows) return fail(ART_E_INVALID, "internal: partial buffer too small");
   const dim3 grid(bpv, n_variants);
+  const size_t sm = c->smem_bytes;
+#define ART_TRACE_LAUNCH(INC, DET)                                                        \
+  do {                                                                                    \
+    if (c->has_defects) trace_kernel<INC, DET, true><<<grid, TPB, sm, st>>>(a);           \
+    else trace_kernel<INC, DET, false><<<grid, TPB, sm, st>>>(a);                         \
+  } while (0)
   if (det) {
-    if (want_inc) trace_kernel<true, true><<<grid, TPB, c->smem_bytes, st>>>(a);
-    else trace_kernel<false, true><<<grid, TPB, c->smem_bytes, st>>>(a);
+    if (want_inc) ART_TRACE_LAUNCH(true, true);
+    else ART_TRACE_LAUNCH(false, true);
     ART_LAUNCHED();
     fold_kernel<<<n_variants, TPB, 0, st>>>(c->d_partials, bpv, 1, central_out, moments_out);
     ART_LAUNCHED();
   } else {
-    if (want_inc) trace_kernel<true, false><<<grid, TPB, c->smem_bytes, st>>>(a);
-    else trace_kernel<false, false><<<grid, TPB, c->smem_bytes, st>>>(a);
+    if (want_inc) ART_TRACE_LAUNCH(true, false);
+    else ART_TRACE_LAUNCH(false, false);
     ART_LAUNCHED();
     if (central_out) {
       fold_kernel<<<n_variants, TPB, 0, st>>>(c->d_partials, bpv, 0, central_out, nullptr);
       ART_LAUNCHED();
     }
   }
+#undef ART_TRACE_LAUNCH
   return ART_OK;
 }
 

@@ -50,6 +50,50 @@ struct Ray {
 ART_HD double sq(double x) { return x * x; }
 
 // ---------------------------------------------------------------------------------------------
+// Branch-free FP64 division / square root / reciprocal square root for the device: an MUFU seed
+// (rcp.approx / rsqrt.approx, ~2^-23) refined by two Newton steps in FMAs and a final residual
+// correction -> results within 1 ulp for normal-range operands, with none of the slow-path calls,
+// predicate fix-ups and register shuffles of the IEEE-exact library sequences.  Operands here
+// are lengths, direction cosines and their products (1e-300 < |x| < 1e300).  A zero divisor gives NaN
+// instead of +-inf; every caller treats both as "no hit" (comparisons with NaN are false).
+// On the host (tests/hostcheck) the plain operators are used.
+// ---------------------------------------------------------------------------------------------
+ART_HD double fdiv(double a, double b) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  r = fma(r, fma(-b, r, 1.0), r);
+  r = fma(r, fma(-b, r, 1.0), r);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+#else
+  return a / b;
+#endif
+}
+ART_HD double frsqrt(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+ART_HD double fsqrt(double x) {
+#ifdef __CUDA_ARCH__
+  const double y = frsqrt(x);
+  double s = x * y;
+  s = fma(fma(-s, s, x), 0.5 * y, s);
+  return x == 0.0 ? 0.0 : s;
+#else
+  return sqrt(x);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
 // RotationPoint as a matrix, ART/ModuleGeometry.py:333-343 with AngleBetweenTwoVectors :40-44
 // (Kahan) and RotationAroundAxis :321-329 (quaternion rotation == Rodrigues).  Shared by the
 // host lowering and the device autoplace kernel so both branch identically.
@@ -144,9 +188,9 @@ ART_HD void solve_quadratic(double a, double b, double c, double& t1, double& t2
     t1 = t2 = ART_NAN;
     return;
   }
-  double q = -0.5 * (b + copysign(sqrt(disc), b));
-  t1 = q / a;
-  t2 = c / q;
+  double q = -0.5 * (b + copysign(fsqrt(disc), b));
+  t1 = fdiv(q, a);
+  t2 = fdiv(c, q);
 }
 
 // Candidate rule shared by the quadrics: t > 1e-12 (KeepPositiveSolution, ModuleGeometry.py:110-120),
@@ -187,7 +231,7 @@ struct TorEval {
 ART_HD TorEval tor_eval(const Ray& r, double t, double R, double r2) {
   double x = fma(t, r.ux, r.px), y = fma(t, r.uy, r.py), z = fma(t, r.uz, r.pz);
   double s = fma(x, x, z * z);
-  double inv = rsqrt(s);
+  double inv = frsqrt(s);
   double rho = s * inv;
   double q = rho - R;
   TorEval e;
@@ -201,29 +245,41 @@ ART_HD TorEval tor_eval(const Ray& r, double t, double R, double r2) {
   return e;
 }
 
+// 1/d to ~2^-46: MUFU.RCP64H seed (2^-23) + one Newton step.  Only used for Newton CORRECTIONS of the
+// root search, which are self-correcting; the converged root does not depend on the step's last bits.
+ART_HD double fast_rcp(double d) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  return fma(r, fma(-d, r, 1.0), r);
+#else
+  return 1.0 / d;
+#endif
+}
+
 // Newton stops once the NEXT correction would be below rounding level: F is convex with
 // F'' <= 2 |u|^2 = 2, so the step after dt is at most dt^2 / |F'|; at the noise floor of F
 // (~ eps r^2) dt itself is ~1e-13 mm and the test holds as well.
-// largest zero of F, Newton from the right of it; NaN if the line misses the solid
-ART_HD double tor_root_right(const Ray& r, double t, double R, double r2, double scale) {
+// largest zero of F, Newton from the right of it (e = evaluation at t); NaN if the line misses the solid
+ART_HD double tor_root_right(const Ray& r, double t, TorEval e, double R, double r2, double scale) {
   for (int it = 0; it < 64; ++it) {
-    TorEval e = tor_eval(r, t, R, r2);
     if (!(e.dF > 0.0)) return ART_NAN;  // walked past the minimum of F without meeting a zero
-    const double dt = e.F / e.dF;
+    const double dt = e.F * fast_rcp(e.dF);
     t -= dt;
     if (dt * dt <= 2e-16 * (fabs(t) + scale) * e.dF) return t;
+    e = tor_eval(r, t, R, r2);
   }
   return ART_NAN;
 }
-// smallest zero of F, Newton from the left of it (start t = 0 with F > 0, dF < 0)
-ART_HD double tor_root_left(const Ray& r, double R, double r2, double scale) {
+// smallest zero of F, Newton from the left of it (start t = 0 with F > 0, dF < 0; e = evaluation at 0)
+ART_HD double tor_root_left(const Ray& r, TorEval e, double R, double r2, double scale) {
   double t = 0.0;
   for (int it = 0; it < 64; ++it) {
-    TorEval e = tor_eval(r, t, R, r2);
     if (!(e.dF < 0.0)) return ART_NAN;
-    const double dt = e.F / e.dF;
+    const double dt = e.F * fast_rcp(e.dF);
     t -= dt;
     if (dt * dt <= 2e-16 * (fabs(t) + scale) * -e.dF) return t;
+    e = tor_eval(r, t, R, r2);
   }
   return ART_NAN;
 }
@@ -231,19 +287,20 @@ ART_HD double tor_root_left(const Ray& r, double R, double r2, double scale) {
 ART_HD double intersect_toroid(const ElemDev& E, const Ray& r) {
   const double R = E.sp[0], rr = E.sp[1], r2 = E.sp[2];
   // start for the right root: the tangent plane z = -(R+r) lies outside the solid
-  double t0 = (-(R + rr) - r.pz) / r.uz;
+  double t0 = fdiv(-(R + rr) - r.pz, r.uz);
   TorEval e0 = tor_eval(r, t0, R, r2);
   if (!(t0 > 0.0 && e0.F >= 0.0 && e0.dF > 0.0 && t0 < 1e300)) {
     // beyond closest approach to the axis point by more than R + r the solid is behind us
     double tc = -(r.px * r.ux + r.py * r.uy + r.pz * r.uz);
     t0 = tc + 1.0009765625 * (R + rr);
+    e0 = tor_eval(r, t0, R, r2);
   }
-  double tb = tor_root_right(r, t0, R, r2, rr);
+  double tb = tor_root_right(r, t0, e0, R, r2, rr);
   double ta = ART_NAN;
   TorEval o = tor_eval(r, 0.0, R, r2);
   if (o.F > 0.0) {
     if (!(o.dF < 0.0)) return ART_NAN;  // moving away from the solid: no forward root
-    ta = tor_root_left(r, R, r2, rr);
+    ta = tor_root_left(r, o, R, r2, rr);
   }
   return pick_candidate<true>(E, r, ta, tb, -R);
 }
@@ -265,7 +322,8 @@ ART_HD void zernike_eval(const double* __restrict__ zt, double X, double Y, doub
                                              double& gx, double& gy) {
   const double Rz = zt[0];
   const int N = (int)zt[1];
-  const double x = X / Rz, y = Y / Rz;
+  const double iR = fdiv(1.0, Rz);
+  const double x = X * iR, y = Y * iR;
   const double s = fma(x, x, y * y);
   const double* rec = zt + 2;
   double Cl = 1.0, Sl = 0.0, Cm = 0.0, Sm = 0.0;  // (x+iy)^l and (x+iy)^(l-1)
@@ -306,8 +364,8 @@ ART_HD void zernike_eval(const double* __restrict__ zt, double X, double Y, doub
     Cl = Cn;
   }
   val = v;
-  gx = dx / Rz;  // ModuleDefects.py:163-164
-  gy = dy / Rz;
+  gx = dx * iR;  // ModuleDefects.py:163-164
+  gy = dy * iR;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -340,23 +398,46 @@ ART_HD void surface_normal(const ElemDev& E, double x, double y, double z, doubl
       nx = 0.0; ny = 0.0; nz = 1.0;
       return;
   }
-  const double inv = rsqrt(fma(gx, gx, fma(gy, gy, gz * gz)));
+  const double inv = frsqrt(fma(gx, gx, fma(gy, gy, gz * gz)));
   nx = gx * inv; ny = gy * inv; nz = gz * inv;
 }
 
-// Kahan angle between two UNIT vectors a, b (ART/ModuleGeometry.py:40-44 with |a| = |b| = 1)
+// atan2(y, x) for y >= 0 (result in [0, pi]), branch-free: one division for the reduced argument
+// z (|z| <= tan(pi/8)) and the Maclaurin series of atan to z^41 (truncation < 2e-18 z).
+ART_HD double fatan2_ypos(double y, double x) {
+  const double ax = fabs(x);
+  const bool swap = y > ax;
+  const double lo = swap ? ax : y, hi = swap ? y : ax;          // lo/hi in [0, 1]
+  const bool big = lo > 0.41421356237309503 * hi;                // beyond tan(pi/8): rotate by pi/4
+  const double z = fdiv(big ? lo - hi : lo, big ? lo + hi : hi);
+  const double w = z * z;
+  double p = -1.0 / 41.0;
+  p = fma(p, w, 1.0 / 39.0);  p = fma(p, w, -1.0 / 37.0); p = fma(p, w, 1.0 / 35.0);  p = fma(p, w, -1.0 / 33.0);
+  p = fma(p, w, 1.0 / 31.0);  p = fma(p, w, -1.0 / 29.0); p = fma(p, w, 1.0 / 27.0);  p = fma(p, w, -1.0 / 25.0);
+  p = fma(p, w, 1.0 / 23.0);  p = fma(p, w, -1.0 / 21.0); p = fma(p, w, 1.0 / 19.0);  p = fma(p, w, -1.0 / 17.0);
+  p = fma(p, w, 1.0 / 15.0);  p = fma(p, w, -1.0 / 13.0); p = fma(p, w, 1.0 / 11.0);  p = fma(p, w, -1.0 / 9.0);
+  p = fma(p, w, 1.0 / 7.0);   p = fma(p, w, -1.0 / 5.0);  p = fma(p, w, 1.0 / 3.0);
+  double a = fma(-z * w, p, z);                                  // atan(z)
+  a += big ? 0.78539816339744831 : 0.0;
+  a = swap ? 1.5707963267948966 - a : a;
+  return x < 0.0 ? 3.1415926535897931 - a : a;
+}
+
+// Angle between two UNIT vectors a, b.  The reference uses Kahan's 2 atan2(|a-b|, |a+b|)
+// (ART/ModuleGeometry.py:40-44); atan2(|a x b|, a.b) is the same angle, equally well conditioned over
+// [0, pi], and needs one square root instead of two.
 ART_HD double unit_angle(double ax, double ay, double az, double bx, double by, double bz) {
-  double dx = ax - bx, dy = ay - by, dz = az - bz;
-  double sx = ax + bx, sy = ay + by, sz = az + bz;
-  return 2.0 * atan2(sqrt(fma(dx, dx, fma(dy, dy, dz * dz))), sqrt(fma(sx, sx, fma(sy, sy, sz * sz))));
+  const double cx = fma(ay, bz, -az * by), cy = fma(az, bx, -ax * bz), cz = fma(ax, by, -ay * bx);
+  return fatan2_ypos(fsqrt(fma(cx, cx, fma(cy, cy, cz * cz))), fma(ax, bx, fma(ay, by, az * bz)));
 }
 
 // ---------------------------------------------------------------------------------------------
 // one element acting on one ray: ART/ModuleProcessing.py:284-309 (frame in, optic, frame out)
 // ---------------------------------------------------------------------------------------------
-template <bool WANT_INC>
+template <bool WANT_INC, bool HAS_DEF = true>
 ART_HD void apply_element(const ElemDev& E, Ray& r, const double* __restrict__ ztab,
-                                              const int* __restrict__ zoff, bool ignore_defects) {
+                                              const int* __restrict__ zoff, bool ignore_defects,
+                                              bool inc_here = true) {
   // lab -> element frame (:289-295): p_e = R (p - pos) + centre, u_e = R u
   Ray e;
   {
@@ -371,13 +452,13 @@ ART_HD void apply_element(const ElemDev& E, Ray& r, const double* __restrict__ z
   double t;
   switch (E.surface) {
     case ART_SURF_PLANE: {  // ART/ModuleMirror.py:73-82: t > 0 (no epsilon) and on the support
-      t = -e.pz / e.uz;
+      t = fdiv(-e.pz, e.uz);
       const double x = fma(t, e.ux, e.px), y = fma(t, e.uy, e.py);
       if (!(t > 0.0 && in_support(E, x, y))) t = ART_NAN;
       break;
     }
     case ART_SURF_MASK: {  // ART/ModuleMask.py:51-61: passes iff t > 0 and NOT on the support
-      t = -e.pz / e.uz;
+      t = fdiv(-e.pz, e.uz);
       const double x = fma(t, e.ux, e.px), y = fma(t, e.uy, e.py);
       if (!(t > 0.0 && !in_support(E, x, y))) t = ART_NAN;
       break;
@@ -432,11 +513,11 @@ ART_HD void apply_element(const ElemDev& E, Ray& r, const double* __restrict__ z
   double ox = e.ux, oy = e.uy, oz = e.uz;  // outgoing direction, element frame
   if (E.surface == ART_SURF_MASK) {
     // _TransmitMaskRay, ART/ModuleMask.py:93-108: direction unchanged, incidence vs ez
-    if (WANT_INC) r.inc = unit_angle(e.ux, e.uy, e.uz, 0.0, 0.0, 1.0);
+    if (WANT_INC && inc_here) r.inc = unit_angle(e.ux, e.uy, e.uz, 0.0, 0.0, 1.0);
   } else {
     double nx, ny, nz;
     surface_normal(E, hx, hy, hz, nx, ny, nz);
-    if (E.n_defects > 0) {
+    if (HAS_DEF && E.n_defects > 0) {
       // DeformedMirror._get_intersection, ART/ModuleMirror.py:969-980:
       //   h = sum offsets(P - C); alpha = angle(-u, n_base(P)); P -= u h / cos(alpha)
       double h = 0.0;
@@ -446,21 +527,22 @@ ART_HD void apply_element(const ElemDev& E, Ray& r, const double* __restrict__ z
         h += v;
       }
       const double cosa = -(nx * e.ux + ny * e.uy + nz * e.uz);
-      const double sh = h / cosa;
+      const double sh = fdiv(h, cosa);
       t -= sh;
       hx = fma(-sh, e.ux, hx); hy = fma(-sh, e.uy, hy); hz = fma(-sh, e.uz, hz);
       surface_normal(E, hx, hy, hz, nx, ny, nz);  // the reflection uses get_normal(shifted point)
       if (!ignore_defects) {
         // DeformedMirror.get_normal + normal_add, ART/ModuleMirror.py:952-961, ModuleGeometry.py:394-407:
         // slopes add; the result is (-gx, -gy, 1) normalised
-        double sx = -nx / nz, sy = -ny / nz;
+        const double inz = fdiv(1.0, nz);
+        double sx = -nx * inz, sy = -ny * inz;
         for (int d = 0; d < E.n_defects; ++d) {
           double v, g0, g1;
           zernike_eval<false, true>(ztab + zoff[E.first_defect + d], hx - E.ctr[0], hy - E.ctr[1], v, g0, g1);
           sx += g0;
           sy += g1;
         }
-        const double inv = rsqrt(fma(sx, sx, fma(sy, sy, 1.0)));
+        const double inv = frsqrt(fma(sx, sx, fma(sy, sy, 1.0)));
         nx = -sx * inv; ny = -sy * inv; nz = inv;
       }
     }
@@ -470,7 +552,7 @@ ART_HD void apply_element(const ElemDev& E, Ray& r, const double* __restrict__ z
     // Ray.vector setter renormalises (ART/ModuleOpticalRay.py:85-90); one Newton step is exact here
     const double sc = fma(-0.5, fma(ox, ox, fma(oy, oy, oz * oz)), 1.5);
     ox *= sc; oy *= sc; oz *= sc;
-    if (WANT_INC) r.inc = unit_angle(-e.ux, -e.uy, -e.uz, nx, ny, nz);
+    if (WANT_INC && inc_here) r.inc = unit_angle(-e.ux, -e.uy, -e.uz, nx, ny, nz);
   }
   r.path += fabs(t);  // |P - A| with |u| = 1 (ModuleMirror.py:904, ModuleMask.py:100)
   // element -> lab frame (:306-309): p = R^T (p_e - centre) + pos, u = R^T u_e

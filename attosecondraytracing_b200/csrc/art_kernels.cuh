@@ -117,7 +117,7 @@ __device__ __forceinline__ DetHit detector_ray(const ArtDetector& D, const Ray& 
   const double nx = D.normal[0], ny = D.normal[1], nz = D.normal[2];
   const double num = fma(nx, D.centre[0] - r.px, fma(ny, D.centre[1] - r.py, nz * (D.centre[2] - r.pz)));
   const double den = fma(nx, r.ux, fma(ny, r.uy, nz * r.uz));
-  const double t = num / den;
+  const double t = fdiv(num, den);
   const double hx = fma(t, r.ux, r.px) - D.centre[0];
   const double hy = fma(t, r.uy, r.py) - D.centre[1];
   const double hz = fma(t, r.uz, r.pz) - D.centre[2];
@@ -128,7 +128,7 @@ __device__ __forceinline__ DetHit detector_ray(const ArtDetector& D, const Ray& 
   // tan^2(angle(u, central vector)/2) from Kahan's form (ART/ModuleGeometry.py:40-44) with unit vectors
   const double dx = r.ux - D.cvec[0], dy = r.uy - D.cvec[1], dz = r.uz - D.cvec[2];
   const double sx = r.ux + D.cvec[0], sy = r.uy + D.cvec[1], sz = r.uz + D.cvec[2];
-  h.tan2 = fma(dx, dx, fma(dy, dy, dz * dz)) / fma(sx, sx, fma(sy, sy, sz * sz));
+  h.tan2 = fdiv(fma(dx, dx, fma(dy, dy, dz * dz)), fma(sx, sx, fma(sy, sy, sz * sz)));
   return h;
 }
 
@@ -172,9 +172,73 @@ __device__ __forceinline__ void moments_add(double (&m)[ART_MOMENTS_LEN], const 
 // of the block's variant sit in shared memory and are read at warp-uniform addresses.
 //   WANT_INC  compute Ray.incidence
 //   WITH_DET  also evaluate the detector of this variant and accumulate its moments (K2 fused)
+//   HAS_DEF   the chain carries Zernike defects (otherwise that code and its registers are compiled out)
+// Build-time tunables (measured on B200): ART_RPT rays per thread (2 = 128-bit column
+// accesses), ART_MINB resident blocks per SM asked of the register allocator, ART_SMEM_ACC keeps
+// the per-thread central sums in shared memory instead of registers.
 // ---------------------------------------------------------------------------------------------
-template <bool WANT_INC, bool WITH_DET>
-__global__ void __launch_bounds__(TPB, 2) trace_kernel(const TraceArgs a) {
+#ifndef ART_RPT
+#define ART_RPT 2
+#endif
+#ifndef ART_MINB
+#define ART_MINB 2
+#endif
+#ifndef ART_SMEM_ACC
+#define ART_SMEM_ACC 1
+#endif
+static_assert(ART_RPT == 1 || ART_RPT == 2, "ART_RPT must be 1 or 2");
+static_assert(RPT == 2, "column helpers are written for pairs");
+
+template <int N>
+__device__ __forceinline__ void load_rays(const double* __restrict__ col, long long i, bool two, double (&v)[N]) {
+  if (N == 2) {
+    load_pair(col, i, two, v[0], v[N - 1]);
+  } else {
+    v[0] = col[i];
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_rays(double* __restrict__ col, long long i, bool vec, const bool (&w)[N],
+                                           const double (&v)[N]) {
+  if (N == 2) {
+    store_pair(col, i, vec, w[0], w[N - 1], v[0], v[N - 1]);
+  } else {
+    if (w[0]) __stcs(col + i, v[0]);
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void store_bundle(const BundleDev& O, long long at, bool vec, bool two, const Ray (&r)[N],
+                                             bool want_inc) {
+  bool w[N];
+  double v[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) w[q] = r[q].alive;
+#define ART_ST(colp, field)                         \
+  {                                                 \
+    _Pragma("unroll") for (int q = 0; q < N; ++q) v[q] = r[q].field; \
+    store_rays<N>(colp, at, vec, w, v);             \
+  }
+  if (O.px) {
+    ART_ST(O.px, px) ART_ST(O.py, py) ART_ST(O.pz, pz)
+    ART_ST(O.ux, ux) ART_ST(O.uy, uy) ART_ST(O.uz, uz)
+  }
+  if (O.path) ART_ST(O.path, path)
+  if (want_inc && O.inc) ART_ST(O.inc, inc)
+#undef ART_ST
+  if (O.alive) {
+    if (N == 2 && two && vec) {
+      *reinterpret_cast<uchar2*>(O.alive + at) = make_uchar2(w[0], w[N - 1]);
+    } else {
+      O.alive[at] = w[0];
+      if (N == 2 && two) O.alive[at + 1] = w[N - 1];
+    }
+  }
+}
+
+template <bool WANT_INC, bool WITH_DET, bool HAS_DEF>
+__global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a) {
+  constexpr int N = ART_RPT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ElemDev* sE = reinterpret_cast<ElemDev*>(smem_raw);
   double* sZ = reinterpret_cast<double*>(smem_raw + sizeof(ElemDev) * ART_MAX_ELEMENTS);
@@ -182,6 +246,13 @@ __global__ void __launch_bounds__(TPB, 2) trace_kernel(const TraceArgs a) {
   constexpr int PLEN = WITH_DET ? PLEN_FUSED : PLEN_TRACE;
   __shared__ double sRed[NWARP * PLEN];
   __shared__ ArtDetector sDet;
+#if ART_SMEM_ACC
+  __shared__ double sAcc[ART_CENTRAL_LEN][TPB];
+#define ART_ACC(j) sAcc[j][threadIdx.x]
+#else
+  double c[ART_CENTRAL_LEN];
+#define ART_ACC(j) c[j]
+#endif
 
   const int v = blockIdx.y;
   {
@@ -197,107 +268,95 @@ __global__ void __launch_bounds__(TPB, 2) trace_kernel(const TraceArgs a) {
       for (int i = threadIdx.x; i < (int)(sizeof(ArtDetector) / sizeof(double)); i += TPB) dd[i] = ds[i];
     }
   }
+#pragma unroll
+  for (int j = 0; j < ART_CENTRAL_LEN; ++j) ART_ACC(j) = 0.0;
   __syncthreads();
 
   const bool ignore_defects = (a.flags & ART_TRACE_IGNORE_DEFECTS) != 0;
   const long long n = a.n;
   const long long row = (long long)v * n;     // first output row of this variant
   const bool out_vec = (row & 1) == 0;
-  const long long npairs = (n + 1) >> 1;
+  const long long nitems = (n + N - 1) / N;
+  const int last = a.n_elements - 1;
 
-  double c[ART_CENTRAL_LEN];
-#pragma unroll
-  for (int j = 0; j < ART_CENTRAL_LEN; ++j) c[j] = 0.0;
   double m[WITH_DET ? ART_MOMENTS_LEN : 1];
   if constexpr (WITH_DET) moments_init(m);
 
-  for (long long pair = (long long)blockIdx.x * TPB + threadIdx.x; pair < npairs;
-       pair += (long long)gridDim.x * TPB) {
-    const long long i = pair << 1;
-    const bool two = i + 1 < n;
-    Ray r[RPT];
-    double w[RPT];
-    load_pair(a.in.px, i, two, r[0].px, r[1].px);
-    load_pair(a.in.py, i, two, r[0].py, r[1].py);
-    load_pair(a.in.pz, i, two, r[0].pz, r[1].pz);
-    load_pair(a.in.ux, i, two, r[0].ux, r[1].ux);
-    load_pair(a.in.uy, i, two, r[0].uy, r[1].uy);
-    load_pair(a.in.uz, i, two, r[0].uz, r[1].uz);
-    if (a.in.path) load_pair(a.in.path, i, two, r[0].path, r[1].path);
-    else r[0].path = r[1].path = 0.0;
-    if (a.in.inten) load_pair(a.in.inten, i, two, w[0], w[1]);
-    else w[0] = w[1] = 1.0;
-    r[0].alive = true;
-    r[1].alive = two;
-    if (a.in.alive) {
-      r[0].alive = a.in.alive[i] != 0;
-      if (two) r[1].alive = a.in.alive[i + 1] != 0;
-    }
-    r[0].inc = r[1].inc = ART_NAN;
+  for (long long item = (long long)blockIdx.x * TPB + threadIdx.x; item < nitems;
+       item += (long long)gridDim.x * TPB) {
+    const long long i = item * N;
+    const bool two = (N == 2) && (i + 1 < n);
+    Ray r[N];
+    double w[N];
+    {
+      double t[N];
+#define ART_LD(colp, field)                      \
+  load_rays<N>(colp, i, two, t);                 \
+  _Pragma("unroll") for (int q = 0; q < N; ++q) r[q].field = t[q];
+      ART_LD(a.in.px, px) ART_LD(a.in.py, py) ART_LD(a.in.pz, pz)
+      ART_LD(a.in.ux, ux) ART_LD(a.in.uy, uy) ART_LD(a.in.uz, uz)
+      if (a.in.path) {
+        ART_LD(a.in.path, path)
+      } else {
 #pragma unroll
-    for (int q = 0; q < RPT; ++q)
-      if (r[q].alive) c[ART_C_SW_IN] += w[q];
+        for (int q = 0; q < N; ++q) r[q].path = 0.0;
+      }
+#undef ART_LD
+      if (a.in.inten) {
+        load_rays<N>(a.in.inten, i, two, w);
+      } else {
+#pragma unroll
+        for (int q = 0; q < N; ++q) w[q] = 1.0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      r[q].alive = (q == 0) || two;
+      if (a.in.alive && r[q].alive) r[q].alive = a.in.alive[i + q] != 0;
+      r[q].inc = ART_NAN;
+    }
+    {
+      double win = 0.0;
+#pragma unroll
+      for (int q = 0; q < N; ++q)
+        if (r[q].alive) win += w[q];
+      ART_ACC(ART_C_SW_IN) += win;
+    }
 
     for (int k = 0; k < a.n_elements; ++k) {
+      const bool inc_here = WANT_INC && (k == last || a.has_hist);
 #pragma unroll
-      for (int q = 0; q < RPT; ++q)
-        if (r[q].alive) apply_element<WANT_INC>(sE[k], r[q], sZ, sZoff, ignore_defects);
-      if (a.has_hist) {
-        const BundleDev& H = a.hist[k];
-        const bool w0 = r[0].alive, w1 = r[1].alive;
-        if (H.px) {
-          store_pair(H.px, row + i, out_vec, w0, w1, r[0].px, r[1].px);
-          store_pair(H.py, row + i, out_vec, w0, w1, r[0].py, r[1].py);
-          store_pair(H.pz, row + i, out_vec, w0, w1, r[0].pz, r[1].pz);
-          store_pair(H.ux, row + i, out_vec, w0, w1, r[0].ux, r[1].ux);
-          store_pair(H.uy, row + i, out_vec, w0, w1, r[0].uy, r[1].uy);
-          store_pair(H.uz, row + i, out_vec, w0, w1, r[0].uz, r[1].uz);
-        }
-        if (H.path) store_pair(H.path, row + i, out_vec, w0, w1, r[0].path, r[1].path);
-        if (WANT_INC && H.inc) store_pair(H.inc, row + i, out_vec, w0, w1, r[0].inc, r[1].inc);
-        if (H.alive) {
-          H.alive[row + i] = w0;
-          if (two) H.alive[row + i + 1] = w1;
-        }
-      }
+      for (int q = 0; q < N; ++q)
+        if (r[q].alive) apply_element<WANT_INC, HAS_DEF>(sE[k], r[q], sZ, sZoff, ignore_defects, inc_here);
+      if (a.has_hist) store_bundle<N>(a.hist[k], row + i, out_vec, two, r, WANT_INC);
     }
+    if (a.has_out) store_bundle<N>(a.out, row + i, out_vec, two, r, WANT_INC);
 
-    const bool w0 = r[0].alive, w1 = r[1].alive;
-    if (a.has_out) {
-      const BundleDev& O = a.out;
-      if (O.px) {
-        store_pair(O.px, row + i, out_vec, w0, w1, r[0].px, r[1].px);
-        store_pair(O.py, row + i, out_vec, w0, w1, r[0].py, r[1].py);
-        store_pair(O.pz, row + i, out_vec, w0, w1, r[0].pz, r[1].pz);
-        store_pair(O.ux, row + i, out_vec, w0, w1, r[0].ux, r[1].ux);
-        store_pair(O.uy, row + i, out_vec, w0, w1, r[0].uy, r[1].uy);
-        store_pair(O.uz, row + i, out_vec, w0, w1, r[0].uz, r[1].uz);
-      }
-      if (O.path) store_pair(O.path, row + i, out_vec, w0, w1, r[0].path, r[1].path);
-      if (WANT_INC && O.inc) store_pair(O.inc, row + i, out_vec, w0, w1, r[0].inc, r[1].inc);
-      if (O.alive) {
-        if (two && out_vec) {
-          *reinterpret_cast<uchar2*>(O.alive + row + i) = make_uchar2(w0, w1);
-        } else {
-          O.alive[row + i] = w0;
-          if (two) O.alive[row + i + 1] = w1;
+    {
+      double s[ART_CENTRAL_LEN - 1];
+#pragma unroll
+      for (int j = 0; j < ART_CENTRAL_LEN - 1; ++j) s[j] = 0.0;
+      bool any = false;
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        if (!r[q].alive) continue;
+        any = true;
+        s[ART_C_SUX] += r[q].ux; s[ART_C_SUY] += r[q].uy; s[ART_C_SUZ] += r[q].uz;
+        s[ART_C_SPX] += r[q].px; s[ART_C_SPY] += r[q].py; s[ART_C_SPZ] += r[q].pz;
+        s[ART_C_SPATH] += r[q].path;
+        s[ART_C_N] += 1.0;
+        s[ART_C_SW_OUT] += w[q];
+        if constexpr (WITH_DET) {
+          const DetHit h = detector_ray(sDet, r[q]);
+          moments_add(m, h, sDet.l0, w[q]);
+          if (a.x_out) a.x_out[row + i + q] = h.x;
+          if (a.y_out) a.y_out[row + i + q] = h.y;
+          if (a.l_out) a.l_out[row + i + q] = h.L;
         }
       }
-    }
+      if (any) {
 #pragma unroll
-    for (int q = 0; q < RPT; ++q) {
-      if (!r[q].alive) continue;
-      c[ART_C_SUX] += r[q].ux; c[ART_C_SUY] += r[q].uy; c[ART_C_SUZ] += r[q].uz;
-      c[ART_C_SPX] += r[q].px; c[ART_C_SPY] += r[q].py; c[ART_C_SPZ] += r[q].pz;
-      c[ART_C_SPATH] += r[q].path;
-      c[ART_C_N] += 1.0;
-      c[ART_C_SW_OUT] += w[q];
-      if constexpr (WITH_DET) {
-        const DetHit h = detector_ray(sDet, r[q]);
-        moments_add(m, h, sDet.l0, w[q]);
-        if (a.x_out) a.x_out[row + i + q] = h.x;
-        if (a.y_out) a.y_out[row + i + q] = h.y;
-        if (a.l_out) a.l_out[row + i + q] = h.L;
+        for (int j = 0; j < ART_CENTRAL_LEN - 1; ++j) ART_ACC(j) += s[j];
       }
     }
   }
@@ -306,14 +365,18 @@ __global__ void __launch_bounds__(TPB, 2) trace_kernel(const TraceArgs a) {
   if constexpr (WITH_DET) {
     double all[PLEN_FUSED];
 #pragma unroll
-    for (int j = 0; j < ART_CENTRAL_LEN; ++j) all[j] = c[j];
+    for (int j = 0; j < ART_CENTRAL_LEN; ++j) all[j] = ART_ACC(j);
 #pragma unroll
     for (int j = 0; j < ART_MOMENTS_LEN; ++j) all[ART_CENTRAL_LEN + j] = m[j];
     block_reduce_row<PLEN_FUSED>(all, [](int j) { return j < ART_CENTRAL_LEN ? 0 : moment_op(j - ART_CENTRAL_LEN); },
                                  sRed, prow);
   } else {
-    block_reduce_row<PLEN_TRACE>(c, [](int) { return 0; }, sRed, prow);
+    double all[PLEN_TRACE];
+#pragma unroll
+    for (int j = 0; j < ART_CENTRAL_LEN; ++j) all[j] = ART_ACC(j);
+    block_reduce_row<PLEN_TRACE>(all, [](int) { return 0; }, sRed, prow);
   }
+#undef ART_ACC
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Kernel tuning helper: times the trace kernel of every library build under build/variants/ (and the
+in-tree one) on the BASELINE workloads.  Each build runs in its own process (ART_B200_LIB).
+
+    python tools/tune_variants.py            # driver: one subprocess per library
+    python tools/tune_variants.py --one      # worker
+"""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def worker():
+    import numpy as np
+    import torch
+    import bench
+    from attosecondraytracing_b200 import engine
+    import attosecondraytracing_b200.ModuleSource as msrc
+    res = {}
+    for wl, nrays in (("cfg2", 10_000_000), ("cfg3", 12_500_000), ("cfg5", 4_000_000), ("cfg4", 2_000_000)):
+        w = bench.load_workload(wl)
+        oes = bench.build_chain_elements(w)
+        sp = bench.source_properties(w, nrays)
+        src = msrc.synthetic_source(sp, device="cuda")
+        chain = engine.DeviceChain(oes)
+        for inc in (True, False):
+            for _ in range(3):
+                chain.trace(src, want_incidence=inc, want_central=True)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                chain.trace(src, want_incidence=inc, want_central=True)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            res[f"{wl}_inc{int(inc)}_ms"] = round(float(np.median(ts)), 4)
+        # detector kernel on the stored bundle
+        outs, central = chain.trace(src, want_incidence=False)
+        det = chain.autoplace(central, w["scene_spec"]["detector_distance"])
+        ts = []
+        for _ in range(8):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            chain.moments(outs[0], det, intensity=src.col("intensity"))
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        res[f"{wl}_det_ms"] = round(float(np.median(ts)), 4)
+        chain.close()
+        del src, outs
+        torch.cuda.empty_cache()
+    print("RESULT " + json.dumps(res), flush=True)
+
+
+def main():
+    libs = sorted(glob.glob(os.path.join(ROOT, "build", "variants", "*.so")))
+    libs.append(os.path.join(ROOT, "attosecondraytracing_b200", "libart_b200.so"))
+    for lib in libs:
+        env = dict(os.environ, ART_B200_LIB=lib)
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=env, capture_output=True, text=True)
+        line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
+        print(os.path.basename(lib), line[0][7:] if line else "FAILED " + out.stderr[-400:], flush=True)
+
+
+if __name__ == "__main__":
+    worker() if "--one" in sys.argv else main()
