@@ -88,15 +88,15 @@ def test_detector_and_statistics_match_reference(name):
     assert np.max(np.abs(xy - g["det_xy_centre"])) <= ptol
     dl = delays[idx].cpu().numpy()
     assert np.max(np.abs(dl - g["det_delays"])) <= DELAY_TOL_FS, np.max(np.abs(dl - g["det_delays"]))
-    assert abs(sr["SpotSizeSD"] - g["SpotSizeSD"]) <= 1e-9 and abs(sr["DurationSD"] - g["DurationSD"]) <= DELAY_TOL_FS
+    assert abs(sr["SpotSizeSD"] - g["SpotSizeSD"]) <= ptol and abs(sr["DurationSD"] - g["DurationSD"]) <= DELAY_TOL_FS
     # statistics
-    assert abs(s["SpotSizeSD"] - g["SpotSizeSD"]) <= 1e-9
+    assert abs(s["SpotSizeSD"] - g["SpotSizeSD"]) <= ptol
     assert abs(s["DurationSD"] - g["DurationSD"]) <= DELAY_TOL_FS
     assert abs(s["ETransmission"] - g["ETransmission"]) <= 1e-9
-    assert abs(s["SpotSizeSD_w"] - g["SpotSizeSD_w"]) <= 1e-9
+    assert abs(s["SpotSizeSD_w"] - g["SpotSizeSD_w"]) <= ptol
     assert abs(s["DurationSD_w"] - g["DurationSD_w"]) <= DELAY_TOL_FS
     assert abs(s["NA"] - g["NA"]) <= 10 * dir_tol(name)  # sin(max angle to the mean direction)
-    assert abs(s["Diameter"] - g["Diameter"]) <= 1e-9
+    assert abs(s["Diameter"] - g["Diameter"]) <= 2 * ptol
     # the fused trace+detector kernel and the sweep entry point give the same moments
     mom2, central2, _, _, _ = chain.trace_detect(src, det, ignore_defects=g.ignore_defects)
     mom3, central3, det3 = chain.sweep(src, g.spec["detector_distance"], ignore_defects=g.ignore_defects)
