@@ -124,7 +124,9 @@ class RayBundle:
         if storage is None:
             storage = torch.empty((len(self._names), pad), dtype=torch.float64, device=self.device)
         self._storage = storage  # rows are 256-byte aligned -> 128-bit column accesses are legal
-        self.alive = torch.ones(pad, dtype=torch.uint8, device=self.device)[: self.n] if with_alive else None
+        # the trace kernel writes every ray's flag, so no initialisation pass is needed on the device
+        self.alive = ((torch.empty if self.device.type == "cuda" else torch.ones)(pad, dtype=torch.uint8, device=self.device)[: self.n]
+                      if with_alive else None)
         self._index = None  # cached indices of the alive rays
         self.version = 0    # bumped by whoever rewrites the columns (cache key of OpticalChain)
 

@@ -59,6 +59,7 @@ struct ArtChain {
   int ztab_len = 0;
   size_t smem_bytes = 0;
   bool has_defects = false;
+  int surfs = 0;                 // SURFS_* class of the chain's surfaces
   double* d_partials = nullptr;
   size_t partial_rows = 0;
   double* d_central = nullptr;   // n_variants x ART_CENTRAL_LEN scratch (sweep, host run)
@@ -232,10 +233,20 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
   c->smem_bytes = sizeof(ElemDev) * ART_MAX_ELEMENTS + sizeof(double) * ztab.size() + sizeof(int) * zoff.size();
   c->smem_bytes = (c->smem_bytes + 15) & ~size_t(15);
   if (c->smem_bytes > 200 * 1024) return bail(ART_E_UNSUPPORTED, "Zernike tables exceed 200 KB of shared memory");
-  CK(allow_smem(trace_kernel<true, false, true>, c->smem_bytes));
-  CK(allow_smem(trace_kernel<false, false, true>, c->smem_bytes));
-  CK(allow_smem(trace_kernel<true, true, true>, c->smem_bytes));
-  CK(allow_smem(trace_kernel<false, true, true>, c->smem_bytes));
+  CK(allow_smem(trace_kernel<true, false, true, SURFS_ANY>, c->smem_bytes));
+  CK(allow_smem(trace_kernel<false, false, true, SURFS_ANY>, c->smem_bytes));
+  CK(allow_smem(trace_kernel<true, true, true, SURFS_ANY>, c->smem_bytes));
+  CK(allow_smem(trace_kernel<false, true, true, SURFS_ANY>, c->smem_bytes));
+  {
+    bool tor = false, quad = false;
+    for (int k = 0; k < n_elements; ++k) {
+      const int sf = elements[k].surface;
+      tor = tor || sf == ART_SURF_TOROIDAL;
+      quad = quad || (sf == ART_SURF_SPHERICAL || sf == ART_SURF_PARABOLIC || sf == ART_SURF_ELLIPSOIDAL ||
+                      sf == ART_SURF_CYLINDRICAL);
+    }
+    c->surfs = (tor && quad) ? SURFS_ANY : (tor ? SURFS_TOROID : SURFS_QUADRIC);
+  }
 
   CK(cudaMalloc(&c->d_elems, h.size() * sizeof(ElemDev)));
   CK(cudaMemcpy(c->d_elems, h.data(), h.size() * sizeof(ElemDev), cudaMemcpyHostToDevice));
@@ -315,10 +326,13 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
   if ((size_t)bpv * n_variants > c->partial_rows) return fail(ART_E_INVALID, "internal: partial buffer too small");
   const dim3 grid(bpv, n_variants);
   const size_t sm = c->smem_bytes;
-#define ART_TRACE_LAUNCH(INC, DET)                                                        \
-  do {                                                                                    \
-    if (c->has_defects) trace_kernel<INC, DET, true><<<grid, TPB, sm, st>>>(a);           \
-    else trace_kernel<INC, DET, false><<<grid, TPB, sm, st>>>(a);                         \
+  // Zernike chains run the general kernel; defect-free chains one specialised for their surface class
+#define ART_TRACE_LAUNCH(INC, DET)                                                                      \
+  do {                                                                                                  \
+    if (c->has_defects) trace_kernel<INC, DET, true, SURFS_ANY><<<grid, TPB, sm, st>>>(a);              \
+    else if (c->surfs == SURFS_TOROID) trace_kernel<INC, DET, false, SURFS_TOROID><<<grid, TPB, sm, st>>>(a);   \
+    else if (c->surfs == SURFS_QUADRIC) trace_kernel<INC, DET, false, SURFS_QUADRIC><<<grid, TPB, sm, st>>>(a); \
+    else trace_kernel<INC, DET, false, SURFS_ANY><<<grid, TPB, sm, st>>>(a);                            \
   } while (0)
   if (det) {
     if (want_inc) ART_TRACE_LAUNCH(true, true);

@@ -173,6 +173,7 @@ __device__ __forceinline__ void moments_add(double (&m)[ART_MOMENTS_LEN], const 
 //   WANT_INC  compute Ray.incidence
 //   WITH_DET  also evaluate the detector of this variant and accumulate its moments (K2 fused)
 //   HAS_DEF   the chain carries Zernike defects (otherwise that code and its registers are compiled out)
+//   SURFS     surface classes compiled in (SURFS_ANY / SURFS_TOROID / SURFS_QUADRIC; planes and masks always)
 // Build-time tunables (measured on B200): ART_RPT rays per thread (2 = 128-bit column
 // accesses), ART_MINB resident blocks per SM asked of the register allocator, ART_SMEM_ACC keeps
 // the per-thread central sums in shared memory instead of registers.
@@ -186,6 +187,10 @@ __device__ __forceinline__ void moments_add(double (&m)[ART_MOMENTS_LEN], const 
 #ifndef ART_SMEM_ACC
 #define ART_SMEM_ACC 1
 #endif
+#ifndef ART_PREFETCH
+#define ART_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 static_assert(ART_RPT == 1 || ART_RPT == 2, "ART_RPT must be 1 or 2");
 static_assert(RPT == 2, "column helpers are written for pairs");
 
@@ -236,9 +241,12 @@ __device__ __forceinline__ void store_bundle(const BundleDev& O, long long at, b
   }
 }
 
-template <bool WANT_INC, bool WITH_DET, bool HAS_DEF>
+template <bool WANT_INC, bool WITH_DET, bool HAS_DEF, int SURFS>
 __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a) {
   constexpr int N = ART_RPT;
+  // two rays in lock-step (lane pack D2) unless the chain carries Zernike defects, whose evaluation
+  // would not fit two lanes in the register file
+  constexpr bool PACK = (N == 2) && !HAS_DEF;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ElemDev* sE = reinterpret_cast<ElemDev*>(smem_raw);
   double* sZ = reinterpret_cast<double*>(smem_raw + sizeof(ElemDev) * ART_MAX_ELEMENTS);
@@ -286,6 +294,16 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
        item += (long long)gridDim.x * TPB) {
     const long long i = item * N;
     const bool two = (N == 2) && (i + 1 < n);
+#if ART_PREFETCH
+    {  // pull the columns of this thread's NEXT rays into L2 while this pair is traced
+      const long long inext = (item + (long long)gridDim.x * TPB) * N;
+      if (inext < n) {
+        prefetch_l2(a.in.px + inext); prefetch_l2(a.in.py + inext); prefetch_l2(a.in.pz + inext);
+        prefetch_l2(a.in.ux + inext); prefetch_l2(a.in.uy + inext); prefetch_l2(a.in.uz + inext);
+        if (a.in.inten) prefetch_l2(a.in.inten + inext);
+      }
+    }
+#endif
     Ray r[N];
     double w[N];
     {
@@ -323,12 +341,26 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
       ART_ACC(ART_C_SW_IN) += win;
     }
 
-    for (int k = 0; k < a.n_elements; ++k) {
-      const bool inc_here = WANT_INC && (k == last || a.has_hist);
+    if constexpr (PACK) {
+      RayT<D2> pr = pack_rays(r[0], r[N - 1]);
+      for (int k = 0; k < a.n_elements; ++k) {
+        const bool inc_here = WANT_INC && (k == last || a.has_hist);
+        if (any(pr.alive)) apply_element<WANT_INC, HAS_DEF, SURFS, D2>(sE[k], pr, sZ, sZoff, ignore_defects, inc_here);
+        if (a.has_hist) {
+          unpack_rays(pr, r[0], r[N - 1]);
+          store_bundle<N>(a.hist[k], row + i, out_vec, two, r, WANT_INC);
+        }
+      }
+      unpack_rays(pr, r[0], r[N - 1]);
+    } else {
+      for (int k = 0; k < a.n_elements; ++k) {
+        const bool inc_here = WANT_INC && (k == last || a.has_hist);
 #pragma unroll
-      for (int q = 0; q < N; ++q)
-        if (r[q].alive) apply_element<WANT_INC, HAS_DEF>(sE[k], r[q], sZ, sZoff, ignore_defects, inc_here);
-      if (a.has_hist) store_bundle<N>(a.hist[k], row + i, out_vec, two, r, WANT_INC);
+        for (int q = 0; q < N; ++q)
+          if (r[q].alive)
+            apply_element<WANT_INC, HAS_DEF, SURFS, double>(sE[k], r[q], sZ, sZoff, ignore_defects, inc_here);
+        if (a.has_hist) store_bundle<N>(a.hist[k], row + i, out_vec, two, r, WANT_INC);
+      }
     }
     if (a.has_out) store_bundle<N>(a.out, row + i, out_vec, two, r, WANT_INC);
 
@@ -390,7 +422,10 @@ struct DetArgs {
   double* partials;  // [variant][block][PLEN_DET]
 };
 
-__global__ void __launch_bounds__(TPB, 2) detector_kernel(const DetArgs a) {
+#ifndef ART_DET_MINB
+#define ART_DET_MINB 2
+#endif
+__global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetArgs a) {
   __shared__ double sRed[NWARP * PLEN_DET];
   __shared__ ArtDetector sDet;
   const int v = blockIdx.y;
@@ -462,16 +497,31 @@ __global__ void __launch_bounds__(TPB) fold_kernel(const double* __restrict__ pa
   const int moff = mode == 1 ? ART_CENTRAL_LEN : 0;  // where the moments start in a row
   const double* base = partials + (size_t)v * nblocks * plen;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int j = 0; j < plen; ++j) {
-    const int op = (mode == 0 || (mode == 1 && j < ART_CENTRAL_LEN)) ? 0 : moment_op(j - moff);
-    double x = op == 0 ? 0.0 : (op == 1 ? CUDART_INF : -CUDART_INF);
-    for (int b = threadIdx.x; b < nblocks; b += TPB) x = red_any(op, x, base[(size_t)b * plen + j]);
+  auto op_of = [&](int j) { return (mode == 0 || (mode == 1 && j < ART_CENTRAL_LEN)) ? 0 : moment_op(j - moff); };
+  // each thread folds whole rows b = tid, tid + TPB, ... (all columns of a row are independent loads)
+  double acc[PLEN_FUSED];
+#pragma unroll
+  for (int j = 0; j < PLEN_FUSED; ++j) {
+    const int op = j < plen ? op_of(j) : 0;
+    acc[j] = op == 0 ? 0.0 : (op == 1 ? CUDART_INF : -CUDART_INF);
+  }
+  for (int b = threadIdx.x; b < nblocks; b += TPB) {
+    const double* row = base + (size_t)b * plen;
+#pragma unroll
+    for (int j = 0; j < PLEN_FUSED; ++j)
+      if (j < plen) acc[j] = red_any(op_of(j), acc[j], row[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < PLEN_FUSED; ++j) {
+    if (j >= plen) break;
+    const int op = op_of(j);
+    double x = acc[j];
     for (int o = 16; o > 0; o >>= 1) x = red_any(op, x, __shfl_xor_sync(0xffffffffu, x, o));
     if (lane == 0) sRed[warp * plen + j] = x;
   }
   __syncthreads();
   for (int j = threadIdx.x; j < plen; j += TPB) {
-    const int op = (mode == 0 || (mode == 1 && j < ART_CENTRAL_LEN)) ? 0 : moment_op(j - moff);
+    const int op = op_of(j);
     double x = sRed[j];
     for (int w = 1; w < NWARP; ++w) x = red_any(op, x, sRed[w * plen + j]);
     if (mode == 0) {

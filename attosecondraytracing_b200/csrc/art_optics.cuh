@@ -1,0 +1,542 @@
+// art_optics.cuh -- the per-ray optics of libart_b200, written once for a "lane pack" type T:
+//   T = double : one ray per thread (also what tests/hostcheck runs on the host)
+//   T = D2     : two rays per thread advanced in lock-step.  Every per-ray decision is a select
+//                on a lane mask, loops run until both lanes are done (finished lanes are frozen,
+//                so a ray's result never depends on its partner), and the two independent
+//                dependency chains give the FP64 pipe twice the instruction-level parallelism.
+// Only warp-uniform quantities (surface / support kind, Zernike order) steer real branches.
+// The reference semantics each function reproduces are cited as file:line of the reference
+// repository (ART v0.93).
+#pragma once
+
+namespace art {
+
+// ---------------------------------------------------------------------------------------------
+// lane packs
+// ---------------------------------------------------------------------------------------------
+struct D2 {
+  double a, b;
+};
+struct B2 {
+  bool a, b;
+};
+template <class T>
+struct MaskOf {
+  typedef bool type;
+};
+template <>
+struct MaskOf<D2> {
+  typedef B2 type;
+};
+
+ART_HD D2 operator+(D2 x, D2 y) { return {x.a + y.a, x.b + y.b}; }
+ART_HD D2 operator-(D2 x, D2 y) { return {x.a - y.a, x.b - y.b}; }
+ART_HD D2 operator*(D2 x, D2 y) { return {x.a * y.a, x.b * y.b}; }
+ART_HD D2 operator+(D2 x, double y) { return {x.a + y, x.b + y}; }
+ART_HD D2 operator-(D2 x, double y) { return {x.a - y, x.b - y}; }
+ART_HD D2 operator*(D2 x, double y) { return {x.a * y, x.b * y}; }
+ART_HD D2 operator+(double x, D2 y) { return {x + y.a, x + y.b}; }
+ART_HD D2 operator-(double x, D2 y) { return {x - y.a, x - y.b}; }
+ART_HD D2 operator*(double x, D2 y) { return {x * y.a, x * y.b}; }
+ART_HD D2 operator-(D2 x) { return {-x.a, -x.b}; }
+ART_HD B2 operator<(D2 x, D2 y) { return {x.a < y.a, x.b < y.b}; }
+ART_HD B2 operator>(D2 x, D2 y) { return {x.a > y.a, x.b > y.b}; }
+ART_HD B2 operator<=(D2 x, D2 y) { return {x.a <= y.a, x.b <= y.b}; }
+ART_HD B2 operator>=(D2 x, D2 y) { return {x.a >= y.a, x.b >= y.b}; }
+ART_HD B2 operator==(D2 x, D2 y) { return {x.a == y.a, x.b == y.b}; }
+ART_HD B2 operator<(D2 x, double y) { return {x.a < y, x.b < y}; }
+ART_HD B2 operator>(D2 x, double y) { return {x.a > y, x.b > y}; }
+ART_HD B2 operator<=(D2 x, double y) { return {x.a <= y, x.b <= y}; }
+ART_HD B2 operator>=(D2 x, double y) { return {x.a >= y, x.b >= y}; }
+ART_HD B2 operator&(B2 x, B2 y) { return {x.a && y.a, x.b && y.b}; }
+ART_HD B2 operator|(B2 x, B2 y) { return {x.a || y.a, x.b || y.b}; }
+ART_HD B2 operator!(B2 x) { return {!x.a, !x.b}; }
+
+// the same vocabulary for one lane
+ART_HD double mfma(double x, double y, double z) { return fma(x, y, z); }
+ART_HD D2 mfma(D2 x, D2 y, D2 z) { return {fma(x.a, y.a, z.a), fma(x.b, y.b, z.b)}; }
+ART_HD D2 mfma(double x, D2 y, D2 z) { return {fma(x, y.a, z.a), fma(x, y.b, z.b)}; }
+ART_HD D2 mfma(D2 x, double y, D2 z) { return {fma(x.a, y, z.a), fma(x.b, y, z.b)}; }
+ART_HD D2 mfma(D2 x, D2 y, double z) { return {fma(x.a, y.a, z), fma(x.b, y.b, z)}; }
+ART_HD D2 mfma(double x, D2 y, double z) { return {fma(x, y.a, z), fma(x, y.b, z)}; }
+ART_HD D2 mfma(D2 x, double y, double z) { return {fma(x.a, y, z), fma(x.b, y, z)}; }
+ART_HD double sel(bool m, double x, double y) { return m ? x : y; }
+ART_HD D2 sel(B2 m, D2 x, D2 y) { return {m.a ? x.a : y.a, m.b ? x.b : y.b}; }
+ART_HD D2 sel(B2 m, D2 x, double y) { return {m.a ? x.a : y, m.b ? x.b : y}; }
+ART_HD D2 sel(B2 m, double x, D2 y) { return {m.a ? x : y.a, m.b ? x : y.b}; }
+ART_HD D2 sel(B2 m, double x, double y) { return {m.a ? x : y, m.b ? x : y}; }
+ART_HD bool any(bool m) { return m; }
+ART_HD bool any(B2 m) { return m.a || m.b; }
+ART_HD bool mand(bool x, bool y) { return x && y; }
+ART_HD B2 mand(B2 x, B2 y) { return x & y; }
+ART_HD B2 mand(B2 x, bool y) { return {x.a && y, x.b && y}; }
+ART_HD bool mor(bool x, bool y) { return x || y; }
+ART_HD B2 mor(B2 x, B2 y) { return x | y; }
+ART_HD bool mnot(bool x) { return !x; }
+ART_HD B2 mnot(B2 x) { return !x; }
+ART_HD double mabs(double x) { return fabs(x); }
+ART_HD D2 mabs(D2 x) { return {fabs(x.a), fabs(x.b)}; }
+ART_HD double mcopysign(double x, double y) { return copysign(x, y); }
+ART_HD D2 mcopysign(D2 x, D2 y) { return {copysign(x.a, y.a), copysign(x.b, y.b)}; }
+ART_HD D2 fdiv(D2 x, D2 y) { return {fdiv(x.a, y.a), fdiv(x.b, y.b)}; }
+ART_HD D2 fdiv(double x, D2 y) { return {fdiv(x, y.a), fdiv(x, y.b)}; }
+ART_HD D2 frsqrt(D2 x) { return {frsqrt(x.a), frsqrt(x.b)}; }
+ART_HD D2 fsqrt(D2 x) { return {fsqrt(x.a), fsqrt(x.b)}; }
+template <class T>
+ART_HD T splat(double x);
+template <>
+ART_HD double splat<double>(double x) { return x; }
+template <>
+ART_HD D2 splat<D2>(double x) { return {x, x}; }
+
+// 1/d to ~2^-46: MUFU.RCP64H seed (2^-23) + one Newton step.  Only used for Newton CORRECTIONS of the
+// root search, which are self-correcting; the converged root does not depend on the step's last bits.
+ART_HD double fast_rcp(double d) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  return fma(r, fma(-d, r, 1.0), r);
+#else
+  return 1.0 / d;
+#endif
+}
+ART_HD D2 fast_rcp(D2 d) { return {fast_rcp(d.a), fast_rcp(d.b)}; }
+
+// A ray (or a pair of rays) in registers.
+template <class T>
+struct RayT {
+  T px, py, pz, ux, uy, uz, path, inc;
+  typename MaskOf<T>::type alive;
+};
+typedef RayT<double> Ray;
+
+ART_HD RayT<D2> pack_rays(const Ray& p, const Ray& q) {
+  RayT<D2> r;
+  r.px = {p.px, q.px}; r.py = {p.py, q.py}; r.pz = {p.pz, q.pz};
+  r.ux = {p.ux, q.ux}; r.uy = {p.uy, q.uy}; r.uz = {p.uz, q.uz};
+  r.path = {p.path, q.path}; r.inc = {p.inc, q.inc};
+  r.alive = {p.alive, q.alive};
+  return r;
+}
+ART_HD void unpack_rays(const RayT<D2>& r, Ray& p, Ray& q) {
+  p.px = r.px.a; p.py = r.py.a; p.pz = r.pz.a; p.ux = r.ux.a; p.uy = r.uy.a; p.uz = r.uz.a;
+  p.path = r.path.a; p.inc = r.inc.a; p.alive = r.alive.a;
+  q.px = r.px.b; q.py = r.py.b; q.pz = r.pz.b; q.ux = r.ux.b; q.uy = r.uy.b; q.uz = r.uz.b;
+  q.path = r.path.b; q.inc = r.inc.b; q.alive = r.alive.b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// supports: `_IncludeSupport`, ART/ModuleSupport.py:68,151,228,322,431 (all comparisons inclusive)
+//   ROUND            ap = {R^2}
+//   ROUND_HOLE       ap = {R^2, Rh^2, cx, cy}
+//   RECT             ap = {|X/2|, |Y/2|}
+//   RECT_HOLE        ap = {|X/2|, |Y/2|, Rh^2, cx, cy}
+//   RECT_RECT_HOLE   ap = {|X/2|, |Y/2|, |hX/2|, |hY/2|, cx, cy}
+// NaN coordinates compare false, as in numpy.
+// ---------------------------------------------------------------------------------------------
+template <class T>
+ART_HD typename MaskOf<T>::type in_support(const ElemDev& E, T x, T y) {
+  x = x - E.soff[0];
+  y = y - E.soff[1];
+  switch (E.support) {
+    case ART_SUPP_ROUND:
+      return mfma(x, x, y * y) <= E.ap[0];
+    case ART_SUPP_ROUND_HOLE: {
+      const T hx = x - E.ap[2], hy = y - E.ap[3];
+      return mand(mfma(x, x, y * y) <= E.ap[0], mnot(mfma(hx, hx, hy * hy) <= E.ap[1]));
+    }
+    case ART_SUPP_RECT:
+      return mand(mabs(x) <= E.ap[0], mabs(y) <= E.ap[1]);
+    case ART_SUPP_RECT_HOLE: {
+      const T hx = x - E.ap[3], hy = y - E.ap[4];
+      return mand(mand(mabs(x) <= E.ap[0], mabs(y) <= E.ap[1]), mnot(mfma(hx, hx, hy * hy) <= E.ap[2]));
+    }
+    default: {  // ART_SUPP_RECT_RECT_HOLE
+      const T hx = x - E.ap[4], hy = y - E.ap[5];
+      return mand(mand(mabs(x) <= E.ap[0], mabs(y) <= E.ap[1]),
+                  mnot(mand(mabs(hx) <= E.ap[2], mabs(hy) <= E.ap[3])));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// real roots of a t^2 + b t + c as np.roots would give them (ART/ModuleGeometry.py:80-91), in the
+// cancellation-free form: q = -(b + sgn(b) sqrt(D))/2, t1 = q/a, t2 = c/q.
+// a == 0 degrades to the single root -c/b (t1 is not finite and fails every later test), D < 0 to
+// none (both NaN).
+// ---------------------------------------------------------------------------------------------
+template <class T>
+ART_HD void solve_quadratic(T a, T b, T c, T& t1, T& t2) {
+  const T w = 4.0 * a * c;
+  const T e = mfma(-4.0 * a, c, w);  // rounding error of w
+  const T f = mfma(b, b, -w);
+  const T disc = f + e;
+  const typename MaskOf<T>::type ok = disc >= 0.0;
+  const T q = -0.5 * (b + mcopysign(fsqrt(sel(ok, disc, 0.0)), b));
+  t1 = sel(ok, fdiv(q, a), ART_NAN);
+  t2 = sel(ok, fdiv(c, q), ART_NAN);
+}
+
+// Candidate rule shared by the curved mirrors: t > 1e-12 (KeepPositiveSolution,
+// ModuleGeometry.py:110-120), surface-side test, support test; one candidate -> it, two -> the
+// nearer one (_IntersectionRayMirror ART/ModuleMirror.py:27-38, ClosestPoint ModuleGeometry.py:138-147).
+template <bool SIDE_Z_NEG, class T>
+ART_HD T pick_candidate(const ElemDev& E, const RayT<T>& r, T t1, T t2, double zlim) {
+  typedef typename MaskOf<T>::type M;
+  M c1 = t1 > 1e-12, c2 = t2 > 1e-12;
+  {
+    const T x = mfma(t1, r.ux, r.px), y = mfma(t1, r.uy, r.py), z = mfma(t1, r.uz, r.pz);
+    if (SIDE_Z_NEG) c1 = mand(c1, z < zlim);
+    c1 = mand(c1, in_support(E, x, y));
+  }
+  {
+    const T x = mfma(t2, r.ux, r.px), y = mfma(t2, r.uy, r.py), z = mfma(t2, r.uz, r.pz);
+    if (SIDE_Z_NEG) c2 = mand(c2, z < zlim);
+    c2 = mand(c2, in_support(E, x, y));
+  }
+  const T nearer = sel(t1 < t2, t1, t2);
+  return sel(mand(c1, c2), nearer, sel(c1, t1, sel(c2, t2, ART_NAN)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Toroid, ART/ModuleMirror.py:443-478: (sqrt(x^2+z^2) - R)^2 + y^2 = r^2.
+//
+// The reference solves the expanded quartic with np.roots and keeps roots with t > 1e-12,
+// z < -R and (x,y) on the support.  B200 path: every such point lies on the OUTER sheet
+// (z < -R => rho > R), which is part of the boundary of the convex solid {dist(., disk of radius
+// R in y=0) <= r}.  Along the ray,  F(t) = max(rho-R,0)^2 + y^2 - r^2  is therefore CONVEX with at
+// most two zeros ta <= tb, and Newton's iteration on a convex function converges monotonically
+// from outside the root interval.  tb is found from the right (start: hit with the tangent plane
+// z = -(R+r), else a provably-right start), ta from t = 0 when the origin lies outside the solid.
+// F keeps full relative accuracy near the surface (no s^2 - 4R^2 rho^2 cancellation).
+// ---------------------------------------------------------------------------------------------
+template <class T>
+struct TorEval {
+  T F, dF;
+};
+template <class T>
+ART_HD TorEval<T> tor_eval(const RayT<T>& r, T t, double R, double r2) {
+  const T x = mfma(t, r.ux, r.px), y = mfma(t, r.uy, r.py), z = mfma(t, r.uz, r.pz);
+  const T s = mfma(x, x, z * z);
+  const T inv = frsqrt(s);
+  const T rho = s * inv;
+  const T q = rho - R;
+  const typename MaskOf<T>::type outer = q > 0.0;
+  const T qq = sel(outer, q, 0.0);
+  TorEval<T> e;
+  e.F = mfma(qq, qq, mfma(y, y, -r2));
+  e.dF = 2.0 * mfma(qq * inv, mfma(x, r.ux, z * r.uz), y * r.uy);
+  return e;
+}
+
+// Newton from outside the root interval of the convex F.  DIR = +1: largest zero, approached from
+// the right (needs F' > 0 on the way); DIR = -1: smallest zero from the left (F' < 0).
+// A lane stops once the NEXT correction would be below rounding level: F'' <= 2 |u|^2 = 2, so the
+// step after dt is at most dt^2 / |F'|; at the noise floor of F (~ eps r^2) dt itself is ~1e-13 mm
+// and the test holds as well.  Lanes that are done are frozen; a lane that walks past the minimum of
+// F without meeting a zero (the line misses the solid) or needs more than 64 steps yields NaN.
+template <int DIR, class T>
+ART_HD T tor_newton(const RayT<T>& r, T t, TorEval<T> e, double R, double r2, double scale,
+                    typename MaskOf<T>::type active) {
+  typedef typename MaskOf<T>::type M;
+  T result = splat<T>(ART_NAN);
+  M todo = active;
+  for (int it = 0; it < 64 && any(todo); ++it) {
+    const T slope = DIR > 0 ? e.dF : -e.dF;
+    const M good = slope > 0.0;
+    const T dt = e.F * fast_rcp(e.dF);
+    const T tn = t - dt;
+    const M conv = mand(good, dt * dt <= 2e-16 * (mabs(tn) + scale) * slope);
+    result = sel(mand(todo, conv), tn, result);
+    todo = mand(todo, mand(good, mnot(conv)));
+    t = sel(todo, tn, t);
+    if (any(todo)) e = tor_eval(r, t, R, r2);
+  }
+  return result;
+}
+
+template <class T>
+ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>::type act) {
+  typedef typename MaskOf<T>::type M;
+  const double R = E.sp[0], rr = E.sp[1], r2 = E.sp[2];
+  // start for the right root: the tangent plane z = -(R+r) lies outside the solid
+  T t0 = fdiv(-(R + rr) - r.pz, r.uz);
+  TorEval<T> e0 = tor_eval(r, t0, R, r2);
+  const M fine = mand(mand(t0 > 0.0, e0.F >= 0.0), mand(e0.dF > 0.0, t0 < 1e300));
+  if (any(mand(act, mnot(fine)))) {
+    // beyond closest approach to the axis point by more than R + r the solid is behind us
+    const T tc = -mfma(r.px, r.ux, mfma(r.py, r.uy, r.pz * r.uz));
+    t0 = sel(fine, t0, tc + 1.0009765625 * (R + rr));
+    const TorEval<T> e1 = tor_eval(r, t0, R, r2);
+    e0.F = sel(fine, e0.F, e1.F);
+    e0.dF = sel(fine, e0.dF, e1.dF);
+  }
+  const T tb = tor_newton<+1>(r, t0, e0, R, r2, rr, act);
+  T ta = splat<T>(ART_NAN);
+  const TorEval<T> o = tor_eval(r, splat<T>(0.0), R, r2);
+  const M outside = o.F > 0.0;  // origin outside the solid: a second, nearer root may exist
+  const M away = mand(outside, mnot(o.dF < 0.0));  // ... but not if we move away from the solid
+  if (any(mand(act, mand(outside, mnot(away))))) {
+    ta = tor_newton<-1>(r, splat<T>(0.0), o, R, r2, rr, mand(act, mand(outside, mnot(away))));
+  }
+  const T t = pick_candidate<true>(E, r, ta, tb, -R);
+  return sel(away, ART_NAN, t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Zernike defect, ART/ModuleDefects.py:149-177.  The reference evaluates Andersen's Cartesian
+// recurrences for ALL (n,m) up to max_order with Python lists.  Device path: the same polynomials
+// written as  Z = Q_k^l(s) * {C_l, S_l}(x,y),  s = x^2+y^2,  C_l + i S_l = (x + i y)^l,
+// Q_k^l(s) = R_{l+2k}^l(rho)/rho^l = (-1)^k P_k^{(l,0)}(1-2s)  (Jacobi), advanced in k by a
+// three-term recurrence -> O(1) registers per ray for any order.  Table (host-built, smem):
+//   zt[0] = radius R (= Support._CircumCirc()), zt[1] = max order N, then for l = 0..N,
+//   k = 0..(N-l)/2: {alpha, beta, gamma, c_cos, c_sin} with
+//   Q_k = (alpha s + beta) Q_{k-1} - gamma Q_{k-2};  c_cos / c_sin = coefficients of the reference
+//   keys (n, (n+l)/2) / (n, (n-l)/2), n = l + 2k.
+// Returns value and Cartesian gradient (already divided by R where the reference does).
+// ---------------------------------------------------------------------------------------------
+template <bool WANT_VALUE, bool WANT_GRAD, class T>
+ART_HD void zernike_eval(const double* __restrict__ zt, T X, T Y, T& val, T& gx, T& gy) {
+  const double Rz = zt[0];
+  const int N = (int)zt[1];
+  const double iR = fdiv(1.0, Rz);
+  const T x = X * iR, y = Y * iR;
+  const T s = mfma(x, x, y * y);
+  const double* rec = zt + 2;
+  T Cl = splat<T>(1.0), Sl = splat<T>(0.0), Cm = splat<T>(0.0), Sm = splat<T>(0.0);  // (x+iy)^l, (x+iy)^(l-1)
+  T v = splat<T>(0.0), dx = splat<T>(0.0), dy = splat<T>(0.0);
+  for (int l = 0; l <= N; ++l) {
+    const int K = (N - l) >> 1;
+    T Q = splat<T>(1.0), Qp = splat<T>(0.0), dQ = splat<T>(0.0), dQp = splat<T>(0.0);
+    T A = splat<T>(rec[3]), B = splat<T>(rec[4]), dA = splat<T>(0.0), dB = splat<T>(0.0);
+    rec += 5;
+    for (int k = 1; k <= K; ++k) {
+      const double al = rec[0], be = rec[1], ga = rec[2], cc = rec[3], cs = rec[4];
+      rec += 5;
+      const T lin = mfma(al, s, be);
+      const T Qn = mfma(lin, Q, -ga * Qp);
+      if (WANT_GRAD) {
+        const T dQn = mfma(al, Q, mfma(lin, dQ, -ga * dQp));
+        dQp = dQ;
+        dQ = dQn;
+        dA = mfma(cc, dQn, dA);
+        dB = mfma(cs, dQn, dB);
+      }
+      Qp = Q;
+      Q = Qn;
+      A = mfma(cc, Qn, A);
+      B = mfma(cs, Qn, B);
+    }
+    if (WANT_VALUE) v = mfma(A, Cl, mfma(B, Sl, v));
+    if (WANT_GRAD) {
+      const T rad = mfma(dA, Cl, dB * Sl);  // sum c dQ/ds * angular part
+      const double fl = (double)l;
+      dx = mfma(2.0 * x, rad, mfma(fl, mfma(A, Cm, B * Sm), dx));
+      dy = mfma(2.0 * y, rad, mfma(fl, mfma(B, Cm, -(A * Sm)), dy));
+    }
+    Cm = Cl;
+    Sm = Sl;
+    const T Cn = mfma(x, Cl, -(y * Sl));
+    Sl = mfma(x, Sl, y * Cl);
+    Cl = Cn;
+  }
+  val = v;
+  gx = dx * iR;  // ModuleDefects.py:163-164
+  gy = dy * iR;
+}
+
+// ---------------------------------------------------------------------------------------------
+// surface normal, `get_normal` of each mirror class (unit vector)
+// ---------------------------------------------------------------------------------------------
+template <class T>
+ART_HD void surface_normal(const ElemDev& E, T x, T y, T z, T& nx, T& ny, T& nz) {
+  T gx, gy, gz;
+  switch (E.surface) {
+    case ART_SURF_SPHERICAL:  // ART/ModuleMirror.py:180-183
+      gx = -x; gy = -y; gz = -z;
+      break;
+    case ART_SURF_PARABOLIC:  // :349-355
+      gx = -x; gy = -y; gz = splat<T>(E.sp[0]);
+      break;
+    case ART_SURF_TOROIDAL: {  // :480-498 (common factor 4 dropped)
+      const T S = mfma(x, x, mfma(y, y, z * z));
+      const T a = S + E.sp[3];        // + (R^2 - r^2)
+      const T b = a - 2.0 * E.sp[4];  // - 2 R^2
+      gx = -(x * b); gy = -(y * a); gz = -(z * b);
+      break;
+    }
+    case ART_SURF_ELLIPSOIDAL:  // :685-693
+      gx = -(x * E.sp[2]); gy = -(y * E.sp[3]); gz = -(z * E.sp[3]);
+      break;
+    case ART_SURF_CYLINDRICAL:  // :846-849
+      gx = splat<T>(0.0); gy = -y; gz = -z;
+      break;
+    default:  // plane, mask: :84-87
+      nx = splat<T>(0.0); ny = splat<T>(0.0); nz = splat<T>(1.0);
+      return;
+  }
+  const T inv = frsqrt(mfma(gx, gx, mfma(gy, gy, gz * gz)));
+  nx = gx * inv; ny = gy * inv; nz = gz * inv;
+}
+
+// atan2(y, x) for y >= 0 (result in [0, pi]), branch-free: one division for the reduced argument
+// z (|z| <= tan(pi/8)) and the Maclaurin series of atan to z^41 (truncation < 2e-18 z).
+template <class T>
+ART_HD T fatan2_ypos(T y, T x) {
+  typedef typename MaskOf<T>::type M;
+  const T ax = mabs(x);
+  const M swap = y > ax;
+  const T lo = sel(swap, ax, y), hi = sel(swap, y, ax);      // lo/hi in [0, 1]
+  const M big = lo > 0.41421356237309503 * hi;               // beyond tan(pi/8): rotate by pi/4
+  const T z = fdiv(sel(big, lo - hi, lo), sel(big, lo + hi, hi));
+  const T w = z * z;
+  T p = splat<T>(-1.0 / 41.0);
+  p = mfma(p, w, 1.0 / 39.0);  p = mfma(p, w, -1.0 / 37.0); p = mfma(p, w, 1.0 / 35.0);  p = mfma(p, w, -1.0 / 33.0);
+  p = mfma(p, w, 1.0 / 31.0);  p = mfma(p, w, -1.0 / 29.0); p = mfma(p, w, 1.0 / 27.0);  p = mfma(p, w, -1.0 / 25.0);
+  p = mfma(p, w, 1.0 / 23.0);  p = mfma(p, w, -1.0 / 21.0); p = mfma(p, w, 1.0 / 19.0);  p = mfma(p, w, -1.0 / 17.0);
+  p = mfma(p, w, 1.0 / 15.0);  p = mfma(p, w, -1.0 / 13.0); p = mfma(p, w, 1.0 / 11.0);  p = mfma(p, w, -1.0 / 9.0);
+  p = mfma(p, w, 1.0 / 7.0);   p = mfma(p, w, -1.0 / 5.0);  p = mfma(p, w, 1.0 / 3.0);
+  T a = mfma(-(z * w), p, z);                                // atan(z)
+  a = a + sel(big, 0.78539816339744831, 0.0);
+  a = sel(swap, 1.5707963267948966 - a, a);
+  return sel(x < 0.0, 3.1415926535897931 - a, a);
+}
+
+// Angle between two UNIT vectors a, b.  The reference uses Kahan's 2 atan2(|a-b|, |a+b|)
+// (ART/ModuleGeometry.py:40-44); atan2(|a x b|, a.b) is the same angle, equally well conditioned over
+// [0, pi], and needs one square root instead of two.
+template <class T>
+ART_HD T unit_angle(T ax, T ay, T az, T bx, T by, T bz) {
+  const T cx = mfma(ay, bz, -(az * by)), cy = mfma(az, bx, -(ax * bz)), cz = mfma(ax, by, -(ay * bx));
+  return fatan2_ypos(fsqrt(mfma(cx, cx, mfma(cy, cy, cz * cz))), mfma(ax, bx, mfma(ay, by, az * bz)));
+}
+
+// surface classes a kernel instantiation is compiled for (the chain says which it needs)
+enum { SURFS_ANY = 0, SURFS_TOROID = 1, SURFS_QUADRIC = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// one element acting on one ray (pair): ART/ModuleProcessing.py:284-309 (frame in, optic, frame out)
+// ---------------------------------------------------------------------------------------------
+template <bool WANT_INC, bool HAS_DEF, int SURFS, class T>
+ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict__ ztab,
+                          const int* __restrict__ zoff, bool ignore_defects, bool inc_here) {
+  typedef typename MaskOf<T>::type M;
+  const M act = r.alive;
+  // lab -> element frame (:289-295): p_e = R (p - pos) + centre, u_e = R u
+  RayT<T> e;
+  {
+    const T dx = r.px - E.pos[0], dy = r.py - E.pos[1], dz = r.pz - E.pos[2];
+    e.px = mfma(E.rot[0], dx, mfma(E.rot[1], dy, mfma(E.rot[2], dz, E.ctr[0])));
+    e.py = mfma(E.rot[3], dx, mfma(E.rot[4], dy, mfma(E.rot[5], dz, E.ctr[1])));
+    e.pz = mfma(E.rot[6], dx, mfma(E.rot[7], dy, mfma(E.rot[8], dz, E.ctr[2])));
+    e.ux = mfma(E.rot[0], r.ux, mfma(E.rot[1], r.uy, E.rot[2] * r.uz));
+    e.uy = mfma(E.rot[3], r.ux, mfma(E.rot[4], r.uy, E.rot[5] * r.uz));
+    e.uz = mfma(E.rot[6], r.ux, mfma(E.rot[7], r.uy, E.rot[8] * r.uz));
+  }
+  T t;
+  const int surf = E.surface;
+  if (surf == ART_SURF_PLANE || surf == ART_SURF_MASK) {
+    // ART/ModuleMirror.py:73-82: t > 0 (no epsilon) and on the support;
+    // ART/ModuleMask.py:51-61: passes iff t > 0 and NOT on the support
+    t = fdiv(-e.pz, e.uz);
+    const T x = mfma(t, e.ux, e.px), y = mfma(t, e.uy, e.py);
+    M ok = in_support(E, x, y);
+    if (surf == ART_SURF_MASK) ok = mnot(ok);
+    t = sel(mand(t > 0.0, ok), t, ART_NAN);
+  } else if (SURFS != SURFS_QUADRIC && surf == ART_SURF_TOROIDAL) {
+    t = intersect_toroid(E, e, act);
+  } else if (SURFS != SURFS_TOROID) {
+    T a, b, c;
+    bool side = true;
+    if (surf == ART_SURF_SPHERICAL) {  // :163-178
+      a = mfma(e.ux, e.ux, mfma(e.uy, e.uy, e.uz * e.uz));
+      b = 2.0 * mfma(e.ux, e.px, mfma(e.uy, e.py, e.uz * e.pz));
+      c = mfma(e.px, e.px, mfma(e.py, e.py, mfma(e.pz, e.pz, -E.sp[1])));
+    } else if (surf == ART_SURF_PARABOLIC) {  // :325-347 (no z test)
+      const double p = E.sp[0];
+      a = mfma(e.ux, e.ux, e.uy * e.uy);
+      b = 2.0 * mfma(e.ux, e.px, mfma(e.uy, e.py, -p * e.uz));
+      c = mfma(e.px, e.px, mfma(e.py, e.py, -2.0 * p * e.pz));
+      side = false;
+    } else if (surf == ART_SURF_ELLIPSOIDAL) {  // :662-683, sp[2] = 1/a^2, sp[3] = 1/b^2
+      const double ia = E.sp[2], ib = E.sp[3];
+      a = mfma(mfma(e.uy, e.uy, e.uz * e.uz), ib, e.ux * e.ux * ia);
+      b = 2.0 * mfma(mfma(e.uy, e.py, e.uz * e.pz), ib, e.ux * e.px * ia);
+      c = mfma(mfma(e.py, e.py, e.pz * e.pz), ib, mfma(e.px * e.px, ia, -1.0));
+    } else {  // ART_SURF_CYLINDRICAL :824-844
+      a = mfma(e.uy, e.uy, e.uz * e.uz);
+      b = 2.0 * mfma(e.uy, e.py, e.uz * e.pz);
+      c = mfma(e.py, e.py, mfma(e.pz, e.pz, -E.sp[1]));
+    }
+    T t1, t2;
+    solve_quadratic(a, b, c, t1, t2);
+    t = side ? pick_candidate<true>(E, e, t1, t2, 0.0) : pick_candidate<false>(E, e, t1, t2, 0.0);
+  } else {
+    t = splat<T>(ART_NAN);
+  }
+  // miss: the reference drops the ray (ModuleMirror.py:932, ModuleMask.py:132)
+  const M hit = mand(act, t == t);
+  if (!any(hit)) {
+    r.alive = hit;
+    return;
+  }
+  T hx = mfma(t, e.ux, e.px), hy = mfma(t, e.uy, e.py), hz = mfma(t, e.uz, e.pz);
+  T ox = e.ux, oy = e.uy, oz = e.uz;  // outgoing direction, element frame
+  T inc = r.inc;
+  if (surf == ART_SURF_MASK) {
+    // _TransmitMaskRay, ART/ModuleMask.py:93-108: direction unchanged, incidence vs ez
+    if (WANT_INC && inc_here) inc = unit_angle(e.ux, e.uy, e.uz, splat<T>(0.0), splat<T>(0.0), splat<T>(1.0));
+  } else {
+    T nx, ny, nz;
+    surface_normal(E, hx, hy, hz, nx, ny, nz);
+    if (HAS_DEF && E.n_defects > 0) {
+      // DeformedMirror._get_intersection, ART/ModuleMirror.py:969-980:
+      //   h = sum offsets(P - C); alpha = angle(-u, n_base(P)); P -= u h / cos(alpha)
+      T h = splat<T>(0.0);
+      for (int d = 0; d < E.n_defects; ++d) {
+        T v, g0, g1;
+        zernike_eval<true, false>(ztab + zoff[E.first_defect + d], hx - E.ctr[0], hy - E.ctr[1], v, g0, g1);
+        h = h + v;
+      }
+      const T cosa = -mfma(nx, e.ux, mfma(ny, e.uy, nz * e.uz));
+      const T sh = fdiv(h, cosa);
+      t = t - sh;
+      hx = mfma(-sh, e.ux, hx); hy = mfma(-sh, e.uy, hy); hz = mfma(-sh, e.uz, hz);
+      surface_normal(E, hx, hy, hz, nx, ny, nz);  // the reflection uses get_normal(shifted point)
+      if (!ignore_defects) {
+        // DeformedMirror.get_normal + normal_add, ART/ModuleMirror.py:952-961, ModuleGeometry.py:394-407:
+        // slopes add; the result is (-gx, -gy, 1) normalised
+        const T inz = fdiv(1.0, nz);
+        T sx = -(nx * inz), sy = -(ny * inz);
+        for (int d = 0; d < E.n_defects; ++d) {
+          T v, g0, g1;
+          zernike_eval<false, true>(ztab + zoff[E.first_defect + d], hx - E.ctr[0], hy - E.ctr[1], v, g0, g1);
+          sx = sx + g0;
+          sy = sy + g1;
+        }
+        const T inv = frsqrt(mfma(sx, sx, mfma(sy, sy, 1.0)));
+        nx = -(sx * inv); ny = -(sy * inv); nz = inv;
+      }
+    }
+    // _ReflectionMirrorRay, ART/ModuleMirror.py:878-906: u' = u - 2 (n.u) n, incidence = angle(-u, n)
+    const T d = mfma(nx, e.ux, mfma(ny, e.uy, nz * e.uz));
+    ox = mfma(-2.0 * d, nx, e.ux); oy = mfma(-2.0 * d, ny, e.uy); oz = mfma(-2.0 * d, nz, e.uz);
+    // Ray.vector setter renormalises (ART/ModuleOpticalRay.py:85-90); one Newton step is exact here
+    const T sc = mfma(-0.5, mfma(ox, ox, mfma(oy, oy, oz * oz)), 1.5);
+    ox = ox * sc; oy = oy * sc; oz = oz * sc;
+    if (WANT_INC && inc_here) inc = unit_angle(-e.ux, -e.uy, -e.uz, nx, ny, nz);
+  }
+  // element -> lab frame (:306-309): p = R^T (p_e - centre) + pos, u = R^T u_e
+  const T dx = hx - E.ctr[0], dy = hy - E.ctr[1], dz = hz - E.ctr[2];
+  r.px = sel(hit, mfma(E.rot[0], dx, mfma(E.rot[3], dy, mfma(E.rot[6], dz, E.pos[0]))), r.px);
+  r.py = sel(hit, mfma(E.rot[1], dx, mfma(E.rot[4], dy, mfma(E.rot[7], dz, E.pos[1]))), r.py);
+  r.pz = sel(hit, mfma(E.rot[2], dx, mfma(E.rot[5], dy, mfma(E.rot[8], dz, E.pos[2]))), r.pz);
+  r.ux = sel(hit, mfma(E.rot[0], ox, mfma(E.rot[3], oy, E.rot[6] * oz)), r.ux);
+  r.uy = sel(hit, mfma(E.rot[1], ox, mfma(E.rot[4], oy, E.rot[7] * oz)), r.uy);
+  r.uz = sel(hit, mfma(E.rot[2], ox, mfma(E.rot[5], oy, E.rot[8] * oz)), r.uz);
+  r.path = sel(hit, r.path + mabs(t), r.path);  // |P - A| with |u| = 1 (ModuleMirror.py:904, ModuleMask.py:100)
+  r.inc = sel(hit, inc, r.inc);
+  r.alive = hit;
+}
+
+}  // namespace art

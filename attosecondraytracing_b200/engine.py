@@ -81,8 +81,12 @@ class DeviceChain:
                         wavelength=src.wavelength)
         return out
 
+    def new_output(self, bundle, n_variants=1, want_incidence=True):
+        """A reusable output bundle for trace(..., out=...): n_variants x bundle.n rows."""
+        return self._new_out(bundle, n_variants, want_incidence)
+
     def trace(self, bundle, ignore_defects=True, history=False, want_incidence=True, want_central=True,
-              variant_first=0, n_variants=None, store_final=True):
+              variant_first=0, n_variants=None, store_final=True, out=None, central=None):
         """Trace `bundle` through the chain.  Returns (bundles, central):
         bundles = list of RayBundle after each element (history=True) or [final bundle];
         for several variants the rows of variant v are [v*n, (v+1)*n).  central = tensor
@@ -97,9 +101,10 @@ class DeviceChain:
             outs = [self._new_out(bundle, nv, want_incidence) for _ in range(self.n_elements)]
             hist_arr = (_cabi.ArtBundleView * self.n_elements)(*[o.view() for o in outs])
         elif store_final:
-            outs = [self._new_out(bundle, nv, want_incidence)]
+            outs = [out if out is not None else self._new_out(bundle, nv, want_incidence)]
             final_view = C.byref(outs[0].view())
-        central = torch.empty((nv, _cabi.CENTRAL_LEN), dtype=torch.float64, device=self.device) if want_central else None
+        if central is None and want_central:
+            central = torch.empty((nv, _cabi.CENTRAL_LEN), dtype=torch.float64, device=self.device)
         vin = bundle.view()
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().art_trace(self._handle, variant_first, nv, C.byref(vin), final_view, hist_arr,
@@ -112,19 +117,20 @@ class DeviceChain:
             o.invalidate()
         return outs, central
 
-    def autoplace(self, central, distance):
+    def autoplace(self, central, distance, det=None):
         """Detector.autoplace for every variant row of `central`; returns an (n_variants, 23) tensor of ArtDetector."""
         nv = central.shape[0]
-        det = torch.empty((nv, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=self.device)
+        if det is None:
+            det = torch.empty((nv, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().art_detector_autoplace(_ptr(central), float(distance), nv, _ptr(det), _stream()))
         return det
 
-    def moments(self, bundle, det, intensity=None, want_points=False):
+    def moments(self, bundle, det, intensity=None, want_points=False, out=None):
         """Detector moments of a stored bundle (n_variants x n rows).  Returns (moments, x, y, l)."""
         self._check_bundle(bundle)
         nv = det.shape[0]
-        mom = torch.empty((nv, _cabi.MOMENTS_LEN), dtype=torch.float64, device=self.device)
+        mom = out if out is not None else torch.empty((nv, _cabi.MOMENTS_LEN), dtype=torch.float64, device=self.device)
         x = y = l = None
         if want_points:
             x = torch.full((bundle.n,), float("nan"), dtype=torch.float64, device=self.device)

@@ -209,13 +209,14 @@ def workload_config(w, args, n_total):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--rays", type=int, default=0, help="rays per GPU (default: the workload's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of as a CUDA graph")
     args = ap.parse_args()
 
     w = load_workload(args.workload)
@@ -253,12 +254,19 @@ def main():
     distance = w["scene_spec"]["detector_distance"]
     K = chain.n_elements
 
+    # buffers of one step, allocated once and reused (no allocator traffic inside the timed region)
+    out = chain.new_output(src, want_incidence=True)
+    central = torch.empty((1, _cabi.CENTRAL_LEN), dtype=torch.float64, device=dev)
+    det = torch.empty((1, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=dev)
+    mom_local = torch.empty((1, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev)
+    inten = src.col("intensity")
+
     def step():
-        outs, central = chain.trace(src, ignore_defects=True, history=False, want_incidence=True)
+        chain.trace(src, ignore_defects=True, history=False, want_incidence=True, out=out, central=central)
         if world > 1:
             dist.all_reduce(central, op=dist.ReduceOp.SUM)
-        det = chain.autoplace(central, distance)
-        mom, _, _, _ = chain.moments(outs[0], det, intensity=src.col("intensity"))
+        chain.autoplace(central, distance, det=det)
+        mom, _, _, _ = chain.moments(out, det, intensity=inten, out=mom_local)
         if world > 1:
             sums = mom[:, :14].contiguous()
             dist.all_reduce(sums, op=dist.ReduceOp.SUM)
@@ -266,7 +274,7 @@ def main():
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             mom = torch.cat([sums, torch.stack([-mx[:, 0], mx[:, 3], -mx[:, 1], mx[:, 4], -mx[:, 2], mx[:, 5], mx[:, 6]],
                                                dim=1), mom[:, 21:]], dim=1)
-        return outs[0], central, det, mom
+        return out, central, det, mom
 
     def barrier():
         if world > 1:
@@ -284,6 +292,28 @@ def main():
     del hist
     torch.cuda.empty_cache()
 
+    # the step as a CUDA graph: five kernel launches (trace, fold, autoplace, detector, fold) replayed
+    # without host work in between.  Multi-GPU steps keep their NCCL all-reduces eager.
+    run_step = step
+    graphed = False
+    if world == 1 and not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            graph.replay()
+            torch.cuda.synchronize()
+            run_step = lambda: (graph.replay(), (out, central, det, mom_local))[1]  # noqa: E731
+            graphed = True
+        except Exception as exc:  # keep the eager step if capture is not possible
+            print(f"[bench] CUDA graph capture failed ({exc}); running eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
+
     # ---- timed region: K steps, device-timed, max over ranks --------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
@@ -292,7 +322,7 @@ def main():
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        final, central, det, mom = step()
+        final, central, det, mom = run_step()
     ev1.record()
     barrier()
     launches = lib.art_launch_count() - launches0
@@ -304,7 +334,7 @@ def main():
     torch.cuda.synchronize()
     for e0, e1 in kev:
         e0.record()
-        chain.trace(src, ignore_defects=True, history=False, want_incidence=True, want_central=False)
+        chain.trace(src, ignore_defects=True, history=False, want_incidence=True, want_central=False, out=out)
         e1.record()
     torch.cuda.synchronize()
     k_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in kev]))
@@ -366,7 +396,8 @@ def main():
                          "fp64": {"model_flops_per_launch": flops, "achieved_tflops": flops / (k_ms * 1e-3) / 1e12,
                                   "peak_tflops_measured_dfma": None if fl is None else fl / 1e12,
                                   "frac": None if fl is None else flops / (k_ms * 1e-3) / fl}},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches) if not graphed else 5 * args.steps, "cuda_graph": graphed,
+            "clocks": clocks,
             "interactions_per_step": interactions_all, "survivors_rank0": int(n_surv),
             "result": {k: s[k] for k in ("SpotSizeSD", "DurationSD", "ETransmission") if k in s},
         }

@@ -48,7 +48,7 @@ extern "C" int hc_trace(const ArtElementDesc* els, int n_el, const ArtZernikeDes
     r.inc = ART_NAN;
     r.alive = true;
     for (int k = 0; k < n_el; ++k) {
-      if (r.alive) apply_element<true>(E[k], r, ztab.data(), zoff.data(), ign);
+      if (r.alive) apply_element<true, true, SURFS_ANY, double>(E[k], r, ztab.data(), zoff.data(), ign, true);
       const long long o = (long long)k * n + i;
       oalive[o] = r.alive;
       opx[o] = r.px; opy[o] = r.py; opz[o] = r.pz;
