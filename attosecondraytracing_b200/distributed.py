@@ -1,0 +1,63 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink; gloo in CPU tests).
+
+The path shards by contiguous ray-index ranges (rays are independent through the whole chain) or,
+for misalignment sweeps, by chain variants.  There is NO per-ray traffic between ranks; the only
+exchanges are the all-reduces of two tiny rows per detector:
+    central sums (10 doubles, SUM)  -> every rank places the identical detector (Detector.autoplace)
+    moments      (24 doubles)       -> sums SUM; extents MIN/MAX packed into one MAX all-reduce
+Both are latency-bound (a few hundred bytes), issued on the compute stream right after the
+reduction kernel, with no host synchronisation in between.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+
+_MIN = _cabi.MOMENT_MIN
+_MAX = _cabi.MOMENT_MAX
+_SUM = list(range(0, 14))
+
+
+def shard_range(n, rank, world):
+    """(first, count) of rank's contiguous slice of n items: [rank*n//world, (rank+1)*n//world)."""
+    lo = (rank * n) // world
+    hi = ((rank + 1) * n) // world
+    return lo, hi - lo
+
+
+def is_distributed(group=None):
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def all_reduce_central(central, group=None):
+    """Sum the central-ray rows (n_variants x 10) over the ranks, in place."""
+    if is_distributed(group):
+        dist.all_reduce(central, op=dist.ReduceOp.SUM, group=group)
+    return central
+
+
+def all_reduce_moments(moments, group=None):
+    """Merge the moments rows (n_variants x 24) over the ranks, in place: additive entries are summed,
+    minima / maxima are reduced together in ONE max-all-reduce (minima negated)."""
+    if not is_distributed(group):
+        return moments
+    sums = moments[:, _SUM].contiguous()
+    ext = torch.cat([-moments[:, _MIN], moments[:, _MAX]], dim=1).contiguous()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
+    moments[:, _SUM] = sums
+    moments[:, _MIN] = -ext[:, : len(_MIN)]
+    moments[:, _MAX] = ext[:, len(_MIN):]
+    return moments
+
+
+def merge_moments(rows):
+    """Host-side merge of moments rows from several shards (sequence of (24,) arrays / tensors)."""
+    rows = torch.stack([torch.as_tensor(r, dtype=torch.float64) for r in rows])
+    out = torch.zeros(_cabi.MOMENTS_LEN, dtype=torch.float64)
+    out[_SUM] = rows[:, _SUM].sum(dim=0)
+    out[_MIN] = rows[:, _MIN].min(dim=0).values
+    out[_MAX] = rows[:, _MAX].max(dim=0).values
+    return out

@@ -117,6 +117,28 @@ class DeviceChain:
             o.invalidate()
         return outs, central
 
+    def count_entering(self, bundle, ignore_defects=True, variant_first=0, n_variants=None):
+        """Rays ENTERING each element, per variant -- the interaction count of the metric
+        (sum over elements of the rays that reach them).  Returns an int64 tensor (n_variants, n_elements).
+        Runs one trace that stores only the per-element alive flags."""
+        self._check_bundle(bundle)
+        nv = self.n_variants - variant_first if n_variants is None else n_variants
+        n, K = bundle.n, self.n_elements
+        alive = torch.empty((K, nv * n), dtype=torch.uint8, device=self.device)
+        views = (_cabi.ArtBundleView * K)()
+        for k in range(K):
+            views[k].alive = alive[k].data_ptr()
+            views[k].n = nv * n
+        flags = (_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0) | _cabi.TRACE_NO_INCIDENCE
+        vin = bundle.view()
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().art_trace(self._handle, variant_first, nv, C.byref(vin), None, views, flags, None,
+                                              _stream()))
+        surv = alive.reshape(K, nv, n).sum(dim=2, dtype=torch.int64).T  # (nv, K): rays LEAVING element k
+        n_in = int(bundle.alive.sum()) if bundle.alive is not None else n
+        first = torch.full((nv, 1), n_in, dtype=torch.int64, device=self.device)
+        return torch.cat([first, surv[:, :-1]], dim=1), surv[:, -1]
+
     def autoplace(self, central, distance, det=None):
         """Detector.autoplace for every variant row of `central`; returns an (n_variants, 23) tensor of ArtDetector."""
         nv = central.shape[0]
@@ -175,15 +197,19 @@ class DeviceChain:
                                                      _stream()))
         return mom, central, x, y, l
 
-    def sweep(self, bundle, distance, ignore_defects=True, variant_first=0, n_variants=None):
+    def sweep(self, bundle, distance, ignore_defects=True, variant_first=0, n_variants=None, out=None):
         """Trace every variant, autoplace its detector at `distance`, reduce its moments.
-        Returns (moments (nv,24), central (nv,10), det (nv,23)) device tensors."""
+        Returns (moments (nv,24), central (nv,10), det (nv,23)) device tensors (`out` = such a
+        triple to reuse)."""
         self._check_bundle(bundle)
         nv = self.n_variants - variant_first if n_variants is None else n_variants
         flags = _cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0
-        mom = torch.empty((nv, _cabi.MOMENTS_LEN), dtype=torch.float64, device=self.device)
-        central = torch.empty((nv, _cabi.CENTRAL_LEN), dtype=torch.float64, device=self.device)
-        det = torch.empty((nv, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=self.device)
+        if out is not None:
+            mom, central, det = out
+        else:
+            mom = torch.empty((nv, _cabi.MOMENTS_LEN), dtype=torch.float64, device=self.device)
+            central = torch.empty((nv, _cabi.CENTRAL_LEN), dtype=torch.float64, device=self.device)
+            det = torch.empty((nv, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=self.device)
         vin = bundle.view()
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().art_sweep(self._handle, variant_first, nv, C.byref(vin), flags, float(distance),
