@@ -86,6 +86,7 @@ class ArtError(RuntimeError):
 _SIGNATURES = {
     "art_version": (C.c_int32, []),
     "art_last_error": (C.c_char_p, []),
+    "art_abi_sizes": (C.c_int32, [C.POINTER(C.c_int32)]),
     "art_device_count": (C.c_int32, [C.POINTER(C.c_int32)]),
     "art_element_rotation": (C.c_int32, [c_double_p, c_double_p, c_double_p]),
     "art_chain_create": (C.c_int32, [C.POINTER(ArtElementDesc), C.c_int32, C.c_int32, C.POINTER(ArtZernikeDesc),
@@ -100,6 +101,7 @@ _SIGNATURES = {
     "art_detector_make": (C.c_int32, [c_double_p, c_double_p, c_double_p, C.c_double, C.POINTER(ArtDetector)]),
     "art_detector_moments": (C.c_int32, [C.c_void_p, C.POINTER(ArtBundleView), C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "art_moments_merge": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "art_sweep": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(ArtBundleView), C.c_uint32, C.c_double,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "art_delays": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -134,6 +136,11 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
+        sizes = (C.c_int32 * 4)()
+        L.art_abi_sizes(sizes)
+        mine = [C.sizeof(t) for t in (ArtElementDesc, ArtZernikeDesc, ArtBundleView, ArtDetector)]
+        if list(sizes) != mine:
+            raise RuntimeError(f"struct layout mismatch between _cabi.py {mine} and libart_b200.so {list(sizes)}")
         _lib = L
     return _lib
 

@@ -111,6 +111,15 @@ extern "C" int32_t art_version(void) { return ART_B200_VERSION; }
 extern "C" const char* art_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t art_launch_count(void) { return g_launches.load(); }
 
+extern "C" int32_t art_abi_sizes(int32_t sizes_out[4]) {
+  if (!sizes_out) return fail(ART_E_INVALID, "sizes_out is NULL");
+  sizes_out[0] = (int32_t)sizeof(ArtElementDesc);
+  sizes_out[1] = (int32_t)sizeof(ArtZernikeDesc);
+  sizes_out[2] = (int32_t)sizeof(ArtBundleView);
+  sizes_out[3] = (int32_t)sizeof(ArtDetector);
+  return ART_OK;
+}
+
 extern "C" int32_t art_device_count(int32_t* count) {
   if (!count) return fail(ART_E_INVALID, "count is NULL");
   int n = 0;
@@ -430,6 +439,15 @@ extern "C" int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bu
   detector_kernel<<<dim3(bpv, n_variants), TPB, 0, st>>>(a);
   ART_LAUNCHED();
   fold_kernel<<<n_variants, TPB, 0, st>>>(chain->d_partials, bpv, 2, nullptr, moments_out);
+  ART_LAUNCHED();
+  return ART_OK;
+}
+
+extern "C" int32_t art_moments_merge(const double* rows, int32_t n_ranks, int32_t n_variants, double* out,
+                                     void* stream) {
+  if (!rows || !out || n_ranks < 1 || n_variants < 1) return fail(ART_E_INVALID, "bad argument");
+  const int total = n_variants * ART_MOMENTS_LEN;
+  merge_moments_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rows, n_ranks, n_variants, out);
   ART_LAUNCHED();
   return ART_OK;
 }

@@ -538,6 +538,19 @@ __global__ void __launch_bounds__(TPB) fold_kernel(const double* __restrict__ pa
   }
 }
 
+// merge of the moments rows gathered from all ranks: rows[rank][variant][24] -> out[variant][24]
+// (additive entries summed in rank order, extents by min / max)
+__global__ void merge_moments_kernel(const double* __restrict__ rows, int n_ranks, int n_variants,
+                                     double* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_variants * ART_MOMENTS_LEN) return;
+  const int j = idx % ART_MOMENTS_LEN;
+  const int op = moment_op(j);
+  double x = rows[idx];
+  for (int r = 1; r < n_ranks; ++r) x = red_any(op, x, rows[(size_t)r * n_variants * ART_MOMENTS_LEN + idx]);
+  out[idx] = x;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Detector.autoplace, ART/ModuleDetector.py:109-137 with FindCentralRay ART/ModuleProcessing.py:464-482:
 // central vector = normalised mean direction, central point = mean point of the surviving rays;

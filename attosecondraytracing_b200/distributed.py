@@ -38,10 +38,23 @@ def all_reduce_central(central, group=None):
     return central
 
 
-def all_reduce_moments(moments, group=None):
-    """Merge the moments rows (n_variants x 24) over the ranks, in place: additive entries are summed,
-    minima / maxima are reduced together in ONE max-all-reduce (minima negated)."""
+def all_reduce_moments(moments, group=None, gather_buffer=None):
+    """Merge the moments rows (n_variants x 24) over the ranks, in place.
+
+    On CUDA: ONE all-gather of the rows followed by the library's merge kernel (art_moments_merge:
+    sums in rank order, extents by min / max) -- a single collective that a CUDA graph can capture.
+    On CPU tensors (gloo tests): additive entries summed, minima / maxima in one max-all-reduce."""
     if not is_distributed(group):
+        return moments
+    if moments.is_cuda:
+        import ctypes as C
+        world = dist.get_world_size(group)
+        if gather_buffer is None:
+            gather_buffer = torch.empty((world,) + tuple(moments.shape), dtype=moments.dtype, device=moments.device)
+        dist.all_gather_into_tensor(gather_buffer, moments.contiguous(), group=group)
+        _cabi.check(_cabi.lib().art_moments_merge(C.c_void_p(gather_buffer.data_ptr()), world, moments.shape[0],
+                                                  C.c_void_p(moments.data_ptr()),
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return moments
     sums = moments[:, _SUM].contiguous()
     ext = torch.cat([-moments[:, _MIN], moments[:, _MAX]], dim=1).contiguous()

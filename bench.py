@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph-nccl", action="store_true", help="multi-GPU: capture the NCCL collectives in the graph too")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of as a CUDA graph")
     args = ap.parse_args()
 
@@ -306,13 +307,14 @@ def run_b200(args, w, oes):
         det_b = torch.empty((1, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=dev)
         mom_b = torch.empty((1, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev)
         inten = src.col("intensity")
+        gather_b = torch.empty((world, 1, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev)
 
         def step():
             chain.trace(src, ignore_defects=True, history=False, want_incidence=True, out=out, central=central_b)
             ad.all_reduce_central(central_b)
             chain.autoplace(central_b, distance, det=det_b)
             chain.moments(out, det_b, intensity=inten, out=mom_b)
-            ad.all_reduce_moments(mom_b)
+            ad.all_reduce_moments(mom_b, gather_buffer=gather_b)
             return out, central_b, det_b, mom_b
 
         e, sv = chain.count_entering(src)
@@ -332,10 +334,10 @@ def run_b200(args, w, oes):
     torch.cuda.synchronize()
 
     # the step as a CUDA graph: its kernel launches replayed without host work in between.
-    # Multi-GPU steps keep their NCCL collectives eager.
+    # Multi-GPU steps keep their two NCCL collectives eager unless --graph-nccl asks to capture them too.
     run_step = step
     graphed = False
-    if world == 1 and not args.no_graph:
+    if not args.no_graph and (world == 1 or args.graph_nccl):
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())

@@ -151,7 +151,11 @@ typedef struct ArtChain ArtChain;
 int32_t art_version(void);
 const char* art_last_error(void);
 
-/* CUDA device count / name of device `dev` (plumbing for the host; no reference counterpart). */
+/* sizeof(ArtElementDesc), sizeof(ArtZernikeDesc), sizeof(ArtBundleView), sizeof(ArtDetector) as this
+ * library was compiled -- lets a binding in another language verify its struct layouts. */
+int32_t art_abi_sizes(int32_t sizes_out[4]);
+
+/* CUDA device count (plumbing for the host; no reference counterpart). */
 int32_t art_device_count(int32_t* count);
 
 /*
@@ -218,6 +222,12 @@ int32_t art_detector_make(const double centre[3], const double normal[3], const 
 int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bundle, int32_t n_variants,
                              const ArtDetector* det, double* x_out, double* y_out, double* l_out,
                              double* moments_out, void* stream);
+
+/* Multi-GPU: merge the moments rows that an all-gather collected from every rank
+ * (rows: device, n_ranks x n_variants x ART_MOMENTS_LEN) into out (n_variants x ART_MOMENTS_LEN):
+ * sums added in rank order, extents by min / max.  The statistics of the sharded bundle then follow
+ * exactly as for a single device. */
+int32_t art_moments_merge(const double* rows, int32_t n_ranks, int32_t n_variants, double* out, void* stream);
 
 /*
  * Trace and detector in ONE kernel (K1 with K2 as its epilogue), for detectors that are known

@@ -1,0 +1,231 @@
+"""CPU tests of the host side: the C ABI loads and exports what include/art_b200.h declares, the
+lowering of scene objects, the alignment (OEPlacement) and misalignment arithmetic against the
+poses the reference produced, the host Zernike evaluation against the oracle's recurrences, and the
+statistics derived from a moments row.  No GPU compute is called here."""
+import copy
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import art_oracle as orc
+from golden_util import Golden, build_optic, golden_names, golden_optical_elements
+from test_distributed_cpu import oracle_central, oracle_moments
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NAMES = golden_names()
+
+
+def test_library_exports_every_declared_symbol():
+    from attosecondraytracing_b200 import _cabi
+    header = open(os.path.join(ROOT, "include", "art_b200.h")).read()
+    declared = set(re.findall(r"\b(art_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found in the header"
+    lib = _cabi.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libart_b200.so does not export {name}"
+    assert declared == set(_cabi.EXPORTED_SYMBOLS), declared ^ set(_cabi.EXPORTED_SYMBOLS)
+    assert lib.art_version() == 100
+    sizes = (C.c_int32 * 4)()
+    assert lib.art_abi_sizes(sizes) == 0
+    assert list(sizes) == [C.sizeof(t) for t in (_cabi.ArtElementDesc, _cabi.ArtZernikeDesc, _cabi.ArtBundleView,
+                                                  _cabi.ArtDetector)] == [192, 40, 88, 184]
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from attosecondraytracing_b200 import _cabi
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _cabi.lib()
+
+
+def test_tracing_without_cuda_raises():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import attosecondraytracing_b200.ModuleProcessing as mp
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
+    g = Golden("cfg1_par")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        mp.RayTracingCalculation(RayBundle.from_numpy(g["src_P"], g["src_U"]), golden_optical_elements(g))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_alignment_reproduces_reference_poses(name):
+    """place_optical_elements (OEPlacement) + the misalignment methods give the reference's poses.
+    On the 5 m telescope the reference's own chief-ray noise is ~3e-9 mm."""
+    import attosecondraytracing_b200.ModuleProcessing as mp
+    g = Golden(name)
+    s = g.spec
+    optics = [build_optic(o) for o in s["optics"]]
+    oes = mp.place_optical_elements(optics, s["distances"], s["incidences"], s["plane_angles"])
+    for op in s.get("post", []):
+        getattr(oes[op["element"]], op["op"])(op["value"])
+    tol = 1e-8 if (name.startswith("cfg5") or name.startswith("tele")) else 1e-10
+    for k, oe in enumerate(oes):
+        assert np.max(np.abs(oe.position - g[f"el{k}_position"])) <= tol
+        assert np.max(np.abs(oe.normal - g[f"el{k}_normal"])) <= 1e-11
+        assert np.max(np.abs(oe.majoraxis - g[f"el{k}_majoraxis"])) <= 1e-11
+        assert np.max(np.abs(optics[k].get_centre() - np.array(s["derived_optics"][k]["centre"]))) <= 1e-12
+        assert optics[k].type == s["derived_optics"][k]["type"]
+
+
+def test_element_rotation_matches_oracle_including_branches():
+    from attosecondraytracing_b200 import _cabi
+    rng = np.random.default_rng(3)
+    cases = [(np.array([0, 0, 1.0]), np.array([1.0, 0, 0])), (np.array([0, 0, -1.0]), np.array([1.0, 0, 0])),
+             (np.array([0, 0, 1.0]), np.array([-1.0, 0, 0])), (np.array([0, 0, -1.0]), np.array([0, 1.0, 0]))]
+    for _ in range(20):
+        n = orc.normalize(rng.normal(size=3))
+        m = orc.normalize(np.cross(n, rng.normal(size=3)))
+        cases.append((n, m))
+    for n, m in cases:
+        R = np.array(_cabi.element_rotation(n, m))
+        assert np.max(np.abs(R - orc.element_frame_matrix(n, m))) <= 1e-14
+
+
+def test_lowering_fills_descriptors():
+    from attosecondraytracing_b200 import _cabi
+    from attosecondraytracing_b200._lowering import LoweredChain
+    g = Golden("cfg4_zern_def")
+    low = LoweredChain([golden_optical_elements(g)])
+    d = low.elements[0]
+    assert d.surface == _cabi.SURF_PARABOLIC and d.support == _cabi.SUPP_RECT
+    assert d.n_defects == 1 and low.n_defects == 1
+    assert low.defects[0].n_coefficients == len(g.spec["optics"][0]["defects"][0]["coefficients"])
+    assert abs(low.defects[0].radius - np.sqrt(40**2 + 40**2) / 2) < 1e-12
+    g3 = Golden("cfg3_2tor")
+    low3 = LoweredChain([golden_optical_elements(g3)] * 3)
+    assert low3.n_variants == 3 and low3.n_elements == 3
+    assert [low3.elements[i].surface for i in range(3)] == [_cabi.SURF_MASK, _cabi.SURF_TOROIDAL, _cabi.SURF_TOROIDAL]
+
+
+def test_host_zernike_matches_oracle_recurrences():
+    """ModuleDefects.Zernike (radial-polynomial form, as in the kernel) == the reference's Cartesian
+    recurrences (oracle.zernike_gradient) for every (n, m) up to order 12."""
+    import attosecondraytracing_b200.ModuleDefects as mdef
+    import attosecondraytracing_b200.ModuleSupport as msupp
+    sup = msupp.SupportRound(10.0)
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-7, 7, size=(6, 2))
+    Z, GX, GY = orc.zernike_gradient(pts[:, 0] / 10.0, pts[:, 1] / 10.0, 12)
+    for n in range(0, 13):
+        for m in range(0, n + 1):
+            z = mdef.Zernike(sup, {(2, 0): 0.0, (n, m): 1.0})
+            for i, p in enumerate(pts):
+                q = np.array([p[0], p[1], 0.0])
+                assert abs(z.get_offset(q) - Z[(n, m)][i]) <= 1e-12 * max(1.0, abs(Z[(n, m)][i])), (n, m)
+                nrm = z.get_normal(q)
+                assert abs(-nrm[0] * 10.0 - GX[(n, m)][i]) <= 1e-11 * max(1.0, abs(GX[(n, m)][i])), (n, m)
+                assert abs(-nrm[1] * 10.0 - GY[(n, m)][i]) <= 1e-11 * max(1.0, abs(GY[(n, m)][i])), (n, m)
+
+
+def test_supports_include_semantics():
+    import attosecondraytracing_b200.ModuleSupport as msupp
+    rng = np.random.default_rng(1)
+    pts = rng.uniform(-40, 40, size=(400, 2))
+    specs = [("round", (30,)), ("roundhole", (30, 5, 10, 5)), ("rect", (60, 30)), ("recthole", (60, 60, 5, 9, -8)),
+             ("rectrecthole", (30, 20, 10, 6, 2, -1))]
+    cls = {"round": msupp.SupportRound, "roundhole": msupp.SupportRoundHole, "rect": msupp.SupportRectangle,
+           "recthole": msupp.SupportRectangleHole, "rectrecthole": msupp.SupportRectangleRectHole}
+    for kind, p in specs:
+        sup = cls[kind](*p)
+        want = orc.support_include((kind,) + p, pts[:, 0], pts[:, 1])
+        got = np.array([sup._IncludeSupport(np.array([x, y, 0.0])) for x, y in pts])
+        assert np.array_equal(got, want), kind
+        assert abs(sup._CircumCirc() - orc.support_circum_circ((kind,) + p)) < 1e-14
+    # edges are inclusive (ART/ModuleGeometry.py:249-268)
+    assert msupp.SupportRound(5)._IncludeSupport(np.array([3.0, 4.0, 0]))
+    assert msupp.SupportRectangle(4, 2)._IncludeSupport(np.array([2.0, -1.0, 0]))
+
+
+def test_optical_element_pose_rules():
+    import attosecondraytracing_b200.ModuleOpticalElement as moe
+    import attosecondraytracing_b200.ModuleMirror as mmirror
+    import attosecondraytracing_b200.ModuleSupport as msupp
+    m = mmirror.MirrorPlane(msupp.SupportRound(10))
+    oe = moe.OpticalElement(m, np.zeros(3), np.array([0, 0, 2.0]), np.array([3.0, 0, 0]))
+    assert np.allclose(oe.normal, [0, 0, 1]) and np.allclose(oe.majoraxis, [1, 0, 0])
+    with pytest.raises(ValueError):
+        oe.majoraxis = np.array([0.0, 0.1, 1.0])
+    with pytest.raises(TypeError):
+        oe.position = [0, 0, 0]
+    oe.rotate_pitch_by(10.0)  # about normal x major = +y; the major axis co-rotates and stays perpendicular
+    assert abs(np.dot(oe.normal, oe.majoraxis)) < 1e-15
+    assert np.allclose(oe.normal, [np.sin(np.deg2rad(10)), 0, np.cos(np.deg2rad(10))])
+    oe.shift_along_cross(2.0)
+    assert np.allclose(oe.position, 2.0 * np.cross(oe.normal, oe.majoraxis))
+    h0 = hash(oe)
+    oe.rotate_yaw_by(1.0)
+    assert hash(oe) != h0
+
+
+def test_chain_and_detector_argument_checks():
+    import attosecondraytracing_b200.ModuleOpticalChain as moc
+    import attosecondraytracing_b200.ModuleDetector as mdet
+    from attosecondraytracing_b200.ModuleOpticalRay import Ray, RayBundle
+    g = Golden("cfg1_par")
+    oes = golden_optical_elements(g)
+    with pytest.raises(TypeError):
+        moc.OpticalChain("rays", oes)
+    with pytest.raises(TypeError):
+        moc.OpticalChain(RayBundle.from_numpy(g["src_P"], g["src_U"]), "elements")
+    rays = [Ray(g["src_P"][i].copy(), g["src_U"][i].copy(), Number=i, Intensity=1.0) for i in range(5)]
+    ch = moc.OpticalChain(rays, oes, "five rays")
+    assert len(ch.source_rays) == 5 and ch.source_rays[3].number == 3
+    chains = ch.get_OE_loop_list(0, "pitch", np.linspace(-0.1, 0.1, 5))
+    assert len(chains) == 5 and chains[0].source_rays is ch.source_rays
+    assert chains[1].loop_variable_name.endswith("pitch rotation (deg)")
+    assert not np.allclose(chains[0].optical_elements[0].normal, chains[4].optical_elements[0].normal)
+    with pytest.raises(ValueError):
+        ch.get_OE_loop_list(0, "wobble", [1.0])
+    with pytest.raises(TypeError):
+        mdet.Detector(np.zeros(3), Normal=np.zeros(3))
+    d = mdet.Detector(np.array([0.0, 0, 0]), np.array([0.0, 0, 5.0]), np.array([0.0, 0, -2.0]))
+    assert np.allclose(d.normal, [0, 0, -1]) and abs(d.get_distance() - 5.0) < 1e-15
+    d.shiftByDistance(1.0)
+    assert abs(d.get_distance() - 6.0) < 1e-15
+    d.shiftToDistance(2.5)
+    assert abs(d.get_distance() - 2.5) < 1e-15
+
+
+def test_ray_bundle_list_facade_on_cpu():
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
+    import torch
+    g = Golden("cfg3_2tor")
+    b = RayBundle.from_numpy(g["src_P"], g["src_U"], intensity=g["src_I"])
+    assert len(b) == 1000 and b[999].number == 999 and abs(b[7].intensity - g["src_I"][7]) < 1e-16
+    b.alive = torch.ones(b.n, dtype=torch.uint8)
+    b.alive[::2] = 0
+    b.invalidate()
+    assert len(b) == 500 and b[0].number == 1 and [r.number for r in b][:3] == [1, 3, 5]
+    with pytest.raises(IndexError):
+        b[500]
+    d = b.to_numpy()
+    assert np.array_equal(d["number"], np.arange(1, 1000, 2)) and np.array_equal(d["P"], g["src_P"][1::2])
+
+
+@pytest.mark.parametrize("name", ["cfg3_2tor", "cfg1_par", "cfg5_tele", "sph_recthole"])
+def test_statistics_from_moments_row(name):
+    """engine.summary_from_moments turns the 24 sums / extents into the reference's statistics."""
+    from attosecondraytracing_b200.engine import summary_from_moments
+    g = Golden(name)
+    last = g.out(g.n_elements - 1)
+    det = {"centre": g["det_centre"], "normal": g["det_normal"], "refpoint": g["det_refpoint"]}
+    idx = np.searchsorted(g["src_num"], last["num"])
+    w = g["src_I"][idx]
+    l0 = last["path"].mean() + g.spec["detector_distance"]
+    m = oracle_moments(det, l0, last["P"], last["U"], last["path"], w)
+    c = oracle_central(last["P"], last["U"], last["path"], w, g["src_I"].sum())
+    s = summary_from_moments(m, c)
+    assert abs(s["SpotSizeSD"] - g["SpotSizeSD"]) <= 1e-9
+    assert abs(s["DurationSD"] - g["DurationSD"]) <= 1e-5
+    assert abs(s["SpotSizeSD_w"] - g["SpotSizeSD_w"]) <= 1e-9
+    assert abs(s["DurationSD_w"] - g["DurationSD_w"]) <= 1e-5
+    assert abs(s["ETransmission"] - g["ETransmission"]) <= 1e-9
+    assert abs(s["Diameter"] - g["Diameter"]) <= 1e-9
+    assert abs(s["NA"] - g["NA"]) <= 1e-10
+    assert summary_from_moments(np.zeros(24))["n_rays"] == 0
