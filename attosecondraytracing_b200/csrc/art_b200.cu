@@ -242,10 +242,19 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
   c->smem_bytes = sizeof(ElemDev) * ART_MAX_ELEMENTS + sizeof(double) * ztab.size() + sizeof(int) * zoff.size();
   c->smem_bytes = (c->smem_bytes + 15) & ~size_t(15);
   if (c->smem_bytes > 200 * 1024) return bail(ART_E_UNSUPPORTED, "Zernike tables exceed 200 KB of shared memory");
-  CK(allow_smem(trace_kernel<true, false, true, SURFS_ANY>, c->smem_bytes));
-  CK(allow_smem(trace_kernel<false, false, true, SURFS_ANY>, c->smem_bytes));
-  CK(allow_smem(trace_kernel<true, true, true, SURFS_ANY>, c->smem_bytes));
-  CK(allow_smem(trace_kernel<false, true, true, SURFS_ANY>, c->smem_bytes));
+  {
+    const size_t fused = c->smem_bytes + SMEM_MOMENTS_BYTES;  // fused-detector kernels add the moment slots
+    CK(allow_smem(trace_kernel<true, false, true, SURFS_ANY>, c->smem_bytes));
+    CK(allow_smem(trace_kernel<false, false, true, SURFS_ANY>, c->smem_bytes));
+    CK(allow_smem(trace_kernel<true, true, true, SURFS_ANY>, fused));
+    CK(allow_smem(trace_kernel<false, true, true, SURFS_ANY>, fused));
+    CK(allow_smem(trace_kernel<true, true, false, SURFS_ANY>, fused));
+    CK(allow_smem(trace_kernel<false, true, false, SURFS_ANY>, fused));
+    CK(allow_smem(trace_kernel<true, true, false, SURFS_TOROID>, fused));
+    CK(allow_smem(trace_kernel<false, true, false, SURFS_TOROID>, fused));
+    CK(allow_smem(trace_kernel<true, true, false, SURFS_QUADRIC>, fused));
+    CK(allow_smem(trace_kernel<false, true, false, SURFS_QUADRIC>, fused));
+  }
   {
     bool tor = false, quad = false;
     for (int k = 0; k < n_elements; ++k) {
@@ -334,7 +343,8 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
   const int bpv = blocks_per_variant(c, in->n, n_variants, ART_RPT);
   if ((size_t)bpv * n_variants > c->partial_rows) return fail(ART_E_INVALID, "internal: partial buffer too small");
   const dim3 grid(bpv, n_variants);
-  const size_t sm = c->smem_bytes;
+  a.moments_smem_offset = (int)c->smem_bytes;
+  const size_t sm = c->smem_bytes + (det ? (size_t)SMEM_MOMENTS_BYTES : 0);
   // Zernike chains run the general kernel; defect-free chains one specialised for their surface class
 #define ART_TRACE_LAUNCH(INC, DET)                                                                      \
   do {                                                                                                  \

@@ -42,6 +42,7 @@ struct TraceArgs {
   double* partials;      // [variant][block][plen]
   const ArtDetector* det;  // fused detector (device, per variant) or null
   double *x_out, *y_out, *l_out;
+  int moments_smem_offset;  // byte offset of the per-thread moment slots in dynamic smem (WITH_DET)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -83,8 +84,8 @@ __device__ __forceinline__ double red_any(int op, double a, double b) {
   return op == 0 ? a + b : (op == 1 ? fmin(a, b) : fmax(a, b));
 }
 
-template <int NV, typename OPF>
-__device__ __forceinline__ void block_reduce_row(double (&v)[NV], OPF opf, double* smem /* NWARP*NV */,
+template <int NV, typename V, typename OPF>
+__device__ __forceinline__ void block_reduce_row(const V& v, OPF opf, double* smem /* NWARP*NV */,
                                                  double* __restrict__ out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -132,14 +133,25 @@ __device__ __forceinline__ DetHit detector_ray(const ArtDetector& D, const Ray& 
   return h;
 }
 
-__device__ __forceinline__ void moments_init(double (&m)[ART_MOMENTS_LEN]) {
+// Per-thread moment accumulators living in shared memory (slot j of thread t at base[j * TPB + t]):
+// 24 doubles per thread would otherwise cost 48 registers for the whole kernel lifetime.
+struct SmemMoments {
+  volatile double* base;  // &slots[0][threadIdx.x]; volatile keeps the compiler from promoting the slots back
+                          // into registers across the ray loop
+  __device__ __forceinline__ volatile double& operator[](int j) const { return base[j * TPB]; }
+};
+constexpr int SMEM_MOMENTS_BYTES = ART_MOMENTS_LEN * TPB * (int)sizeof(double);
+
+template <class ACC>
+__device__ __forceinline__ void moments_init(ACC& m) {
 #pragma unroll
   for (int j = 0; j < ART_MOMENTS_LEN; ++j) {
     const int op = moment_op(j);
     m[j] = op == 0 ? 0.0 : (op == 1 ? CUDART_INF : -CUDART_INF);
   }
 }
-__device__ __forceinline__ void moments_add(double (&m)[ART_MOMENTS_LEN], const DetHit& h, double l0, double w) {
+template <class ACC>
+__device__ __forceinline__ void moments_add(ACC& m, const DetHit& h, double l0, double w) {
   const double d = h.L - l0;
   m[ART_M_N] += 1.0;
   m[ART_M_SX] += h.x;
@@ -287,7 +299,9 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
   const long long nitems = (n + N - 1) / N;
   const int last = a.n_elements - 1;
 
-  double m[WITH_DET ? ART_MOMENTS_LEN : 1];
+  // fused detector: per-thread moment slots behind the tables in dynamic shared memory
+  SmemMoments m;
+  m.base = reinterpret_cast<double*>(smem_raw + a.moments_smem_offset) + threadIdx.x;
   if constexpr (WITH_DET) moments_init(m);
 
   for (long long item = (long long)blockIdx.x * TPB + threadIdx.x; item < nitems;
@@ -394,19 +408,15 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
   }
 
   double* prow = a.partials + ((size_t)v * gridDim.x + blockIdx.x) * PLEN;
-  if constexpr (WITH_DET) {
-    double all[PLEN_FUSED];
-#pragma unroll
-    for (int j = 0; j < ART_CENTRAL_LEN; ++j) all[j] = ART_ACC(j);
-#pragma unroll
-    for (int j = 0; j < ART_MOMENTS_LEN; ++j) all[ART_CENTRAL_LEN + j] = m[j];
-    block_reduce_row<PLEN_FUSED>(all, [](int j) { return j < ART_CENTRAL_LEN ? 0 : moment_op(j - ART_CENTRAL_LEN); },
-                                 sRed, prow);
-  } else {
+  {
     double all[PLEN_TRACE];
 #pragma unroll
     for (int j = 0; j < ART_CENTRAL_LEN; ++j) all[j] = ART_ACC(j);
     block_reduce_row<PLEN_TRACE>(all, [](int) { return 0; }, sRed, prow);
+  }
+  if constexpr (WITH_DET) {
+    __syncthreads();  // sRed is reused
+    block_reduce_row<ART_MOMENTS_LEN>(m, [](int j) { return moment_op(j); }, sRed, prow + ART_CENTRAL_LEN);
   }
 #undef ART_ACC
 }
@@ -438,7 +448,7 @@ __global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetAr
   const long long n = a.n, row = (long long)v * n;
   const bool vec = (row & 1) == 0;
   const long long npairs = (n + 1) >> 1;
-  double m[ART_MOMENTS_LEN];
+  double m[ART_MOMENTS_LEN];  // registers: measured faster here than shared-memory slots (streaming kernel)
   moments_init(m);
   for (long long pair = (long long)blockIdx.x * TPB + threadIdx.x; pair < npairs;
        pair += (long long)gridDim.x * TPB) {
