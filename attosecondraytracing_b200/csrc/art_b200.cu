@@ -669,6 +669,89 @@ extern "C" int32_t art_run_host(ArtChain* c, const ArtBundleView* in_host, const
   return ART_OK;
 }
 
+// RayTracingCalculation for a host caller: host columns in, the bundle after every element (and / or
+// the final one) back in host columns.  Allocates and frees its device staging per call.
+extern "C" int32_t art_trace_host(ArtChain* c, const ArtBundleView* in_host, const ArtBundleView* out_final_host,
+                                  const ArtBundleView* out_history_host, uint32_t flags) {
+  if (!c || !in_host) return fail(ART_E_INVALID, "NULL argument");
+  if (in_host->n < 0) return fail(ART_E_INVALID, "negative ray count");
+  if (!in_host->px || !in_host->py || !in_host->pz || !in_host->ux || !in_host->uy || !in_host->uz)
+    return fail(ART_E_INVALID, "the point and vector columns (px..uz) are required");
+  const int K = c->n_elements;
+  const size_t n = (size_t)in_host->n;
+  const int n_out = (out_history_host ? K : 0) + (out_final_host ? 1 : 0);
+  for (int k = 0; k < n_out; ++k) {
+    const ArtBundleView* o = (out_history_host && k < K) ? &out_history_host[k] : out_final_host;
+    if (o->n != in_host->n) return fail(ART_E_INVALID, "output bundles must hold n rays");
+  }
+  ART_CUDA(cudaSetDevice(c->device));
+  const size_t cap = (n + 31) & ~size_t(31);
+  double* dcols = nullptr;
+  uint8_t* dflags = nullptr;
+  const size_t ncols = 8 + 8 * (size_t)n_out;
+  if (cap) {
+    ART_CUDA(cudaMalloc(&dcols, sizeof(double) * ncols * cap));
+    if (cudaMalloc(&dflags, (size_t)(1 + n_out) * cap) != cudaSuccess) {
+      cudaFree(dcols);
+      return fail(ART_E_NOMEM, "out of device memory for the host staging buffers");
+    }
+  }
+  auto cleanup = [&]() {
+    cudaFree(dcols);
+    cudaFree(dflags);
+  };
+  auto col = [&](size_t j) { return dcols + j * cap; };
+  cudaStream_t st = nullptr;  // legacy default stream: the copies below are synchronous with the host
+  ArtBundleView din = {};
+  din.n = (int64_t)n;
+  const double* src[8] = {in_host->px, in_host->py, in_host->pz, in_host->ux,
+                          in_host->uy, in_host->uz, in_host->path, in_host->intensity};
+  double** dst[8] = {&din.px, &din.py, &din.pz, &din.ux, &din.uy, &din.uz, &din.path, &din.intensity};
+  cudaError_t e = cudaSuccess;
+  for (int j = 0; j < 8 && e == cudaSuccess; ++j) {
+    if (!src[j]) continue;
+    *dst[j] = col(j);
+    if (n) e = cudaMemcpyAsync(col(j), src[j], sizeof(double) * n, cudaMemcpyHostToDevice, st);
+  }
+  if (e == cudaSuccess && in_host->alive) {
+    din.alive = dflags;
+    if (n) e = cudaMemcpyAsync(dflags, in_host->alive, n, cudaMemcpyHostToDevice, st);
+  }
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(ART_E_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
+  }
+  std::vector<ArtBundleView> dviews(n_out);
+  for (int k = 0; k < n_out; ++k) {
+    ArtBundleView& d = dviews[k];
+    d = ArtBundleView{};
+    d.n = (int64_t)n;
+    double** f[8] = {&d.px, &d.py, &d.pz, &d.ux, &d.uy, &d.uz, &d.path, &d.incidence};
+    for (int j = 0; j < 8; ++j) *f[j] = col(8 + 8 * (size_t)k + j);
+    d.alive = dflags + (size_t)(1 + k) * cap;
+  }
+  const ArtBundleView* dhist = out_history_host ? dviews.data() : nullptr;
+  const ArtBundleView* dfinal = out_final_host ? &dviews[n_out - 1] : nullptr;
+  int32_t rc = launch_trace(c, 0, 1, &din, dfinal, dhist, flags, nullptr, nullptr, nullptr, nullptr, nullptr,
+                            nullptr, st);
+  if (rc) {
+    cleanup();
+    return rc;
+  }
+  for (int k = 0; k < n_out && e == cudaSuccess && n; ++k) {
+    const ArtBundleView* o = (out_history_host && k < K) ? &out_history_host[k] : out_final_host;
+    double* h[8] = {o->px, o->py, o->pz, o->ux, o->uy, o->uz, o->path, o->incidence};
+    for (int j = 0; j < 8 && e == cudaSuccess; ++j)
+      if (h[j]) e = cudaMemcpyAsync(h[j], col(8 + 8 * (size_t)k + j), sizeof(double) * n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && o->alive)
+      e = cudaMemcpyAsync(o->alive, dflags + (size_t)(1 + k) * cap, n, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) return fail(ART_E_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
+  return ART_OK;
+}
+
 // -------------------------------------------------------------------------------------------------
 // probes
 // -------------------------------------------------------------------------------------------------

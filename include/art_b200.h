@@ -292,6 +292,17 @@ int32_t art_run_host(ArtChain* chain, const ArtBundleView* in_host, const ArtBun
                      uint32_t flags, double distance, const ArtDetector* manual_det,
                      double* moments_host, double* central_host, ArtDetector* det_host);
 
+/*
+ * ART/ModuleProcessing.py:250 RayTracingCalculation for a caller that holds HOST arrays (the
+ * reference's list[Ray] flattened to columns): copies the source bundle to the device, traces
+ * variant 0 and copies back the bundle after EVERY element (out_history_host: n_elements views,
+ * may be NULL) and / or the final bundle (out_final_host, may be NULL).  Output columns that are
+ * NULL are skipped; `alive` tells which rays the reference would have kept.  Synchronises;
+ * allocates and frees its device staging buffers per call.
+ */
+int32_t art_trace_host(ArtChain* chain, const ArtBundleView* in_host, const ArtBundleView* out_final_host,
+                       const ArtBundleView* out_history_host, uint32_t flags);
+
 /* FP64 FMA throughput probe for the roofline denominator: runs a register-resident DFMA loop on
  * the whole device and returns measured FLOP/s (2 per FMA).  Synchronises. */
 int32_t art_probe_fp64(double* flops_per_second);

@@ -216,3 +216,101 @@ def test_device_sources_match_oracle():
         part = msrc.synthetic_source(sp, device="cuda", first=1000, count=512)
         pd = part.to_numpy()
         assert np.array_equal(pd["P"], d["P"][1000:1512]) and np.array_equal(pd["U"], d["U"][1000:1512])
+
+
+@pytest.mark.parametrize("name", ["cfg3_2tor", "cfg1_par", "sph_zern2_def", "mask_rrh_plane"])
+def test_reference_side_ctypes_binding(name):
+    """integration/art_b200_binding.py (numpy + ctypes only; what INTEGRATION.md tells a maintainer of
+    the reference to add) reproduces the reference's list[list[Ray]] through art_trace_host."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "integration"))
+    import art_b200_binding as b200
+    from attosecondraytracing_b200 import _cabi
+    from attosecondraytracing_b200.ModuleOpticalRay import Ray
+    b200.load(_cabi.LIB_PATH)
+    g = Golden(name)
+    oes = golden_optical_elements(g)  # same attribute names as the reference's objects (duck typing)
+    rays = [Ray(g["src_P"][i].copy(), g["src_U"][i].copy(), Number=int(g["src_num"][i]), Intensity=float(g["src_I"][i]))
+            for i in range(g["src_P"].shape[0])]
+    rtc = b200.make_RayTracingCalculation(Ray)
+    out = rtc(rays, oes, IgnoreDefects=g.ignore_defects)
+    assert len(out) == g.n_elements
+    for k, bundle in enumerate(out):
+        ref = g.out(k)
+        num = np.array([r.number for r in bundle], dtype=np.int64)
+        P = np.array([r.point for r in bundle]).reshape(-1, 3)
+        U = np.array([r.vector for r in bundle]).reshape(-1, 3)
+        path = np.array([np.sum(r.path) for r in bundle])
+        inc = np.array([r.incidence for r in bundle])
+        compare_bundle(name, k, ref, num, P, U, path, inc)
+
+
+@pytest.mark.parametrize("name", ["cfg1_par", "cfg2_tor2f", "cfg3_2tor", "cfg4_zern_ign", "ell_offaxis", "cyl_cx"])
+def test_public_api_end_to_end(name):
+    """The reference-facing Python API (same names as ART): OEPlacement -> OpticalChain.get_output_rays
+    -> Detector.autoplace -> GetResultSummary / getETransmission / per-ray detector lists."""
+    import attosecondraytracing_b200.ModuleProcessing as mp
+    import attosecondraytracing_b200.ModuleDetector as mdet
+    import attosecondraytracing_b200.ModuleAnalysisAndPlots as mplots
+    from golden_util import build_optic
+    g = Golden(name)
+    s = g.spec
+    chain = mp.OEPlacement(dict(s["source"]), [build_optic(o) for o in s["optics"]], list(s["distances"]),
+                           list(s["incidences"]), list(s["plane_angles"]), name)
+    for op in s.get("post", []):
+        getattr(chain.optical_elements[op["element"]], op["op"])(op["value"])
+    out = chain.get_output_rays()
+    assert out is chain.get_output_rays()  # cached
+    assert len(out) == g.n_elements
+    for k, b in enumerate(out):
+        d = b.to_numpy()
+        compare_bundle(name, k, g.out(k), d["number"], d["P"], d["U"], d["path"], d["incidence"])
+    final = out[-1]
+    r0 = final[0]
+    ref_last = g.out(g.n_elements - 1)
+    assert r0.number == int(ref_last["num"][0]) and np.max(np.abs(r0.point - ref_last["P"][0])) <= 1e-9
+    det = mdet.Detector(chain.optical_elements[-1].position)
+    det.autoplace(final, s["detector_distance"])
+    assert np.max(np.abs(det.centre - g["det_centre"])) <= 1e-9
+    assert abs(det.get_distance() - float(g["det_distance"])) <= 1e-9
+    sd, dur = mplots.GetResultSummary(det, final)
+    assert abs(sd - g["SpotSizeSD"]) <= 1e-9 and abs(dur - g["DurationSD"]) <= DELAY_TOL_FS
+    assert abs(mplots.getETransmission(chain.source_rays, final) - g["ETransmission"]) <= 1e-9
+    assert np.max(np.abs(np.asarray(det.get_Delays(final)) - g["det_delays"])) <= DELAY_TOL_FS
+    assert abs(mp.StandardDeviation(det.get_Delays(final)) - g["DurationSD"]) <= DELAY_TOL_FS
+    assert abs(mp.ReturnNumericalAperture(final, 1) - g["NA"]) <= 1e-10
+    central = mp.FindCentralRay(final)
+    assert np.max(np.abs(central.point - g["det_refpoint"])) <= 1e-9
+    # editing an element invalidates the cache and re-traces
+    chain.optical_elements[0].shift_along_normal(0.01)
+    out2 = chain.get_output_rays()
+    assert out2 is not out
+
+
+def test_sweep_statistics_matches_individual_chains():
+    """ModuleOpticalChain.sweep_statistics (one batched launch) == tracing every chain of the loop list
+    on its own; the pitch = 0.02 deg entry reproduces the reference's tele_pitch fixture."""
+    import attosecondraytracing_b200.ModuleProcessing as mp
+    import attosecondraytracing_b200.ModuleOpticalChain as moc
+    import attosecondraytracing_b200.ModuleDetector as mdet
+    import attosecondraytracing_b200.ModuleAnalysisAndPlots as mplots
+    from golden_util import build_optic
+    g = Golden("tele_pitch")
+    s = g.spec
+    chain = mp.OEPlacement(dict(s["source"]), [build_optic(o) for o in s["optics"]], list(s["distances"]),
+                           list(s["incidences"]), list(s["plane_angles"]))
+    values = [-0.05, -0.01, 0.0, 0.02, 0.05]
+    chains = chain.get_OE_loop_list(2, "pitch", values)
+    stats = moc.sweep_statistics(chains, s["detector_distance"])
+    assert len(stats) == len(values)
+    for ch, st in zip(chains, stats):
+        final = ch.get_output_rays()[-1]
+        det = mdet.Detector(ch.optical_elements[-1].position)
+        det.autoplace(final, s["detector_distance"])
+        sd, dur = mplots.GetResultSummary(det, final)
+        assert abs(st["SpotSizeSD"] - sd) <= 1e-12 and abs(st["DurationSD"] - dur) <= 1e-7  # different pivots l0
+        assert st["n_rays"] == len(final)
+    assert abs(stats[3]["SpotSizeSD"] - g["SpotSizeSD"]) <= 3e-8  # 5 m telescope noise floor (SURVEY.md C.1)
+    assert abs(stats[3]["DurationSD"] - g["DurationSD"]) <= DELAY_TOL_FS
