@@ -243,17 +243,19 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
   c->smem_bytes = (c->smem_bytes + 15) & ~size_t(15);
   if (c->smem_bytes > 200 * 1024) return bail(ART_E_UNSUPPORTED, "Zernike tables exceed 200 KB of shared memory");
   {
-    const size_t fused = c->smem_bytes + SMEM_MOMENTS_BYTES;  // fused-detector kernels add the moment slots
-    CK(allow_smem(trace_kernel<true, false, true, SURFS_ANY>, c->smem_bytes));
-    CK(allow_smem(trace_kernel<false, false, true, SURFS_ANY>, c->smem_bytes));
-    CK(allow_smem(trace_kernel<true, true, true, SURFS_ANY>, fused));
-    CK(allow_smem(trace_kernel<false, true, true, SURFS_ANY>, fused));
-    CK(allow_smem(trace_kernel<true, true, false, SURFS_ANY>, fused));
-    CK(allow_smem(trace_kernel<false, true, false, SURFS_ANY>, fused));
-    CK(allow_smem(trace_kernel<true, true, false, SURFS_TOROID>, fused));
-    CK(allow_smem(trace_kernel<false, true, false, SURFS_TOROID>, fused));
-    CK(allow_smem(trace_kernel<true, true, false, SURFS_QUADRIC>, fused));
-    CK(allow_smem(trace_kernel<false, true, false, SURFS_QUADRIC>, fused));
+    // dynamic shared memory: tables | moment slots (fused detector) | cp.async input stages (plain trace)
+    const size_t fused = c->smem_bytes + SMEM_MOMENTS_BYTES;
+    const size_t plain = c->smem_bytes + STAGE_BYTES;
+#define ART_ALLOW(DEFS, SURF)                                               \
+  CK(allow_smem(trace_kernel<true, false, DEFS, SURF>, plain));             \
+  CK(allow_smem(trace_kernel<false, false, DEFS, SURF>, plain));            \
+  CK(allow_smem(trace_kernel<true, true, DEFS, SURF>, fused));              \
+  CK(allow_smem(trace_kernel<false, true, DEFS, SURF>, fused));
+    ART_ALLOW(true, SURFS_ANY)
+    ART_ALLOW(false, SURFS_ANY)
+    ART_ALLOW(false, SURFS_TOROID)
+    ART_ALLOW(false, SURFS_QUADRIC)
+#undef ART_ALLOW
   }
   {
     bool tor = false, quad = false;
@@ -290,7 +292,8 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
 static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, const ArtBundleView* in,
                             const ArtBundleView* out_final, const ArtBundleView* out_history, uint32_t flags,
                             const ArtDetector* det, double* x_out, double* y_out, double* l_out,
-                            double* central_out, double* moments_out, cudaStream_t st) {
+                            double* central_out, double* moments_out, cudaStream_t st, bool keep_l2 = false,
+                            double place_distance = 0.0, ArtDetector* place_det = nullptr) {
   if (!c) return fail(ART_E_INVALID, "chain is NULL");
   if (!in) return fail(ART_E_INVALID, "input bundle is NULL");
   if (variant_first < 0 || n_variants < 1 || variant_first + n_variants > c->n_variants)
@@ -344,7 +347,9 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
   if ((size_t)bpv * n_variants > c->partial_rows) return fail(ART_E_INVALID, "internal: partial buffer too small");
   const dim3 grid(bpv, n_variants);
   a.moments_smem_offset = (int)c->smem_bytes;
-  const size_t sm = c->smem_bytes + (det ? (size_t)SMEM_MOMENTS_BYTES : 0);
+  a.stage_smem_offset = (int)c->smem_bytes;
+  a.keep_l2 = keep_l2 ? 1 : 0;
+  const size_t sm = c->smem_bytes + (det ? (size_t)SMEM_MOMENTS_BYTES : (size_t)STAGE_BYTES);
   // Zernike chains run the general kernel; defect-free chains one specialised for their surface class
 #define ART_TRACE_LAUNCH(INC, DET)                                                                      \
   do {                                                                                                  \
@@ -364,7 +369,9 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
     else ART_TRACE_LAUNCH(false, false);
     ART_LAUNCHED();
     if (central_out) {
-      fold_kernel<<<n_variants, TPB, 0, st>>>(c->d_partials, bpv, 0, central_out, nullptr);
+      // place_det: fold the central sums and place the variant's detector in the same launch
+      fold_kernel<<<n_variants, TPB, 0, st>>>(c->d_partials, bpv, place_det ? 3 : 0, central_out, nullptr,
+                                              place_distance, place_det);
       ART_LAUNCHED();
     }
   }
@@ -462,19 +469,23 @@ extern "C" int32_t art_moments_merge(const double* rows, int32_t n_ranks, int32_
   return ART_OK;
 }
 
+// The sweep traces every ray twice (pass 1: central sums, fold + autoplace; pass 2: fused trace +
+// detector) and stores nothing per ray.  The alternative -- trace once, keep each variant's final
+// bundle (57 B/ray) in L2 and run the detector kernel on it -- was built and measured slower on B200
+// (26.3 vs 22.9 ms for 256 variants x 10^6 rays): a variant's rows plus the source bundle do not fit
+// L2 together, and per-variant launches leave the GPU idle between four short dependent kernels.
 extern "C" int32_t art_sweep(ArtChain* chain, int32_t variant_first, int32_t n_variants, const ArtBundleView* in,
                              uint32_t flags, double distance, double* central_out, ArtDetector* det_out,
                              double* moments_out, void* stream) {
-  if (!chain || !det_out || !moments_out) return fail(ART_E_INVALID, "bad argument");
+  if (!chain || !det_out || !moments_out || !in) return fail(ART_E_INVALID, "bad argument");
   double* central = central_out ? central_out : chain->d_central;
   const uint32_t f = flags | ART_TRACE_NO_INCIDENCE;
+  cudaStream_t st = (cudaStream_t)stream;
   int32_t rc = launch_trace(chain, variant_first, n_variants, in, nullptr, nullptr, f, nullptr, nullptr, nullptr,
-                            nullptr, central, nullptr, (cudaStream_t)stream);
-  if (rc) return rc;
-  rc = art_detector_autoplace(central, distance, n_variants, det_out, stream);
+                            nullptr, central, nullptr, st, false, distance, det_out);
   if (rc) return rc;
   return launch_trace(chain, variant_first, n_variants, in, nullptr, nullptr, f, det_out, nullptr, nullptr, nullptr,
-                      nullptr, moments_out, (cudaStream_t)stream);
+                      nullptr, moments_out, st);
 }
 
 extern "C" int32_t art_delays(const double* l, const uint8_t* alive, int64_t n, int32_t n_variants,

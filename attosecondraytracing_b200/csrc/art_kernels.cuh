@@ -43,6 +43,8 @@ struct TraceArgs {
   const ArtDetector* det;  // fused detector (device, per variant) or null
   double *x_out, *y_out, *l_out;
   int moments_smem_offset;  // byte offset of the per-thread moment slots in dynamic smem (WITH_DET)
+  int stage_smem_offset;    // byte offset of the cp.async input stages in dynamic smem (plain trace)
+  int keep_l2;              // final-bundle stores with the default cache policy (re-read from L2 next)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -60,8 +62,20 @@ __device__ __forceinline__ void load_pair(const double* __restrict__ col, long l
     b = 0.0;
   }
 }
+// Stores are streaming (st.global.cs, evict-first: the bundle is written once and read by nobody soon)
+// unless `keep` asks for the default policy because the very next kernel re-reads the rows from L2
+// (the chunked sweep).
 __device__ __forceinline__ void store_pair(double* __restrict__ col, long long i, bool vec, bool w0, bool w1,
-                                           double a, double b) {
+                                           double a, double b, bool keep = false) {
+  if (keep) {
+    if (vec && w0 && w1) {
+      *reinterpret_cast<double2*>(col + i) = make_double2(a, b);
+    } else {
+      if (w0) col[i] = a;
+      if (w1) col[i + 1] = b;
+    }
+    return;
+  }
   if (vec && w0 && w1) {
     __stcs(reinterpret_cast<double2*>(col + i), make_double2(a, b));
   } else {
@@ -202,7 +216,26 @@ __device__ __forceinline__ void moments_add(ACC& m, const DetHit& h, double l0, 
 #ifndef ART_PREFETCH
 #define ART_PREFETCH 0
 #endif
+#ifndef ART_STAGE
+#define ART_STAGE 1
+#endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Input staging: every thread copies the 16-byte column slices of its NEXT ray pair into its own
+// shared-memory slots with cp.async (LDGSTS) while it traces the current pair, so the DRAM latency of
+// the source columns is hidden behind the FP64 work without costing registers.  Slots are private
+// to the issuing thread: cp.async.wait_group is the only synchronisation needed.
+constexpr int STAGE_COLS = 8;  // px py pz ux uy uz intensity path
+constexpr int STAGE_BYTES = 2 * STAGE_COLS * TPB * 16;
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+}
 static_assert(ART_RPT == 1 || ART_RPT == 2, "ART_RPT must be 1 or 2");
 static_assert(RPT == 2, "column helpers are written for pairs");
 
@@ -216,9 +249,9 @@ __device__ __forceinline__ void load_rays(const double* __restrict__ col, long l
 }
 template <int N>
 __device__ __forceinline__ void store_rays(double* __restrict__ col, long long i, bool vec, const bool (&w)[N],
-                                           const double (&v)[N]) {
+                                           const double (&v)[N], bool keep) {
   if (N == 2) {
-    store_pair(col, i, vec, w[0], w[N - 1], v[0], v[N - 1]);
+    store_pair(col, i, vec, w[0], w[N - 1], v[0], v[N - 1], keep);
   } else {
     if (w[0]) __stcs(col + i, v[0]);
   }
@@ -226,7 +259,7 @@ __device__ __forceinline__ void store_rays(double* __restrict__ col, long long i
 
 template <int N>
 __device__ __forceinline__ void store_bundle(const BundleDev& O, long long at, bool vec, bool two, const Ray (&r)[N],
-                                             bool want_inc) {
+                                             bool want_inc, bool keep = false) {
   bool w[N];
   double v[N];
 #pragma unroll
@@ -234,7 +267,7 @@ __device__ __forceinline__ void store_bundle(const BundleDev& O, long long at, b
 #define ART_ST(colp, field)                         \
   {                                                 \
     _Pragma("unroll") for (int q = 0; q < N; ++q) v[q] = r[q].field; \
-    store_rays<N>(colp, at, vec, w, v);             \
+    store_rays<N>(colp, at, vec, w, v, keep);       \
   }
   if (O.px) {
     ART_ST(O.px, px) ART_ST(O.py, py) ART_ST(O.pz, pz)
@@ -259,6 +292,11 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
   // two rays in lock-step (lane pack D2) unless the chain carries Zernike defects, whose evaluation
   // would not fit two lanes in the register file
   constexpr bool PACK = (N == 2) && !HAS_DEF;
+  // cp.async input staging: plain trace only (the fused-detector kernels spend their shared memory on
+  // the moment slots and read an L2-resident source bundle)
+  // and, by measurement, only where Ray.incidence is not computed (with it the extra live state of the
+  // staging loop costs more in spills than the hidden latency gains: 0.469 vs 0.430 ms on cfg2)
+  constexpr bool STAGE = (N == 2) && !WITH_DET && !WANT_INC && (ART_STAGE != 0);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ElemDev* sE = reinterpret_cast<ElemDev*>(smem_raw);
   double* sZ = reinterpret_cast<double*>(smem_raw + sizeof(ElemDev) * ART_MAX_ELEMENTS);
@@ -304,10 +342,27 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
   m.base = reinterpret_cast<double*>(smem_raw + a.moments_smem_offset) + threadIdx.x;
   if constexpr (WITH_DET) moments_init(m);
 
-  for (long long item = (long long)blockIdx.x * TPB + threadIdx.x; item < nitems;
-       item += (long long)gridDim.x * TPB) {
+  double2* const sStage = reinterpret_cast<double2*>(smem_raw + a.stage_smem_offset) + threadIdx.x;
+  auto stage_issue = [&](int stage, long long it) {
+    const long long ii = it * 2;
+    double2* b = sStage + stage * STAGE_COLS * TPB;
+    cp_async16(b + 0 * TPB, a.in.px + ii); cp_async16(b + 1 * TPB, a.in.py + ii); cp_async16(b + 2 * TPB, a.in.pz + ii);
+    cp_async16(b + 3 * TPB, a.in.ux + ii); cp_async16(b + 4 * TPB, a.in.uy + ii); cp_async16(b + 5 * TPB, a.in.uz + ii);
+    if (a.in.inten) cp_async16(b + 6 * TPB, a.in.inten + ii);
+    if (a.in.path) cp_async16(b + 7 * TPB, a.in.path + ii);
+    cp_async_commit();
+  };
+  const long long stride = (long long)gridDim.x * TPB;
+  long long item = (long long)blockIdx.x * TPB + threadIdx.x;
+  int stage = 0;
+  bool staged = STAGE && item < nitems && (item * 2 + 1 < n);
+  if (staged) stage_issue(0, item);
+  for (; item < nitems; item += stride, stage ^= 1) {
     const long long i = item * N;
     const bool two = (N == 2) && (i + 1 < n);
+    const long long nxt = item + stride;
+    const bool staged_next = STAGE && nxt < nitems && (nxt * 2 + 1 < n);
+    if (staged_next) stage_issue(stage ^ 1, nxt);
 #if ART_PREFETCH
     {  // pull the columns of this thread's NEXT rays into L2 while this pair is traced
       const long long inext = (item + (long long)gridDim.x * TPB) * N;
@@ -320,7 +375,20 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
 #endif
     Ray r[N];
     double w[N];
-    {
+    if (staged) {
+      if (staged_next) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      const double2* b = sStage + stage * STAGE_COLS * TPB;
+      double2 v;
+      v = b[0 * TPB]; r[0].px = v.x; r[N - 1].px = v.y;
+      v = b[1 * TPB]; r[0].py = v.x; r[N - 1].py = v.y;
+      v = b[2 * TPB]; r[0].pz = v.x; r[N - 1].pz = v.y;
+      v = b[3 * TPB]; r[0].ux = v.x; r[N - 1].ux = v.y;
+      v = b[4 * TPB]; r[0].uy = v.x; r[N - 1].uy = v.y;
+      v = b[5 * TPB]; r[0].uz = v.x; r[N - 1].uz = v.y;
+      if (a.in.inten) { v = b[6 * TPB]; w[0] = v.x; w[N - 1] = v.y; } else { w[0] = w[N - 1] = 1.0; }
+      if (a.in.path) { v = b[7 * TPB]; r[0].path = v.x; r[N - 1].path = v.y; } else { r[0].path = r[N - 1].path = 0.0; }
+    } else {
       double t[N];
 #define ART_LD(colp, field)                      \
   load_rays<N>(colp, i, two, t);                 \
@@ -341,6 +409,7 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
         for (int q = 0; q < N; ++q) w[q] = 1.0;
       }
     }
+    staged = staged_next;
 #pragma unroll
     for (int q = 0; q < N; ++q) {
       r[q].alive = (q == 0) || two;
@@ -376,7 +445,7 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
         if (a.has_hist) store_bundle<N>(a.hist[k], row + i, out_vec, two, r, WANT_INC);
       }
     }
-    if (a.has_out) store_bundle<N>(a.out, row + i, out_vec, two, r, WANT_INC);
+    if (a.has_out) store_bundle<N>(a.out, row + i, out_vec, two, r, WANT_INC, a.keep_l2 != 0);
 
     {
       double s[ART_CENTRAL_LEN - 1];
@@ -498,9 +567,17 @@ __global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetAr
 //   mode 1: row = central | moments  -> central_out (nullable), moments_out
 //   mode 2: row = moments            -> moments_out
 // ---------------------------------------------------------------------------------------------
+__host__ __device__ inline void detector_fill(const double* centre, const double* normal, const double* refpoint,
+                                              const double* cvec, double l0, double n_rays, ArtDetector* D);
+__device__ inline void autoplace_row(const double* c, double distance, ArtDetector* det);
+
+//   mode 3: as mode 0, and the block's thread 0 then places the variant's detector (autoplace_row)
 __global__ void __launch_bounds__(TPB) fold_kernel(const double* __restrict__ partials, int nblocks, int mode,
                                                    double* __restrict__ central_out,
-                                                   double* __restrict__ moments_out) {
+                                                   double* __restrict__ moments_out, double distance = 0.0,
+                                                   ArtDetector* __restrict__ det_out = nullptr) {
+  const bool place = mode == 3;
+  if (place) mode = 0;
   __shared__ double sRed[NWARP * PLEN_FUSED];
   const int v = blockIdx.x;
   const int plen = mode == 0 ? PLEN_TRACE : (mode == 1 ? PLEN_FUSED : PLEN_DET);
@@ -546,6 +623,10 @@ __global__ void __launch_bounds__(TPB) fold_kernel(const double* __restrict__ pa
       moments_out[(size_t)v * ART_MOMENTS_LEN + j] = x;
     }
   }
+  if (place) {
+    __syncthreads();  // central_out row of this variant is complete (written by threads 0..9 of this block)
+    if (threadIdx.x == 0) autoplace_row(central_out + (size_t)v * ART_CENTRAL_LEN, distance, det_out + v);
+  }
 }
 
 // merge of the moments rows gathered from all ranks: rows[rank][variant][24] -> out[variant][24]
@@ -580,11 +661,7 @@ __host__ __device__ inline void detector_fill(const double* centre, const double
   D->n_rays = n_rays;
 }
 
-__global__ void autoplace_kernel(const double* __restrict__ central, double distance, int n_variants,
-                                 ArtDetector* __restrict__ det) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n_variants) return;
-  const double* c = central + (size_t)v * ART_CENTRAL_LEN;
+__device__ inline void autoplace_row(const double* c, double distance, ArtDetector* det) {
   const double N = c[ART_C_N];
   double cv[3] = {c[ART_C_SUX] / N, c[ART_C_SUY] / N, c[ART_C_SUZ] / N};
   const double cn = sqrt(cv[0] * cv[0] + cv[1] * cv[1] + cv[2] * cv[2]);
@@ -592,7 +669,14 @@ __global__ void autoplace_kernel(const double* __restrict__ central, double dist
   const double cp[3] = {c[ART_C_SPX] / N, c[ART_C_SPY] / N, c[ART_C_SPZ] / N};
   const double nrm[3] = {-cv[0], -cv[1], -cv[2]};
   const double ctr[3] = {cp[0] - nrm[0] * distance, cp[1] - nrm[1] * distance, cp[2] - nrm[2] * distance};
-  detector_fill(ctr, nrm, cp, cv, c[ART_C_SPATH] / N + distance, N, det + v);
+  detector_fill(ctr, nrm, cp, cv, c[ART_C_SPATH] / N + distance, N, det);
+}
+
+__global__ void autoplace_kernel(const double* __restrict__ central, double distance, int n_variants,
+                                 ArtDetector* __restrict__ det) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_variants) return;
+  autoplace_row(central + (size_t)v * ART_CENTRAL_LEN, distance, det + v);
 }
 
 // delays in fs relative to the unweighted mean path, ART/ModuleDetector.py:277-278
