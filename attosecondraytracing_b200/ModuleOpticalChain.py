@@ -106,7 +106,7 @@ class OpticalChain:
                         "so you should rather give 'axis' as a numpy-array of length 3.")
 
     def _replace_source(self, P=None, U=None):
-        old = self.source_rays
+        old = self.source_rays.materialize()
         new = RayBundle(old.n, device=old.device, columns=old._names, wavelength=old.wavelength,
                         storage=old._storage.clone())
         new.number = old.number

@@ -119,6 +119,7 @@ class RayBundle:
         self.device = torch.device(device)
         self.wavelength = wavelength
         self.number = None  # optional int64 tensor of explicit ray numbers
+        self.origin = None  # point source: ONE (3,) point shared by all rays instead of px/py/pz columns
         self._names = tuple(columns)
         pad = max(_padded(self.n), 32)
         if storage is None:
@@ -131,15 +132,37 @@ class RayBundle:
         self.version = 0    # bumped by whoever rewrites the columns (cache key of OpticalChain)
 
     # ---- columns ----------------------------------------------------------------------------
+    _POINT = ("px", "py", "pz")
+
     def has(self, name):
-        return name in self._names
+        return name in self._names or (self.origin is not None and name in self._POINT)
 
     def col(self, name):
+        if name not in self._names and self.origin is not None and name in self._POINT:
+            return self.origin[self._POINT.index(name)].expand(self.n)  # stride-0 read-only view
         return self._storage[self._names.index(name), : self.n]
+
+    def trace_flags(self):
+        """Flags the trace entry points need for this bundle's layout (ART_TRACE_UNIFORM_POINT)."""
+        return _cabi.TRACE_UNIFORM_POINT if self.origin is not None else 0
+
+    def materialize(self):
+        """A bundle with real px/py/pz columns (no-op unless this is a uniform-origin point source)."""
+        if self.origin is None:
+            return self
+        names = self._POINT + self._names
+        b = RayBundle(self.n, device=self.device, columns=names, wavelength=self.wavelength)
+        for i, c in enumerate(self._POINT):
+            b.col(c).fill_(float(self.origin[i]))
+        for c in self._names:
+            b.col(c).copy_(self.col(c))
+        b.alive, b.number = self.alive, self.number
+        return b
 
     def __getattr__(self, name):
         if name in _COLUMNS:
-            if name in self.__dict__.get("_names", ()):
+            if name in self.__dict__.get("_names", ()) or (self.__dict__.get("origin") is not None
+                                                            and name in self._POINT):
                 return self.col(name)
             return None
         raise AttributeError(name)
@@ -149,7 +172,9 @@ class RayBundle:
         v = _cabi.ArtBundleView()
         base, stride = self._storage.data_ptr(), self._storage.stride(0) * 8
         for name in _COLUMNS:  # row pointers from the base: an empty slice has no data_ptr of its own
-            setattr(v, name, base + self._names.index(name) * stride if self.has(name) else None)
+            setattr(v, name, base + self._names.index(name) * stride if name in self._names else None)
+        if self.origin is not None:  # uniform point: px, py, pz each point to one double
+            v.px, v.py, v.pz = (self.origin.data_ptr() + 8 * i for i in range(3))
         v.alive = self.alive.untyped_storage().data_ptr() if self.alive is not None else None
         v.n = self.n
         return v
@@ -208,10 +233,13 @@ class RayBundle:
                       storage=self._storage.to(device))
         b.alive = None if self.alive is None else self.alive.to(device)
         b.number = None if self.number is None else self.number.to(device)
+        b.origin = None if self.origin is None else self.origin.to(device)
         return b
 
     def pin_memory(self):
         self._storage = self._storage.pin_memory()
+        if self.origin is not None:
+            self.origin = self.origin.pin_memory()
         return self
 
     # ---- the list facade ----------------------------------------------------------------------
@@ -255,6 +283,8 @@ class RayBundle:
         g = int(self.alive_index()[i])
         row = self._storage[:, g].cpu().numpy()
         vals = dict(zip(self._names, row))
+        if self.origin is not None:
+            vals.update(zip(self._POINT, self.origin.cpu().numpy()))
         num = g if self.number is None else int(self.number[g])
         inc = vals.get("incidence")
         return Ray(np.array([vals["px"], vals["py"], vals["pz"]]), np.array([vals["ux"], vals["uy"], vals["uz"]]),
@@ -282,4 +312,4 @@ class RayBundle:
 
     def content_key(self):
         """Cheap identity of the bundle's content for OpticalChain's result cache."""
-        return (id(self._storage), self.n, self.version)
+        return (id(self._storage), self.n, self.version, None if self.origin is None else tuple(self.origin.tolist()))

@@ -33,6 +33,7 @@ MOMENT_MAX = [M_XMAX, M_YMAX, M_DMAX, M_TMAX]
 
 TRACE_IGNORE_DEFECTS = 1
 TRACE_NO_INCIDENCE = 2
+TRACE_UNIFORM_POINT = 4
 
 c_double_p = C.POINTER(C.c_double)
 c_u8_p = C.POINTER(C.c_uint8)

@@ -93,13 +93,13 @@ static BundleDev to_dev(const ArtBundleView* b) {
   return d;
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-static const char* check_columns(const ArtBundleView* b, bool need_pu) {
+static const char* check_columns(const ArtBundleView* b, bool need_pu, bool uniform_point = false) {
   const double* cols[9] = {b->px, b->py, b->pz, b->ux, b->uy, b->uz, b->path, b->incidence, b->intensity};
   int have = 0;
   for (int i = 0; i < 6; ++i) have += cols[i] != nullptr;
   if (need_pu && have != 6) return "the point and vector columns (px..uz) are required";
   if (have != 0 && have != 6) return "point / vector columns must be given all six or not at all";
-  for (int i = 0; i < 9; ++i)
+  for (int i = uniform_point ? 3 : 0; i < 9; ++i)  // a uniform point is three single doubles
     if (cols[i] && !aligned16(cols[i])) return "ray columns must be 16-byte aligned";
   return nullptr;
 }
@@ -256,6 +256,7 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
     ART_ALLOW(false, SURFS_TOROID)
     ART_ALLOW(false, SURFS_QUADRIC)
 #undef ART_ALLOW
+    CK(allow_smem(detector_kernel, STAGE_BYTES));
   }
   {
     bool tor = false, quad = false;
@@ -299,7 +300,9 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
   if (variant_first < 0 || n_variants < 1 || variant_first + n_variants > c->n_variants)
     return fail(ART_E_INVALID, "variant range outside the chain's variants");
   if (in->n < 0) return fail(ART_E_INVALID, "negative ray count");
-  if (const char* why = check_columns(in, true)) return fail(ART_E_INVALID, std::string("input bundle: ") + why);
+  const bool uniform_point = (flags & ART_TRACE_UNIFORM_POINT) != 0;
+  if (const char* why = check_columns(in, true, uniform_point))
+    return fail(ART_E_INVALID, std::string("input bundle: ") + why);
   if (out_final) {
     if (const char* why = check_columns(out_final, false))
       return fail(ART_E_INVALID, std::string("output bundle: ") + why);
@@ -349,6 +352,7 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
   a.moments_smem_offset = (int)c->smem_bytes;
   a.stage_smem_offset = (int)c->smem_bytes;
   a.keep_l2 = keep_l2 ? 1 : 0;
+  a.uniform_point = uniform_point ? 1 : 0;
   const size_t sm = c->smem_bytes + (det ? (size_t)SMEM_MOMENTS_BYTES : (size_t)STAGE_BYTES);
   // Zernike chains run the general kernel; defect-free chains one specialised for their surface class
 #define ART_TRACE_LAUNCH(INC, DET)                                                                      \
@@ -428,6 +432,8 @@ extern "C" int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bu
   if (!bundle || !det || !moments_out || n_variants < 1) return fail(ART_E_INVALID, "bad argument");
   ArtChain tmp;  // launch-shape defaults when no chain lends its scratch
   if (!chain) {
+    // no chain has opted this device in to the kernel's shared-memory size yet
+    ART_CUDA(cudaFuncSetAttribute(detector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
     int dev = 0;
     ART_CUDA(cudaGetDevice(&dev));
     int sms = 148;
@@ -453,7 +459,7 @@ extern "C" int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bu
   if ((size_t)bpv * n_variants > chain->partial_rows)
     return fail(ART_E_INVALID, "n_variants exceeds the chain's variant count");
   cudaStream_t st = (cudaStream_t)stream;
-  detector_kernel<<<dim3(bpv, n_variants), TPB, 0, st>>>(a);
+  detector_kernel<<<dim3(bpv, n_variants), TPB, STAGE_BYTES, st>>>(a);
   ART_LAUNCHED();
   fold_kernel<<<n_variants, TPB, 0, st>>>(chain->d_partials, bpv, 2, nullptr, moments_out);
   ART_LAUNCHED();
@@ -510,7 +516,10 @@ extern "C" int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t fi
   if (kind != 0 && kind != 1) return fail(ART_E_INVALID, "kind must be 0 (point source) or 1 (plane wave)");
   if (n_total < 1 || first < 0 || count < 0 || first + count > n_total || bundle->n < count)
     return fail(ART_E_INVALID, "bad index range");
-  if (const char* why = check_columns(bundle, true)) return fail(ART_E_INVALID, std::string("bundle: ") + why);
+  const bool no_points = !bundle->px && !bundle->py && !bundle->pz;  // point source kept as a uniform origin
+  if (!(no_points && kind == 0 && bundle->ux && bundle->uy && bundle->uz)) {
+    if (const char* why = check_columns(bundle, true)) return fail(ART_E_INVALID, std::string("bundle: ") + why);
+  }
   SourceArgs a;
   a.kind = kind;
   a.n_total = n_total;
@@ -535,7 +544,7 @@ static double* g_ext_partials[64] = {};  // per device scratch of kIntensityBloc
 extern "C" int32_t art_source_extents(const ArtBundleView* bundle, const double axis[3], double* extents_out,
                                       void* stream) {
   if (!bundle || !axis || !extents_out) return fail(ART_E_INVALID, "NULL argument");
-  if (const char* why = check_columns(bundle, true)) return fail(ART_E_INVALID, std::string("bundle: ") + why);
+  if (!bundle->ux || !bundle->uy || !bundle->uz) return fail(ART_E_INVALID, "bundle: the vector columns are required");
   int dev = 0;
   ART_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(ART_E_UNSUPPORTED, "device index above 63");
@@ -561,7 +570,8 @@ extern "C" int32_t art_source_intensity(const ArtBundleView* bundle, const doubl
                                         double scale, double fraction, void* stream) {
   if (!bundle || !axis) return fail(ART_E_INVALID, "NULL argument");
   if (!bundle->intensity) return fail(ART_E_INVALID, "bundle has no intensity column");
-  if (const char* why = check_columns(bundle, true)) return fail(ART_E_INVALID, std::string("bundle: ") + why);
+  if (!bundle->ux || !bundle->uy || !bundle->uz) return fail(ART_E_INVALID, "bundle: the vector columns are required");
+  if (mode == 1 && !bundle->px) return fail(ART_E_INVALID, "bundle: mode 1 needs the point columns");
   if (mode != 0 && mode != 1) return fail(ART_E_INVALID, "mode must be 0 or 1");
   if (!(fraction > 0.0 && fraction < 1.0)) fraction = 0.1353352832366127;  // 1/e^2, ART/ModuleSource.py:233-238
   IntensityArgs a;
@@ -626,10 +636,12 @@ extern "C" int32_t art_run_host(ArtChain* c, const ArtBundleView* in_host, const
   const double* src[7] = {in_host->px, in_host->py, in_host->pz, in_host->ux,
                           in_host->uy, in_host->uz, in_host->intensity};
   double** dst[7] = {&din.px, &din.py, &din.pz, &din.ux, &din.uy, &din.uz, &din.intensity};
+  const bool uniform_point = (flags & ART_TRACE_UNIFORM_POINT) != 0;
   for (int j = 0; j < 7; ++j) {
     if (!src[j]) continue;
     *dst[j] = col(j);
-    if (n) ART_CUDA(cudaMemcpyAsync(col(j), src[j], sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    const size_t cnt = (uniform_point && j < 3) ? 1 : n;  // point source: one origin for all rays
+    if (cnt) ART_CUDA(cudaMemcpyAsync(col(j), src[j], sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
   }
   if (in_host->path || in_host->alive)
     return fail(ART_E_UNSUPPORTED, "art_run_host starts from a fresh source bundle (no path / alive columns)");
@@ -719,10 +731,12 @@ extern "C" int32_t art_trace_host(ArtChain* c, const ArtBundleView* in_host, con
                           in_host->uy, in_host->uz, in_host->path, in_host->intensity};
   double** dst[8] = {&din.px, &din.py, &din.pz, &din.ux, &din.uy, &din.uz, &din.path, &din.intensity};
   cudaError_t e = cudaSuccess;
+  const bool uniform_point = (flags & ART_TRACE_UNIFORM_POINT) != 0;
   for (int j = 0; j < 8 && e == cudaSuccess; ++j) {
     if (!src[j]) continue;
     *dst[j] = col(j);
-    if (n) e = cudaMemcpyAsync(col(j), src[j], sizeof(double) * n, cudaMemcpyHostToDevice, st);
+    const size_t cnt = (uniform_point && j < 3) ? (cap ? 1 : 0) : n;
+    if (cnt) e = cudaMemcpyAsync(col(j), src[j], sizeof(double) * cnt, cudaMemcpyHostToDevice, st);
   }
   if (e == cudaSuccess && in_host->alive) {
     din.alive = dflags;

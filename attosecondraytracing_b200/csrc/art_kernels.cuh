@@ -6,7 +6,10 @@
 
 namespace art {
 
-constexpr int TPB = 256;       // threads per block
+#ifndef ART_TPB
+#define ART_TPB 256
+#endif
+constexpr int TPB = ART_TPB;   // threads per block
 constexpr int RPT = 2;         // rays per thread: adjacent rays -> 128-bit column accesses
 constexpr int NWARP = TPB / 32;
 
@@ -45,6 +48,7 @@ struct TraceArgs {
   int moments_smem_offset;  // byte offset of the per-thread moment slots in dynamic smem (WITH_DET)
   int stage_smem_offset;    // byte offset of the cp.async input stages in dynamic smem (plain trace)
   int keep_l2;              // final-bundle stores with the default cache policy (re-read from L2 next)
+  int uniform_point;        // in.px/py/pz point to one double each (ART_TRACE_UNIFORM_POINT)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -346,7 +350,9 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
   auto stage_issue = [&](int stage, long long it) {
     const long long ii = it * 2;
     double2* b = sStage + stage * STAGE_COLS * TPB;
-    cp_async16(b + 0 * TPB, a.in.px + ii); cp_async16(b + 1 * TPB, a.in.py + ii); cp_async16(b + 2 * TPB, a.in.pz + ii);
+    if (!a.uniform_point) {
+      cp_async16(b + 0 * TPB, a.in.px + ii); cp_async16(b + 1 * TPB, a.in.py + ii); cp_async16(b + 2 * TPB, a.in.pz + ii);
+    }
     cp_async16(b + 3 * TPB, a.in.ux + ii); cp_async16(b + 4 * TPB, a.in.uy + ii); cp_async16(b + 5 * TPB, a.in.uz + ii);
     if (a.in.inten) cp_async16(b + 6 * TPB, a.in.inten + ii);
     if (a.in.path) cp_async16(b + 7 * TPB, a.in.path + ii);
@@ -380,9 +386,13 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
       else cp_async_wait<0>();
       const double2* b = sStage + stage * STAGE_COLS * TPB;
       double2 v;
-      v = b[0 * TPB]; r[0].px = v.x; r[N - 1].px = v.y;
-      v = b[1 * TPB]; r[0].py = v.x; r[N - 1].py = v.y;
-      v = b[2 * TPB]; r[0].pz = v.x; r[N - 1].pz = v.y;
+      if (a.uniform_point) {  // point source: one origin for all rays (re-read per pair: an L1 hit, no live registers)
+        r[0].px = r[N - 1].px = a.in.px[0]; r[0].py = r[N - 1].py = a.in.py[0]; r[0].pz = r[N - 1].pz = a.in.pz[0];
+      } else {
+        v = b[0 * TPB]; r[0].px = v.x; r[N - 1].px = v.y;
+        v = b[1 * TPB]; r[0].py = v.x; r[N - 1].py = v.y;
+        v = b[2 * TPB]; r[0].pz = v.x; r[N - 1].pz = v.y;
+      }
       v = b[3 * TPB]; r[0].ux = v.x; r[N - 1].ux = v.y;
       v = b[4 * TPB]; r[0].uy = v.x; r[N - 1].uy = v.y;
       v = b[5 * TPB]; r[0].uz = v.x; r[N - 1].uz = v.y;
@@ -393,7 +403,12 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
 #define ART_LD(colp, field)                      \
   load_rays<N>(colp, i, two, t);                 \
   _Pragma("unroll") for (int q = 0; q < N; ++q) r[q].field = t[q];
-      ART_LD(a.in.px, px) ART_LD(a.in.py, py) ART_LD(a.in.pz, pz)
+      if (a.uniform_point) {
+#pragma unroll
+        for (int q = 0; q < N; ++q) { r[q].px = a.in.px[0]; r[q].py = a.in.py[0]; r[q].pz = a.in.pz[0]; }
+      } else {
+        ART_LD(a.in.px, px) ART_LD(a.in.py, py) ART_LD(a.in.pz, pz)
+      }
       ART_LD(a.in.ux, ux) ART_LD(a.in.uy, uy) ART_LD(a.in.uz, uz)
       if (a.in.path) {
         ART_LD(a.in.path, path)
@@ -409,7 +424,6 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
         for (int q = 0; q < N; ++q) w[q] = 1.0;
       }
     }
-    staged = staged_next;
 #pragma unroll
     for (int q = 0; q < N; ++q) {
       r[q].alive = (q == 0) || two;
@@ -423,6 +437,7 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
         if (r[q].alive) win += w[q];
       ART_ACC(ART_C_SW_IN) += win;
     }
+    const bool staged_now = staged;  // (w is re-read after the chain instead of living through it)
 
     if constexpr (PACK) {
       RayT<D2> pr = pack_rays(r[0], r[N - 1]);
@@ -447,6 +462,17 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
     }
     if (a.has_out) store_bundle<N>(a.out, row + i, out_vec, two, r, WANT_INC, a.keep_l2 != 0);
 
+    // the intensities again: from the (still intact) stage slot or an L1/L2 hit -- cheaper than keeping
+    // four registers alive through the whole chain
+    if (a.in.inten) {
+      if (staged_now) {
+        const double2 v = (sStage + stage * STAGE_COLS * TPB)[6 * TPB];
+        w[0] = v.x; w[N - 1] = v.y;
+      } else {
+        load_rays<N>(a.in.inten, i, two, w);
+      }
+    }
+    staged = staged_next;
     {
       double s[ART_CENTRAL_LEN - 1];
 #pragma unroll
@@ -504,7 +530,25 @@ struct DetArgs {
 #ifndef ART_DET_MINB
 #define ART_DET_MINB 2
 #endif
+__device__ __forceinline__ void detector_pair(const DetArgs& a, const ArtDetector& D, long long at, const Ray (&r)[RPT],
+                                              const double (&w)[RPT], const bool (&al)[RPT],
+                                              double (&m)[ART_MOMENTS_LEN]) {
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    if (!al[q]) continue;
+    const DetHit h = detector_ray(D, r[q]);
+    moments_add(m, h, D.l0, w[q]);
+    if (a.x_out) a.x_out[at + q] = h.x;
+    if (a.y_out) a.y_out[at + q] = h.y;
+    if (a.l_out) a.l_out[at + q] = h.L;
+  }
+}
+
+// Streaming kernel: the column slices of a thread's NEXT ray pair are copied into its private
+// shared-memory slots with cp.async while the current pair is evaluated, and the alive flags are
+// fetched two pairs ahead so that the columns of dead pairs are never requested.
 __global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];  // STAGE_BYTES of cp.async slots
   __shared__ double sRed[NWARP * PLEN_DET];
   __shared__ ArtDetector sDet;
   const int v = blockIdx.y;
@@ -517,44 +561,98 @@ __global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetAr
   const long long n = a.n, row = (long long)v * n;
   const bool vec = (row & 1) == 0;
   const long long npairs = (n + 1) >> 1;
-  double m[ART_MOMENTS_LEN];  // registers: measured faster here than shared-memory slots (streaming kernel)
+  const long long stride = (long long)gridDim.x * TPB;
+  double m[ART_MOMENTS_LEN];  // registers: measured faster here than shared-memory slots
   moments_init(m);
-  for (long long pair = (long long)blockIdx.x * TPB + threadIdx.x; pair < npairs;
-       pair += (long long)gridDim.x * TPB) {
-    const long long i = pair << 1;
-    const bool two = i + 1 < n;
-    bool al[RPT] = {true, two};
-    if (a.b.alive) {
-      al[0] = a.b.alive[row + i] != 0;
-      al[1] = two && a.b.alive[row + i + 1] != 0;
+
+  if (vec) {
+    double2* const sStage = reinterpret_cast<double2*>(smem_raw) + threadIdx.x;
+    // alive flags of pair p as bits (bit 0 / bit 1); pairs beyond the end -> 0
+    auto flags_of = [&](long long p) -> unsigned {
+      if (p >= npairs) return 0u;
+      const long long i = p << 1;
+      const bool two = i + 1 < n;
+      if (!a.b.alive) return two ? 3u : 1u;
+      if (two) {
+        const uchar2 f = *reinterpret_cast<const uchar2*>(a.b.alive + row + i);
+        return (f.x ? 1u : 0u) | (f.y ? 2u : 0u);
+      }
+      return a.b.alive[row + i] ? 1u : 0u;
+    };
+    auto issue = [&](int stage, long long p) {  // only full pairs are staged
+      const long long at = row + (p << 1);
+      double2* bs = sStage + stage * STAGE_COLS * TPB;
+      cp_async16(bs + 0 * TPB, a.b.px + at); cp_async16(bs + 1 * TPB, a.b.py + at); cp_async16(bs + 2 * TPB, a.b.pz + at);
+      cp_async16(bs + 3 * TPB, a.b.ux + at); cp_async16(bs + 4 * TPB, a.b.uy + at); cp_async16(bs + 5 * TPB, a.b.uz + at);
+      if (a.b.path) cp_async16(bs + 6 * TPB, a.b.path + at);
+      if (a.b.inten) cp_async16(bs + 7 * TPB, a.b.inten + (p << 1));
+      cp_async_commit();
+    };
+    long long pair = (long long)blockIdx.x * TPB + threadIdx.x;
+    unsigned fl = flags_of(pair);
+    bool staged = fl != 0 && ((pair << 1) + 1 < n);
+    if (staged) issue(0, pair);
+    unsigned fl_next = flags_of(pair + stride);
+    int stage = 0;
+    for (; pair < npairs; pair += stride, stage ^= 1) {
+      const long long nxt = pair + stride;
+      const bool staged_next = fl_next != 0 && nxt < npairs && ((nxt << 1) + 1 < n);
+      if (staged_next) issue(stage ^ 1, nxt);
+      const unsigned fl_next2 = flags_of(nxt + stride);  // in flight during this pair's arithmetic
+      if (fl != 0) {
+        const long long i = pair << 1;
+        Ray r[RPT];
+        double w[RPT];
+        const bool al[RPT] = {(fl & 1u) != 0, (fl & 2u) != 0};
+        if (staged) {
+          if (staged_next) cp_async_wait<1>();
+          else cp_async_wait<0>();
+          const double2* bs = sStage + stage * STAGE_COLS * TPB;
+          double2 t;
+          t = bs[0 * TPB]; r[0].px = t.x; r[1].px = t.y;
+          t = bs[1 * TPB]; r[0].py = t.x; r[1].py = t.y;
+          t = bs[2 * TPB]; r[0].pz = t.x; r[1].pz = t.y;
+          t = bs[3 * TPB]; r[0].ux = t.x; r[1].ux = t.y;
+          t = bs[4 * TPB]; r[0].uy = t.x; r[1].uy = t.y;
+          t = bs[5 * TPB]; r[0].uz = t.x; r[1].uz = t.y;
+          if (a.b.path) { t = bs[6 * TPB]; r[0].path = t.x; r[1].path = t.y; } else { r[0].path = r[1].path = 0.0; }
+          if (a.b.inten) { t = bs[7 * TPB]; w[0] = t.x; w[1] = t.y; } else { w[0] = w[1] = 1.0; }
+        } else {  // the single ray at the ragged end
+          r[0].px = a.b.px[row + i]; r[0].py = a.b.py[row + i]; r[0].pz = a.b.pz[row + i];
+          r[0].ux = a.b.ux[row + i]; r[0].uy = a.b.uy[row + i]; r[0].uz = a.b.uz[row + i];
+          r[0].path = a.b.path ? a.b.path[row + i] : 0.0;
+          w[0] = a.b.inten ? a.b.inten[i] : 1.0;
+          r[1] = r[0];
+          w[1] = 0.0;
+        }
+        detector_pair(a, sDet, row + i, r, w, al, m);
+      }
+      fl = fl_next;
+      fl_next = fl_next2;
+      staged = staged_next;
     }
-    if (!al[0] && !al[1]) continue;
-    Ray r[RPT];
-    double w[RPT];
-    const bool v2 = two && vec;
-    load_pair(a.b.px + row, i, v2, r[0].px, r[1].px);
-    load_pair(a.b.py + row, i, v2, r[0].py, r[1].py);
-    load_pair(a.b.pz + row, i, v2, r[0].pz, r[1].pz);
-    load_pair(a.b.ux + row, i, v2, r[0].ux, r[1].ux);
-    load_pair(a.b.uy + row, i, v2, r[0].uy, r[1].uy);
-    load_pair(a.b.uz + row, i, v2, r[0].uz, r[1].uz);
-    if (a.b.path) load_pair(a.b.path + row, i, v2, r[0].path, r[1].path);
-    else r[0].path = r[1].path = 0.0;
-    if (two && !vec) {
-      r[1].px = a.b.px[row + i + 1]; r[1].py = a.b.py[row + i + 1]; r[1].pz = a.b.pz[row + i + 1];
-      r[1].ux = a.b.ux[row + i + 1]; r[1].uy = a.b.uy[row + i + 1]; r[1].uz = a.b.uz[row + i + 1];
-      if (a.b.path) r[1].path = a.b.path[row + i + 1];
-    }
-    if (a.b.inten) load_pair(a.b.inten, i, two, w[0], w[1]);
-    else w[0] = w[1] = 1.0;
+  } else {
+    // odd row offset (odd n, odd variant): 8-byte accesses
+    for (long long pair = (long long)blockIdx.x * TPB + threadIdx.x; pair < npairs; pair += stride) {
+      const long long i = pair << 1;
+      const bool two = i + 1 < n;
+      bool al[RPT] = {true, two};
+      if (a.b.alive) {
+        al[0] = a.b.alive[row + i] != 0;
+        al[1] = two && a.b.alive[row + i + 1] != 0;
+      }
+      if (!al[0] && !al[1]) continue;
+      Ray r[RPT];
+      double w[RPT];
 #pragma unroll
-    for (int q = 0; q < RPT; ++q) {
-      if (!al[q]) continue;
-      const DetHit h = detector_ray(sDet, r[q]);
-      moments_add(m, h, sDet.l0, w[q]);
-      if (a.x_out) a.x_out[row + i + q] = h.x;
-      if (a.y_out) a.y_out[row + i + q] = h.y;
-      if (a.l_out) a.l_out[row + i + q] = h.L;
+      for (int q = 0; q < RPT; ++q) {
+        const long long at = row + i + ((q == 1 && two) ? 1 : 0);
+        r[q].px = a.b.px[at]; r[q].py = a.b.py[at]; r[q].pz = a.b.pz[at];
+        r[q].ux = a.b.ux[at]; r[q].uy = a.b.uy[at]; r[q].uz = a.b.uz[at];
+        r[q].path = a.b.path ? a.b.path[at] : 0.0;
+        w[q] = a.b.inten ? a.b.inten[at - row] : 1.0;
+      }
+      detector_pair(a, sDet, row + i, r, w, al, m);
     }
   }
   block_reduce_row<PLEN_DET>(m, [](int j) { return moment_op(j); }, sRed,
@@ -732,7 +830,7 @@ __global__ void source_kernel(const SourceArgs a) {
       ux = a.rot[2]; uy = a.rot[5]; uz = a.rot[8];
     }
     const double un = 1.0 / sqrt(fma(ux, ux, fma(uy, uy, uz * uz)));
-    a.b.px[j] = px; a.b.py[j] = py; a.b.pz[j] = pz;
+    if (a.b.px) { a.b.px[j] = px; a.b.py[j] = py; a.b.pz[j] = pz; }
     a.b.ux[j] = ux * un; a.b.uy[j] = uy * un; a.b.uz[j] = uz * un;
     if (a.b.path) a.b.path[j] = 0.0;
     if (a.b.alive) a.b.alive[j] = 1;
@@ -757,7 +855,7 @@ __global__ void __launch_bounds__(TPB) intensity_kernel(const IntensityArgs a) {
   double mx[2] = {0.0, 0.0};
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < a.n; i += (long long)gridDim.x * TPB) {
     const double ang = unit_angle(a.axis[0], a.axis[1], a.axis[2], a.b.ux[i], a.b.uy[i], a.b.uz[i]);
-    const double px = a.b.px[i], py = a.b.py[i], pz = a.b.pz[i];
+    const double px = a.b.px ? a.b.px[i] : 0.0, py = a.b.px ? a.b.py[i] : 0.0, pz = a.b.px ? a.b.pz[i] : 0.0;
     const double dist = sqrt(fma(px, px, fma(py, py, pz * pz)));
     if (a.pass == 0) {
       mx[0] = fmax(mx[0], ang);

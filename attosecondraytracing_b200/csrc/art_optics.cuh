@@ -526,16 +526,18 @@ ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict
     ox = ox * sc; oy = oy * sc; oz = oz * sc;
     if (WANT_INC && inc_here) inc = unit_angle(-e.ux, -e.uy, -e.uz, nx, ny, nz);
   }
-  // element -> lab frame (:306-309): p = R^T (p_e - centre) + pos, u = R^T u_e
+  // element -> lab frame (:306-309): p = R^T (p_e - centre) + pos, u = R^T u_e.
+  // Written unconditionally: a lane that missed is dead from here on and its columns are never read
+  // or stored again, so the old P, U need not stay alive through this function just to be selected back.
   const T dx = hx - E.ctr[0], dy = hy - E.ctr[1], dz = hz - E.ctr[2];
-  r.px = sel(hit, mfma(E.rot[0], dx, mfma(E.rot[3], dy, mfma(E.rot[6], dz, E.pos[0]))), r.px);
-  r.py = sel(hit, mfma(E.rot[1], dx, mfma(E.rot[4], dy, mfma(E.rot[7], dz, E.pos[1]))), r.py);
-  r.pz = sel(hit, mfma(E.rot[2], dx, mfma(E.rot[5], dy, mfma(E.rot[8], dz, E.pos[2]))), r.pz);
-  r.ux = sel(hit, mfma(E.rot[0], ox, mfma(E.rot[3], oy, E.rot[6] * oz)), r.ux);
-  r.uy = sel(hit, mfma(E.rot[1], ox, mfma(E.rot[4], oy, E.rot[7] * oz)), r.uy);
-  r.uz = sel(hit, mfma(E.rot[2], ox, mfma(E.rot[5], oy, E.rot[8] * oz)), r.uz);
-  r.path = sel(hit, r.path + mabs(t), r.path);  // |P - A| with |u| = 1 (ModuleMirror.py:904, ModuleMask.py:100)
-  r.inc = sel(hit, inc, r.inc);
+  r.px = mfma(E.rot[0], dx, mfma(E.rot[3], dy, mfma(E.rot[6], dz, E.pos[0])));
+  r.py = mfma(E.rot[1], dx, mfma(E.rot[4], dy, mfma(E.rot[7], dz, E.pos[1])));
+  r.pz = mfma(E.rot[2], dx, mfma(E.rot[5], dy, mfma(E.rot[8], dz, E.pos[2])));
+  r.ux = mfma(E.rot[0], ox, mfma(E.rot[3], oy, E.rot[6] * oz));
+  r.uy = mfma(E.rot[1], ox, mfma(E.rot[4], oy, E.rot[7] * oz));
+  r.uz = mfma(E.rot[2], ox, mfma(E.rot[5], oy, E.rot[8] * oz));
+  r.path = r.path + mabs(t);  // |P - A| with |u| = 1 (ModuleMirror.py:904, ModuleMask.py:100)
+  r.inc = inc;
   r.alive = hit;
 }
 

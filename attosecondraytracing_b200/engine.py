@@ -93,7 +93,8 @@ class DeviceChain:
         (n_variants, 10) of the central-ray sums, or None."""
         self._check_bundle(bundle)
         nv = self.n_variants - variant_first if n_variants is None else n_variants
-        flags = (_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0) | (0 if want_incidence else _cabi.TRACE_NO_INCIDENCE)
+        flags = ((_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0) | (0 if want_incidence else _cabi.TRACE_NO_INCIDENCE)
+                 | bundle.trace_flags())
         outs = []
         hist_arr = None
         final_view = None
@@ -129,7 +130,7 @@ class DeviceChain:
         for k in range(K):
             views[k].alive = alive[k].data_ptr()
             views[k].n = nv * n
-        flags = (_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0) | _cabi.TRACE_NO_INCIDENCE
+        flags = (_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0) | _cabi.TRACE_NO_INCIDENCE | bundle.trace_flags()
         vin = bundle.view()
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().art_trace(self._handle, variant_first, nv, C.byref(vin), None, views, flags, None,
@@ -151,6 +152,7 @@ class DeviceChain:
     def moments(self, bundle, det, intensity=None, want_points=False, out=None):
         """Detector moments of a stored bundle (n_variants x n rows).  Returns (moments, x, y, l)."""
         self._check_bundle(bundle)
+        bundle = bundle.materialize()  # the detector kernel reads per-ray points
         nv = det.shape[0]
         mom = out if out is not None else torch.empty((nv, _cabi.MOMENTS_LEN), dtype=torch.float64, device=self.device)
         x = y = l = None
@@ -182,7 +184,7 @@ class DeviceChain:
         """Fused trace + detector for known detectors; returns (moments, central, x, y, l)."""
         self._check_bundle(bundle)
         nv = det.shape[0]
-        flags = (_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0) | _cabi.TRACE_NO_INCIDENCE
+        flags = (_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0) | _cabi.TRACE_NO_INCIDENCE | bundle.trace_flags()
         mom = torch.empty((nv, _cabi.MOMENTS_LEN), dtype=torch.float64, device=self.device)
         central = torch.empty((nv, _cabi.CENTRAL_LEN), dtype=torch.float64, device=self.device)
         x = y = l = None
@@ -203,7 +205,7 @@ class DeviceChain:
         triple to reuse)."""
         self._check_bundle(bundle)
         nv = self.n_variants - variant_first if n_variants is None else n_variants
-        flags = _cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0
+        flags = (_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0) | bundle.trace_flags()
         if out is not None:
             mom, central, det = out
         else:
@@ -221,7 +223,7 @@ class DeviceChain:
         autoplace, moments, D2H inside one synchronous C call.  Returns (moments, central, det) numpy."""
         if host_bundle.device.type != "cpu":
             raise RuntimeError("run_host takes a host-resident bundle")
-        flags = (_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0)
+        flags = (_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0) | host_bundle.trace_flags()
         if out_host is None or not out_host.has("incidence"):
             flags |= _cabi.TRACE_NO_INCIDENCE
         mom = np.empty(_cabi.MOMENTS_LEN)

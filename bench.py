@@ -61,9 +61,10 @@ def source_properties(w, n_total):
     return sp
 
 
-def algorithmic_bytes(n_src, n_surv, want_inc=True, with_intensity=True):
-    """read P,U (+intensity) per source ray; write P,U,path(,incidence)+alive per survivor."""
-    return (48 + (8 if with_intensity else 0)) * n_src + (57 + (8 if want_inc else 0)) * n_surv
+def algorithmic_bytes(n_src, n_surv, want_inc=True, in_columns=7):
+    """read the source columns (P, U, intensity = 7 doubles; 4 for a point source whose
+    origin is shared by all rays); write P,U,path(,incidence)+alive per survivor."""
+    return 8 * in_columns * n_src + (57 + (8 if want_inc else 0)) * n_surv
 
 
 # ----------------------------------------------------------------------------------------------
@@ -205,7 +206,7 @@ def workload_config(w, args, n_total):
     return {"workload": f"{w['name']}: {w['scene']} ({', '.join(o['kind'] for o in s['optics'])}), "
                         f"{n_total} rays per GPU, detector autoplace at {s['detector_distance']} mm",
             "rays_per_gpu": int(n_total), "elements": len(s["optics"]),
-            "l2": "inputs larger than L2 (>= 480 MB of ray columns per step)", "ignore_defects": True}
+            "l2": "inputs larger than L2 (>= 320 MB of source columns + 650 MB of outputs per step)", "ignore_defects": True}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -321,7 +322,7 @@ def run_b200(args, w, oes):
         entering = [int(x) for x in e[0].cpu()]
         n_surv = int(sv[0])
         kernel_name = "trace_kernel<WANT_INC=1,WITH_DET=0>"
-        abytes = algorithmic_bytes(count, n_surv)
+        abytes = algorithmic_bytes(count, n_surv, in_columns=len(src._names))
     interactions_rank = int(sum(entering))
 
     def barrier():
@@ -402,7 +403,7 @@ def run_b200(args, w, oes):
     e2e = None
     if not sweep:
         host = src.to("cpu").pin_memory()
-        h2d = (7 * 8) * count
+        h2d = 8 * len(src._names) * count + (24 if src.origin is not None else 0)
         d2h = 8 * (_cabi.MOMENTS_LEN + _cabi.CENTRAL_LEN) + 8 * _cabi.DETECTOR_DOUBLES
         for _ in range(2):
             chain.run_host(host, distance)
@@ -421,9 +422,10 @@ def run_b200(args, w, oes):
     else:
         # the sweep's per-step host traffic is the pose table in (built once) and the result rows out
         host = src.to("cpu").pin_memory()
-        h2d = (7 * 8) * count
+        h2d = 8 * len(src._names) * count + (24 if src.origin is not None else 0)
         d2h = 8 * nv_rank * (_cabi.MOMENTS_LEN + _cabi.CENTRAL_LEN)
         dsrc = engine.RayBundle(count, device=dev, columns=host._names)
+        dsrc.origin = src.origin
         barrier()
         t0 = time.perf_counter()
         e2e_steps = max(2, min(args.steps, 5))
@@ -453,7 +455,7 @@ def run_b200(args, w, oes):
             # two traces per variant (central pass + detector pass); per-ray outputs are never stored
             flops = 2.0 * nv_rank * chain_flops(oes, [e_ / nv_rank for e_ in entering], n_surv / nv_rank, True)
             flops_kernel = flops / 2.0
-            abytes = (7 * 8) * count * nv_rank  # the source bundle re-read per variant (L2-resident)
+            abytes = 8 * len(src._names) * count * nv_rank  # the source bundle re-read per variant (L2-resident)
             roof = {"bound": "hbm", "achieved": abytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": abytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                     "note": "FP64-bound path: the source bundle stays in L2; the binding ceiling is the fp64 entry"}

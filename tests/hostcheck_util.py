@@ -14,7 +14,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "attosecondraytracing_b200", "csrc")
 
 
 def build():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("art_device.cuh", "art_lowering.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("art_device.cuh", "art_optics.cuh", "art_lowering.h")]
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

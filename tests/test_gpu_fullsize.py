@@ -27,6 +27,7 @@ def _gather(bundle, idx, RayBundle, intensity=None):
         small.col(n).copy_(bundle.col(n)[idx])
     if bundle.alive is not None:
         small.alive.copy_(bundle.alive[idx])
+    small.origin = bundle.origin
     small.number = idx.clone()
     small.invalidate()
     return small
