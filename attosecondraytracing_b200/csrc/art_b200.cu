@@ -246,11 +246,15 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
     // dynamic shared memory: tables | moment slots (fused detector) | cp.async input stages (plain trace)
     const size_t fused = c->smem_bytes + SMEM_MOMENTS_BYTES;
     const size_t plain = c->smem_bytes + STAGE_BYTES;
-#define ART_ALLOW(DEFS, SURF)                                               \
-  CK(allow_smem(trace_kernel<true, false, DEFS, SURF>, plain));             \
-  CK(allow_smem(trace_kernel<false, false, DEFS, SURF>, plain));            \
-  CK(allow_smem(trace_kernel<true, true, DEFS, SURF>, fused));              \
-  CK(allow_smem(trace_kernel<false, true, DEFS, SURF>, fused));
+#define ART_ALLOW(DEFS, SURF)                                                      \
+  CK(allow_smem(trace_kernel<true, false, DEFS, SURF, false>, plain));             \
+  CK(allow_smem(trace_kernel<false, false, DEFS, SURF, false>, plain));            \
+  CK(allow_smem(trace_kernel<true, true, DEFS, SURF, false>, fused));              \
+  CK(allow_smem(trace_kernel<false, true, DEFS, SURF, false>, fused));             \
+  CK(allow_smem(trace_kernel<true, false, DEFS, SURF, true>, plain));              \
+  CK(allow_smem(trace_kernel<false, false, DEFS, SURF, true>, plain));             \
+  CK(allow_smem(trace_kernel<true, true, DEFS, SURF, true>, fused));               \
+  CK(allow_smem(trace_kernel<false, true, DEFS, SURF, true>, fused));
     ART_ALLOW(true, SURFS_ANY)
     ART_ALLOW(false, SURFS_ANY)
     ART_ALLOW(false, SURFS_TOROID)
@@ -355,12 +359,17 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
   a.uniform_point = uniform_point ? 1 : 0;
   const size_t sm = c->smem_bytes + (det ? (size_t)SMEM_MOMENTS_BYTES : (size_t)STAGE_BYTES);
   // Zernike chains run the general kernel; defect-free chains one specialised for their surface class
-#define ART_TRACE_LAUNCH(INC, DET)                                                                      \
-  do {                                                                                                  \
-    if (c->has_defects) trace_kernel<INC, DET, true, SURFS_ANY><<<grid, TPB, sm, st>>>(a);              \
-    else if (c->surfs == SURFS_TOROID) trace_kernel<INC, DET, false, SURFS_TOROID><<<grid, TPB, sm, st>>>(a);   \
-    else if (c->surfs == SURFS_QUADRIC) trace_kernel<INC, DET, false, SURFS_QUADRIC><<<grid, TPB, sm, st>>>(a); \
-    else trace_kernel<INC, DET, false, SURFS_ANY><<<grid, TPB, sm, st>>>(a);                            \
+#define ART_TRACE_LAUNCH2(INC, DET, UPT)                                                                      \
+  do {                                                                                                       \
+    if (c->has_defects) trace_kernel<INC, DET, true, SURFS_ANY, UPT><<<grid, TPB, sm, st>>>(a);              \
+    else if (c->surfs == SURFS_TOROID) trace_kernel<INC, DET, false, SURFS_TOROID, UPT><<<grid, TPB, sm, st>>>(a);   \
+    else if (c->surfs == SURFS_QUADRIC) trace_kernel<INC, DET, false, SURFS_QUADRIC, UPT><<<grid, TPB, sm, st>>>(a); \
+    else trace_kernel<INC, DET, false, SURFS_ANY, UPT><<<grid, TPB, sm, st>>>(a);                            \
+  } while (0)
+#define ART_TRACE_LAUNCH(INC, DET)                       \
+  do {                                                   \
+    if (uniform_point) ART_TRACE_LAUNCH2(INC, DET, true); \
+    else ART_TRACE_LAUNCH2(INC, DET, false);             \
   } while (0)
   if (det) {
     if (want_inc) ART_TRACE_LAUNCH(true, true);
@@ -380,6 +389,7 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
     }
   }
 #undef ART_TRACE_LAUNCH
+#undef ART_TRACE_LAUNCH2
   return ART_OK;
 }
 

@@ -204,6 +204,7 @@ __device__ __forceinline__ void moments_add(ACC& m, const DetHit& h, double l0, 
 //   WITH_DET  also evaluate the detector of this variant and accumulate its moments (K2 fused)
 //   HAS_DEF   the chain carries Zernike defects (otherwise that code and its registers are compiled out)
 //   SURFS     surface classes compiled in (SURFS_ANY / SURFS_TOROID / SURFS_QUADRIC; planes and masks always)
+//   UPT       the input bundle is a point source with ONE origin (ART_TRACE_UNIFORM_POINT)
 // Build-time tunables (measured on B200): ART_RPT rays per thread (2 = 128-bit column
 // accesses), ART_MINB resident blocks per SM asked of the register allocator, ART_SMEM_ACC keeps
 // the per-thread central sums in shared memory instead of registers.
@@ -290,7 +291,7 @@ __device__ __forceinline__ void store_bundle(const BundleDev& O, long long at, b
   }
 }
 
-template <bool WANT_INC, bool WITH_DET, bool HAS_DEF, int SURFS>
+template <bool WANT_INC, bool WITH_DET, bool HAS_DEF, int SURFS, bool UPT>
 __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a) {
   constexpr int N = ART_RPT;
   // two rays in lock-step (lane pack D2) unless the chain carries Zernike defects, whose evaluation
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
   auto stage_issue = [&](int stage, long long it) {
     const long long ii = it * 2;
     double2* b = sStage + stage * STAGE_COLS * TPB;
-    if (!a.uniform_point) {
+    if (!UPT) {
       cp_async16(b + 0 * TPB, a.in.px + ii); cp_async16(b + 1 * TPB, a.in.py + ii); cp_async16(b + 2 * TPB, a.in.pz + ii);
     }
     cp_async16(b + 3 * TPB, a.in.ux + ii); cp_async16(b + 4 * TPB, a.in.uy + ii); cp_async16(b + 5 * TPB, a.in.uz + ii);
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
       else cp_async_wait<0>();
       const double2* b = sStage + stage * STAGE_COLS * TPB;
       double2 v;
-      if (a.uniform_point) {  // point source: one origin for all rays (re-read per pair: an L1 hit, no live registers)
+      if (UPT) {  // point source: one origin for all rays (re-read per pair: an L1 hit, no live registers)
         r[0].px = r[N - 1].px = a.in.px[0]; r[0].py = r[N - 1].py = a.in.py[0]; r[0].pz = r[N - 1].pz = a.in.pz[0];
       } else {
         v = b[0 * TPB]; r[0].px = v.x; r[N - 1].px = v.y;
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
 #define ART_LD(colp, field)                      \
   load_rays<N>(colp, i, two, t);                 \
   _Pragma("unroll") for (int q = 0; q < N; ++q) r[q].field = t[q];
-      if (a.uniform_point) {
+      if (UPT) {
 #pragma unroll
         for (int q = 0; q < N; ++q) { r[q].px = a.in.px[0]; r[q].py = a.in.py[0]; r[q].pz = a.in.pz[0]; }
       } else {
@@ -437,7 +438,6 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
         if (r[q].alive) win += w[q];
       ART_ACC(ART_C_SW_IN) += win;
     }
-    const bool staged_now = staged;  // (w is re-read after the chain instead of living through it)
 
     if constexpr (PACK) {
       RayT<D2> pr = pack_rays(r[0], r[N - 1]);
@@ -462,16 +462,6 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
     }
     if (a.has_out) store_bundle<N>(a.out, row + i, out_vec, two, r, WANT_INC, a.keep_l2 != 0);
 
-    // the intensities again: from the (still intact) stage slot or an L1/L2 hit -- cheaper than keeping
-    // four registers alive through the whole chain
-    if (a.in.inten) {
-      if (staged_now) {
-        const double2 v = (sStage + stage * STAGE_COLS * TPB)[6 * TPB];
-        w[0] = v.x; w[N - 1] = v.y;
-      } else {
-        load_rays<N>(a.in.inten, i, two, w);
-      }
-    }
     staged = staged_next;
     {
       double s[ART_CENTRAL_LEN - 1];
