@@ -171,6 +171,21 @@ def cpu_oracle_rate(w, oes, n_total, sample, workers):
     return inter / wall, inter, wall
 
 
+def reference_literal_rate(w):
+    """Speed of the UNMODIFIED reference on this workload's seeded subset, as measured in the build
+    container while generating the golden fixture (tests/golden/<cfg>_sub*.npz metadata; the reference
+    itself cannot travel to the GPU box)."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from golden_util import Golden, golden_names
+        names = [n for n in golden_names() if n.startswith(w["name"] + "_sub")]
+        g = Golden(names[0])
+        return {"value": g.spec["interactions"] / g.spec["reference_trace_seconds"], "unit": UNIT, "cores": 1,
+                "where": "build container, ART v0.93 RayTracingCalculation on fixture " + names[0]}
+    except Exception:
+        return None
+
+
 def run_reference(args, w, oes):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -462,8 +477,15 @@ def run_b200(args, w, oes):
         else:
             flops_kernel = chain_flops(oes, entering, n_surv, True) - n_surv * 60.0  # detector is another kernel
             achieved = abytes / (k_ms * 1e-3) / 1e9
+            traffic = None
+            try:  # DRAM bytes of this kernel from the committed ncu --set full capture of the same command
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+                if w["name"] in tj and not args.rays:
+                    traffic = tj[w["name"]]["traffic"]
+            except Exception:
+                pass
             roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None}
+                    "traffic": traffic}
         roof.update({"kernel": kernel_name, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": abytes,
                      "peak_source": peak_src,
                      "fp64": {"model_flops_per_launch": flops_kernel,
@@ -491,7 +513,8 @@ def run_b200(args, w, oes):
             rate, inter, wall = cpu_oracle_rate(w, oes, n_cpu, sample, 1)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{sample} rays of the same {n_cpu}-ray bundle, numpy oracle "
-                                              f"(oracle/art_oracle.py), {wall:.1f} s"}
+                                              f"(oracle/art_oracle.py), {wall:.1f} s",
+                                    "reference_literal": reference_literal_rate(w)}
         print(json.dumps(line), flush=True)
     chain.close()
     if world > 1:
