@@ -138,11 +138,28 @@ def _oracle_elements(oes):
     return els
 
 
+def _cpu_source(sp, idx):
+    """Rows `idx` of the synthetic bundle for the CPU legs (oracle generators; the Gaussian weights are
+    normalised with the bundle axis = +x and the edge ray, which is what the full-bundle normalisation
+    amounts to for a Vogel spiral)."""
+    import art_oracle as orc
+    n = sp["NumberRays"]
+    if sp["Divergence"] == 0:
+        radius = sp["SourceSize"] / 2
+        P, U, num = orc.plane_wave_disk(np.zeros(3), orc.EX, radius, n, idx)
+        inten = np.exp(-2 * (orc.norm(P) / radius) ** 2)
+    else:
+        P, U, num = orc.point_source(np.zeros(3), orc.EX, sp["Divergence"], n, idx)
+        ang = orc.angle_between(np.broadcast_to(orc.EX, U.shape), U)
+        inten = np.exp(-2 * (np.tan(ang) / sp["Divergence"]) ** 2)
+    return P, U, inten
+
+
 def _cpu_worker(args):
     import art_oracle as orc
     sp, els, idx, dist = args
-    P, U, num, inten = orc.source_for(sp, k=idx)
-    t0 = time.perf_counter()
+    P, U, inten = _cpu_source(sp, idx)
+    t0 = time.perf_counter()  # timed: the path itself (trace + detector + statistics), not the source generation
     traced = orc.trace_chain(P, U, els, ignore_defects=True)
     last = traced[-1]
     if last["index"].size > 1:
@@ -152,7 +169,8 @@ def _cpu_worker(args):
 
 
 def cpu_oracle_rate(w, oes, n_total, sample, workers):
-    """Interactions/s of the numpy oracle on `sample` rays of the workload split over `workers` processes."""
+    """Interactions/s of the numpy oracle on `sample` rays of the workload split over `workers`
+    processes that run concurrently: interactions / slowest worker's compute time."""
     import multiprocessing as mpc
     sp = source_properties(w, n_total)
     els = _oracle_elements(oes)
@@ -160,15 +178,23 @@ def cpu_oracle_rate(w, oes, n_total, sample, workers):
     idx = np.linspace(0, n_src - 1, sample).astype(np.int64)
     chunks = [c for c in np.array_split(idx, workers) if c.size]
     dist = w["scene_spec"]["detector_distance"]
-    t0 = time.perf_counter()
     if workers == 1:
         res = [_cpu_worker((sp, els, chunks[0], dist))]
     else:
         with mpc.get_context("fork").Pool(workers) as pool:
             res = pool.map(_cpu_worker, [(sp, els, c, dist) for c in chunks])
-    wall = time.perf_counter() - t0
+    wall = max(r[1] for r in res)
     inter = sum(r[0] for r in res)
     return inter / wall, inter, wall
+
+
+def auto_sample(w, oes, n_total, workers, seconds, lo=2000, hi=4_000_000):
+    """Sample size (rays) whose CPU pass takes about `seconds`, from a small probe of the same workload."""
+    probe = 4000 * workers
+    cpu_oracle_rate(w, oes, n_total, probe, workers)  # imports, page-in
+    rate, inter, wall = cpu_oracle_rate(w, oes, n_total, probe, workers)
+    per_ray = wall / (probe / workers)  # seconds per ray per worker
+    return int(min(hi, max(lo, workers * seconds / per_ray)))
 
 
 def reference_literal_rate(w):
@@ -192,8 +218,9 @@ def run_reference(args, w, oes):
         return
     cores = os.cpu_count() or 1
     n_total = w["rays"]
-    sample = args.cpu_sample or 400_000
-    cpu_oracle_rate(w, oes, n_total, min(sample, 20000), cores)  # warm-up (imports, page-in)
+    # each step is a bounded sample of the workload: ~0.6 s of CPU work per step so that the default
+    # --steps 200 --warmup 10 run ends within a few minutes
+    sample = args.cpu_sample or auto_sample(w, oes, n_total, cores, 0.6)
     for _ in range(max(args.warmup - 1, 0)):
         cpu_oracle_rate(w, oes, n_total, sample, cores)
     rates, inter_total, t_total = [], 0, 0.0
@@ -507,9 +534,8 @@ def run_b200(args, w, oes):
             "result": {k: s[k] for k in ("SpotSizeSD", "DurationSD", "ETransmission") if k in s},
         }
         if not args.no_cpu_baseline and world == 1:
-            sample = args.cpu_sample or 200_000
             n_cpu = n if sweep else n * world
-            cpu_oracle_rate(w, oes, n_cpu, 10000, 1)
+            sample = args.cpu_sample or auto_sample(w, oes, n_cpu, 1, 15.0)  # ~15 s on one core
             rate, inter, wall = cpu_oracle_rate(w, oes, n_cpu, sample, 1)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{sample} rays of the same {n_cpu}-ray bundle, numpy oracle "
