@@ -218,9 +218,9 @@ def run_reference(args, w, oes):
         return
     cores = os.cpu_count() or 1
     n_total = w["rays"]
-    # each step is a bounded sample of the workload: ~0.6 s of CPU work per step so that the default
+    # each step is a bounded sample of the workload: ~0.3 s of CPU work per step so that the default
     # --steps 200 --warmup 10 run ends within a few minutes
-    sample = args.cpu_sample or auto_sample(w, oes, n_total, cores, 0.6)
+    sample = args.cpu_sample or auto_sample(w, oes, n_total, cores, 0.3)
     for _ in range(max(args.warmup - 1, 0)):
         cpu_oracle_rate(w, oes, n_total, sample, cores)
     rates, inter_total, t_total = [], 0, 0.0
