@@ -157,6 +157,15 @@ class Detector:
                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return out[r["idx"]].cpu().numpy()
 
+    def get_scan_sums(self, RayList):
+        """The 32 scan sums of the bundle on this detector (art_detector_scan_moments): the input of the
+        closed-form detector-distance optimiser (ModuleProcessing.FindOptimalDistance)."""
+        from .engine import DeviceChain
+        r = self._evaluate(RayList)
+        scan = DeviceChain.scan_moments(_Scratchless(r["bundle"].device), r["bundle"], r["det"])
+        torch.cuda.current_stream().synchronize()
+        return scan.cpu().numpy()[0]
+
     def get_statistics(self, RayList, RayListIn=None):
         """All bundle statistics from ONE kernel pass (dict: SpotSizeSD mm, DurationSD fs, weighted
         variants, Diameter, NA, ...) without materialising per-ray lists."""

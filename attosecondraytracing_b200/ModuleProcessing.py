@@ -217,6 +217,33 @@ def ReturnNumericalAperture(RayList, RefractiveIndex: float = 1):
     return float(torch.sin(ang.max())) * RefractiveIndex
 
 
+def FindOptimalDistance(Detector, RayList, OptFor="intensity", Amplitude=None, Precision=3, IntensityWeighted=False,
+                        verbose=False):
+    """Detector position that minimises the spot size ("size"), the duration ("duration") or
+    SpotSize^2 * Duration ("intensity") within +-Amplitude of the current distance
+    (ART/ModuleProcessing.py:369-460).  Returns (moved copy of Detector, OptSizeSpot mm, OptDuration fs).
+
+    The reference re-intersects every ray with 80 trial detectors (and therefore subsamples to 1000
+    random rays, ARTmain.py:168); here ONE kernel pass over ALL rays yields 32 sums from which the
+    statistics at any detector shift follow in closed form, and the reference's search schedule is
+    evaluated on those."""
+    from .engine import optimal_shift_from_scan
+    scan = Detector.get_scan_sums(RayList)
+    st = Detector.get_statistics(RayList)
+    first = Detector.get_distance()
+    if verbose:
+        print(f"Searching optimal detector position for *{OptFor}* ...", end="", flush=True)
+    s, spot, dur, amp = optimal_shift_from_scan(scan, first, st["SpotSizeSD"], st["NA"], OptFor, Amplitude, Precision,
+                                                IntensityWeighted)
+    moving = Detector.copy_detector()
+    moving.shiftByDistance(float(s))
+    if not first - amp + 10**-Precision < moving.get_distance() < first + amp - 10**-Precision:
+        print("There`s no minimum-size/duration focus in the searched range.")
+    if verbose:
+        print("\r\033[K", end="", flush=True)
+    return moving, spot, dur
+
+
 def _hash_list_of_objects(objs):
     """Summed hashes, as ART/ModuleProcessing.py:597-602 (kept for small host-side lists)."""
     return sum(hash(o) for o in objs)

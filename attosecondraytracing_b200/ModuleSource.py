@@ -19,40 +19,45 @@ from .ModuleOpticalRay import RayBundle
 _SRC_COLUMNS = ("px", "py", "pz", "ux", "uy", "uz", "intensity")
 
 
-def _generate(kind, n_total, first, count, rho, axis, origin, wavelength, device):
+def _generate(kind, n_total, first, count, rho, axis, origin, wavelength, device, stride=1):
     device = require_cuda(device)
     # a point source keeps ONE origin for all rays instead of three point columns (24 B/ray less)
     cols = _SRC_COLUMNS[3:] if kind == 0 else _SRC_COLUMNS
     b = RayBundle(count, device=device, columns=cols, wavelength=wavelength)
     if kind == 0:
         b.origin = torch.as_tensor(np.asarray(origin, dtype=np.float64), device=device).clone()
-    if first != 0:
-        b.number = torch.arange(first, first + count, device=device, dtype=torch.int64)
+    if first != 0 or stride != 1:
+        b.number = first + stride * torch.arange(count, device=device, dtype=torch.int64)
     v = b.view()
     v.intensity = None
     if kind == 0:
         v.px = v.py = v.pz = None  # the generator writes directions only
     with torch.cuda.device(device):
-        _cabi.check(_cabi.lib().art_source_generate(kind, n_total, first, count, float(rho), _cabi.vec3(axis),
+        _cabi.check(_cabi.lib().art_source_generate(kind, n_total, first, count, stride, float(rho), _cabi.vec3(axis),
                                                     _cabi.vec3(origin), C.byref(v), _stream()))
     b.col("intensity").fill_(1.0)
     return b
 
 
-def PointSource(S, Axis, Divergence, NbRays, Wavelength=None, device=None, first=0, count=None):
+def _slice_count(n_rays, first, stride):
+    return max(0, (n_rays - first + stride - 1) // stride)
+
+
+def PointSource(S, Axis, Divergence, NbRays, Wavelength=None, device=None, first=0, count=None, stride=1):
     """Rays from the point S filling a cone of half-angle Divergence (rad) about Axis on Vogel's
-    spiral (ART/ModuleSource.py:54-81).  `first`/`count` select a slice of the NbRays-ray bundle."""
-    count = NbRays - first if count is None else count
-    return _generate(0, NbRays, first, count, np.tan(Divergence), Axis, S, Wavelength, device)
+    spiral (ART/ModuleSource.py:54-81).  `first`/`count`/`stride` select rays first, first+stride, ...
+    of the NbRays-ray bundle (one rank's share)."""
+    count = _slice_count(NbRays, first, stride) if count is None else count
+    return _generate(0, NbRays, first, count, np.tan(Divergence), Axis, S, Wavelength, device, stride)
 
 
-def PlaneWaveDisk(Centre, Axis, Radius, NbRays, Wavelength=None, device=None, first=0, count=None):
+def PlaneWaveDisk(Centre, Axis, Radius, NbRays, Wavelength=None, device=None, first=0, count=None, stride=1):
     """Collimated rays from a disk (ART/ModuleSource.py:135-169).  As in the reference the bundle
     holds NbRays-1 rays: points 0 .. NbRays-2 of the NbRays-point spiral."""
-    count = NbRays - 1 - first if count is None else count
-    if first + count > NbRays - 1:
+    count = _slice_count(NbRays - 1, first, stride) if count is None else count
+    if count > 0 and first + (count - 1) * stride > NbRays - 2:
         raise ValueError("PlaneWaveDisk(NbRays) has NbRays-1 rays")
-    return _generate(1, NbRays, first, count, Radius, Axis, Centre, Wavelength, device)
+    return _generate(1, NbRays, first, count, Radius, Axis, Centre, Wavelength, device, stride)
 
 
 def ApplyGaussianIntensityToRayList(RayList, IntensityFraction=1 / np.e**2, group=None, axis=None, scale=None):
@@ -94,7 +99,7 @@ def ApplyGaussianIntensityToRayList(RayList, IntensityFraction=1 / np.e**2, grou
 
 
 def synthetic_source(SourceProperties, first_optic_support=None, device=None, first=0, count=None, group=None,
-                     intensity=True):
+                     intensity=True, stride=1):
     """The source bundle `OEPlacement` launches (ART/ModuleProcessing.py:55-79): from the origin along
     +x; a plane-wave disk when Divergence == 0 (radius SourceSize/2, or from the first optic's
     support when SourceSize == 0), else a point source; Gaussian intensities down to 1/e^2 at the edge.
@@ -111,11 +116,11 @@ def synthetic_source(SourceProperties, first_optic_support=None, device=None, fi
             radius = 0.5 * min(sup.dimX, sup.dimY) if hasattr(sup, "dimX") else sup.radius
         else:
             radius = size / 2
-        b = PlaneWaveDisk(origin, axis, radius, n, Wavelength=wl, device=device, first=first, count=count)
+        b = PlaneWaveDisk(origin, axis, radius, n, Wavelength=wl, device=device, first=first, count=count, stride=stride)
     else:
         if size != 0:
             raise NotImplementedError("ExtendedSource bundles are not generated on the device")
-        b = PointSource(origin, axis, div, n, Wavelength=wl, device=device, first=first, count=count)
+        b = PointSource(origin, axis, div, n, Wavelength=wl, device=device, first=first, count=count, stride=stride)
     if intensity:
         ApplyGaussianIntensityToRayList(b, 1 / np.e**2, group=group)
     return b

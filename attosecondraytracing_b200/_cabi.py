@@ -27,6 +27,9 @@ CENTRAL_LEN = 10
 (M_N, M_SX, M_SY, M_SXX, M_SYY, M_SD, M_SDD, M_SW, M_SWX, M_SWY, M_SWXX, M_SWYY, M_SWD, M_SWDD,
  M_XMIN, M_XMAX, M_YMIN, M_YMAX, M_DMIN, M_DMAX, M_TMAX) = range(21)
 MOMENTS_LEN = 24
+SCAN_LEN = 32
+(S_N, S_SW, S_X, S_Y, S_AX, S_AY, S_XX, S_YY, S_AXAX, S_AYAY, S_XAX, S_YAY, S_D, S_G, S_DD, S_GG, S_DG) = range(17)
+S_WEIGHTED = 17
 MOMENT_SUM = list(range(0, 14)) + [21, 22, 23]
 MOMENT_MIN = [M_XMIN, M_YMIN, M_DMIN]
 MOMENT_MAX = [M_XMAX, M_YMAX, M_DMAX, M_TMAX]
@@ -102,12 +105,14 @@ _SIGNATURES = {
     "art_detector_make": (C.c_int32, [c_double_p, c_double_p, c_double_p, C.c_double, C.POINTER(ArtDetector)]),
     "art_detector_moments": (C.c_int32, [C.c_void_p, C.POINTER(ArtBundleView), C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "art_detector_scan_moments": (C.c_int32, [C.c_void_p, C.POINTER(ArtBundleView), C.c_int32, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]),
     "art_moments_merge": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "art_sweep": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(ArtBundleView), C.c_uint32, C.c_double,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "art_delays": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p]),
-    "art_source_generate": (C.c_int32, [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_double_p,
+    "art_source_generate": (C.c_int32, [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_double_p,
                                         c_double_p, C.POINTER(ArtBundleView), C.c_void_p]),
     "art_source_extents": (C.c_int32, [C.POINTER(ArtBundleView), c_double_p, C.c_void_p, C.c_void_p]),
     "art_source_intensity": (C.c_int32, [C.POINTER(ArtBundleView), c_double_p, C.c_int32, C.c_double, C.c_double,

@@ -476,6 +476,41 @@ extern "C" int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bu
   return ART_OK;
 }
 
+extern "C" int32_t art_detector_scan_moments(ArtChain* chain, const ArtBundleView* bundle, int32_t n_variants,
+                                             const ArtDetector* det, double* scan_out, void* stream) {
+  if (!bundle || !det || !scan_out || n_variants < 1) return fail(ART_E_INVALID, "bad argument");
+  if (const char* why = check_columns(bundle, true)) return fail(ART_E_INVALID, std::string("bundle: ") + why);
+  if (bundle->n < 0 || bundle->n % n_variants != 0)
+    return fail(ART_E_INVALID, "bundle must hold n_variants * n rays");
+  ArtChain tmp;
+  if (!chain) {
+    int dev = 0;
+    ART_CUDA(cudaGetDevice(&dev));
+    int sms = 148;
+    ART_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    tmp.sm_count = sms;
+    tmp.partial_rows = (size_t)sms * 8 + (size_t)n_variants + 8;
+    int32_t rc = global_scratch(tmp.partial_rows, &tmp.d_partials);
+    if (rc) return rc;
+    chain = &tmp;
+  }
+  DetArgs a;
+  a.b = to_dev(bundle);
+  a.n = bundle->n / n_variants;
+  a.det = det;
+  a.x_out = a.y_out = a.l_out = nullptr;
+  a.partials = chain->d_partials;
+  const int bpv = blocks_per_variant(chain, a.n, n_variants, 1);
+  if ((size_t)bpv * n_variants > chain->partial_rows)
+    return fail(ART_E_INVALID, "n_variants exceeds the chain's variant count");
+  cudaStream_t st = (cudaStream_t)stream;
+  scan_kernel<<<dim3(bpv, n_variants), TPB, 0, st>>>(a);
+  ART_LAUNCHED();
+  fold_kernel<<<n_variants, TPB, 0, st>>>(chain->d_partials, bpv, 4, nullptr, scan_out);
+  ART_LAUNCHED();
+  return ART_OK;
+}
+
 extern "C" int32_t art_moments_merge(const double* rows, int32_t n_ranks, int32_t n_variants, double* out,
                                      void* stream) {
   if (!rows || !out || n_ranks < 1 || n_variants < 1) return fail(ART_E_INVALID, "bad argument");
@@ -519,12 +554,13 @@ extern "C" int32_t art_delays(const double* l, const uint8_t* alive, int64_t n, 
 // -------------------------------------------------------------------------------------------------
 // sources
 // -------------------------------------------------------------------------------------------------
-extern "C" int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t first, int64_t count, double rho,
-                                       const double axis[3], const double origin[3], const ArtBundleView* bundle,
-                                       void* stream) {
+extern "C" int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t first, int64_t count, int64_t stride,
+                                       double rho, const double axis[3], const double origin[3],
+                                       const ArtBundleView* bundle, void* stream) {
   if (!bundle || !axis || !origin) return fail(ART_E_INVALID, "NULL argument");
   if (kind != 0 && kind != 1) return fail(ART_E_INVALID, "kind must be 0 (point source) or 1 (plane wave)");
-  if (n_total < 1 || first < 0 || count < 0 || first + count > n_total || bundle->n < count)
+  if (n_total < 1 || first < 0 || count < 0 || stride < 1 || bundle->n < count ||
+      (count > 0 && first + (count - 1) * stride >= n_total))
     return fail(ART_E_INVALID, "bad index range");
   const bool no_points = !bundle->px && !bundle->py && !bundle->pz;  // point source kept as a uniform origin
   if (!(no_points && kind == 0 && bundle->ux && bundle->uy && bundle->uz)) {
@@ -535,6 +571,7 @@ extern "C" int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t fi
   a.n_total = n_total;
   a.first = first;
   a.count = count;
+  a.stride = stride;
   a.rho = rho;
   const double ez[3] = {0.0, 0.0, 1.0};
   rotation_from_to(ez, axis, a.rot);  // RotationRayList(RayList, ez, Axis), ART/ModuleSource.py:79,167

@@ -649,11 +649,57 @@ __global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetAr
                              a.partials + ((size_t)v * gridDim.x + blockIdx.x) * PLEN_DET);
 }
 
+// Scan sums for FindOptimalDistance (ART/ModuleProcessing.py:317-460), layout ART_S_* of the header.
+__global__ void __launch_bounds__(TPB, 2) scan_kernel(const DetArgs a) {
+  __shared__ double sRed[NWARP * ART_SCAN_LEN];
+  __shared__ ArtDetector sDet;
+  const int v = blockIdx.y;
+  {
+    const double* ds = reinterpret_cast<const double*>(a.det + v);
+    double* dd = reinterpret_cast<double*>(&sDet);
+    for (int i = threadIdx.x; i < (int)(sizeof(ArtDetector) / sizeof(double)); i += TPB) dd[i] = ds[i];
+  }
+  __syncthreads();
+  const long long n = a.n, row = (long long)v * n;
+  double m[ART_SCAN_LEN];
+#pragma unroll
+  for (int j = 0; j < ART_SCAN_LEN; ++j) m[j] = 0.0;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) {
+    if (a.b.alive && !a.b.alive[row + i]) continue;
+    Ray r;
+    r.px = a.b.px[row + i]; r.py = a.b.py[row + i]; r.pz = a.b.pz[row + i];
+    r.ux = a.b.ux[row + i]; r.uy = a.b.uy[row + i]; r.uz = a.b.uz[row + i];
+    r.path = a.b.path ? a.b.path[row + i] : 0.0;
+    const double w = a.b.inten ? a.b.inten[i] : 1.0;
+    const DetHit h = detector_ray(sDet, r);
+    const double d = h.L - sDet.l0;
+    // cu = cvec.u; g = 1/cu; gp = g - 1 = (|u - cvec|^2 / 2) / cu without cancellation (unit vectors)
+    const double cu = fma(sDet.cvec[0], r.ux, fma(sDet.cvec[1], r.uy, sDet.cvec[2] * r.uz));
+    const double ex = r.ux - sDet.cvec[0], ey = r.uy - sDet.cvec[1], ez = r.uz - sDet.cvec[2];
+    const double g = fdiv(1.0, cu);
+    const double gp = 0.5 * fma(ex, ex, fma(ey, ey, ez * ez)) * g;
+    const double ax = g * fma(sDet.rot[0], r.ux, fma(sDet.rot[1], r.uy, sDet.rot[2] * r.uz));
+    const double ay = g * fma(sDet.rot[3], r.ux, fma(sDet.rot[4], r.uy, sDet.rot[5] * r.uz));
+    const double t[15] = {h.x, h.y, ax, ay, h.x * h.x, h.y * h.y, ax * ax, ay * ay, h.x * ax, h.y * ay,
+                          d, gp, d * d, gp * gp, d * gp};
+    m[ART_S_N] += 1.0;
+    m[ART_S_SW] += w;
+#pragma unroll
+    for (int j = 0; j < 15; ++j) {
+      m[ART_S_X + j] += t[j];
+      m[ART_S_WEIGHTED + j] = fma(w, t[j], m[ART_S_WEIGHTED + j]);
+    }
+  }
+  block_reduce_row<ART_SCAN_LEN>(m, [](int) { return 0; }, sRed,
+                                 a.partials + ((size_t)v * gridDim.x + blockIdx.x) * ART_SCAN_LEN);
+}
+
 // ---------------------------------------------------------------------------------------------
 // second reduction stage: one block per variant folds that variant's block rows in a fixed order.
 //   mode 0: row = central            -> central_out
 //   mode 1: row = central | moments  -> central_out (nullable), moments_out
 //   mode 2: row = moments            -> moments_out
+//   mode 4: row = scan sums (ART_SCAN_LEN, all additive) -> moments_out
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ inline void detector_fill(const double* centre, const double* normal, const double* refpoint,
                                               const double* cvec, double l0, double n_rays, ArtDetector* D);
@@ -668,11 +714,13 @@ __global__ void __launch_bounds__(TPB) fold_kernel(const double* __restrict__ pa
   if (place) mode = 0;
   __shared__ double sRed[NWARP * PLEN_FUSED];
   const int v = blockIdx.x;
-  const int plen = mode == 0 ? PLEN_TRACE : (mode == 1 ? PLEN_FUSED : PLEN_DET);
+  const int plen = mode == 0 ? PLEN_TRACE : (mode == 1 ? PLEN_FUSED : (mode == 4 ? (int)ART_SCAN_LEN : PLEN_DET));
   const int moff = mode == 1 ? ART_CENTRAL_LEN : 0;  // where the moments start in a row
   const double* base = partials + (size_t)v * nblocks * plen;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  auto op_of = [&](int j) { return (mode == 0 || (mode == 1 && j < ART_CENTRAL_LEN)) ? 0 : moment_op(j - moff); };
+  auto op_of = [&](int j) {
+    return (mode == 0 || mode == 4 || (mode == 1 && j < ART_CENTRAL_LEN)) ? 0 : moment_op(j - moff);
+  };
   // each thread folds whole rows b = tid, tid + TPB, ... (all columns of a row are independent loads)
   double acc[PLEN_FUSED];
 #pragma unroll
@@ -707,6 +755,8 @@ __global__ void __launch_bounds__(TPB) fold_kernel(const double* __restrict__ pa
       } else {
         moments_out[(size_t)v * ART_MOMENTS_LEN + (j - ART_CENTRAL_LEN)] = x;
       }
+    } else if (mode == 4) {
+      moments_out[(size_t)v * ART_SCAN_LEN + j] = x;
     } else {
       moments_out[(size_t)v * ART_MOMENTS_LEN + j] = x;
     }
@@ -790,7 +840,7 @@ __global__ void delays_kernel(const double* __restrict__ l, const uint8_t* __res
 // ---------------------------------------------------------------------------------------------
 struct SourceArgs {
   int kind;
-  long long n_total, first, count;
+  long long n_total, first, count, stride;
   double rho;
   double rot[9];
   double origin[3];
@@ -800,7 +850,7 @@ __global__ void source_kernel(const SourceArgs a) {
   const double golden = 3.141592653589793 * (3.0 - sqrt(5.0));
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.count;
        j += (long long)gridDim.x * blockDim.x) {
-    const double k = (double)(a.first + j);
+    const double k = (double)(a.first + j * a.stride);
     const double rad = sqrt(k / (double)a.n_total) * a.rho;
     double s, c;
     sincos(golden * k, &s, &c);

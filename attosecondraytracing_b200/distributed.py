@@ -1,6 +1,7 @@
 """Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink; gloo in CPU tests).
 
-The path shards by contiguous ray-index ranges (rays are independent through the whole chain) or,
+The path shards the ray index (round-robin for balance, or contiguous ranges; rays are independent
+through the whole chain) or,
 for misalignment sweeps, by chain variants.  There is NO per-ray traffic between ranks; the only
 exchanges are the all-reduces of two tiny rows per detector:
     central sums (10 doubles, SUM)  -> every rank places the identical detector (Detector.autoplace)
@@ -25,6 +26,13 @@ def shard_range(n, rank, world):
     lo = (rank * n) // world
     hi = ((rank + 1) * n) // world
     return lo, hi - lo
+
+
+def shard_strided(n, rank, world):
+    """(first, count, stride) of rank's round-robin share of n items: rank, rank + world, ...  Used for
+    ray bundles: an aperture typically blocks a contiguous range of Vogel-spiral indices, so
+    contiguous shards would leave some ranks with only dead rays."""
+    return rank, max(0, (n - rank + world - 1) // world), world
 
 
 def is_distributed(group=None):

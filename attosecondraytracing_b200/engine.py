@@ -171,6 +171,22 @@ class DeviceChain:
                                                          _ptr(l), _ptr(mom), _stream()))
         return mom, x, y, l
 
+    def scan_moments(self, bundle, det):
+        """The ART_SCAN_LEN sums per variant from which spot / duration SDs at any detector shift follow
+        (FindOptimalDistance in closed form).  Returns an (n_variants, 32) tensor."""
+        self._check_bundle(bundle)
+        bundle = bundle.materialize()
+        nv = det.shape[0]
+        out = torch.empty((nv, _cabi.SCAN_LEN), dtype=torch.float64, device=self.device)
+        v = bundle.view()
+        if not bundle.has("intensity"):
+            shared = getattr(bundle, "shared_intensity", None)
+            v.intensity = shared.data_ptr() if shared is not None else None
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().art_detector_scan_moments(self._handle, C.byref(v), nv, _ptr(det), _ptr(out),
+                                                              _stream()))
+        return out
+
     def delays(self, l, alive, det, moments, n_variants=1):
         """Per-ray delays (fs) relative to the unweighted mean path; NaN for dead rays."""
         out = torch.full_like(l, float("nan"))
@@ -282,6 +298,57 @@ def summary_from_moments(m, central=None):
         c = np.asarray(central, dtype=np.float64)
         out["ETransmission"] = float(100 * c[_cabi.C_SW_OUT] / c[_cabi.C_SW_IN])   # ModuleAnalysisAndPlots.py:62-77
     return out
+
+
+def scan_statistics(scan, s, weighted=False):
+    """(spot size SD in mm, duration SD in fs) with the detector moved by `s` mm along the beam, from one
+    row of scan sums (include/art_b200.h ART_S_*): the variances of x + s ax, y + s ay and d + s gp."""
+    m = np.asarray(scan, dtype=np.float64)
+    o = _cabi.S_WEIGHTED - _cabi.S_X if weighted else 0
+    W = m[_cabi.S_SW] if weighted else m[_cabi.S_N]
+
+    def var(k_a, k_b, k_aa, k_bb, k_ab):
+        s1 = m[k_a + o] + s * m[k_b + o]
+        s2 = m[k_aa + o] + 2.0 * s * m[k_ab + o] + s * s * m[k_bb + o]
+        return max(s2 / W - (s1 / W) ** 2, 0.0)
+
+    vx = var(_cabi.S_X, _cabi.S_AX, _cabi.S_XX, _cabi.S_AXAX, _cabi.S_XAX)
+    vy = var(_cabi.S_Y, _cabi.S_AY, _cabi.S_YY, _cabi.S_AYAY, _cabi.S_YAY)
+    vd = var(_cabi.S_D, _cabi.S_G, _cabi.S_DD, _cabi.S_GG, _cabi.S_DG)
+    return float(np.sqrt(vx + vy)), float(np.sqrt(vd) * 1e15 / LIGHTSPEED)
+
+
+def optimal_shift_from_scan(scan, first_distance, spot_sd0, numerical_aperture, OptFor="intensity", Amplitude=None,
+                            Precision=3, IntensityWeighted=False):
+    """The search schedule of FindOptimalDistance / _FindOptimalDistanceBIS
+    (ART/ModuleProcessing.py:317-460) evaluated on the closed-form statistics: Precision+1 refinements
+    of 2*Amplitude/Step detector positions each, fitness SpotSize^2 * Duration ("intensity"),
+    Duration or SpotSize; the first minimum wins.  Returns (shift s in mm, OptSizeSpot, OptDuration,
+    Amplitude used)."""
+    if OptFor not in ("intensity", "size", "spotsize", "duration"):
+        raise NameError("I don`t recognize what you want to optimize the detector distance for. OptFor must be "
+                        "either 'intensity', 'size' or 'duration'.")
+    if Amplitude is None:  # :431-434
+        Amplitude = min(4 * np.ceil(2 * spot_sd0 / np.tan(np.arcsin(numerical_aperture))), first_distance)
+    Step = Amplitude / 10
+    s = 0.0
+    opt_spot = opt_dur = float("nan")
+    for k in range(Precision + 1):
+        amp_k, step_k = Amplitude * 0.1**k, Step * 0.1**k
+        s -= amp_k
+        n = int(2 * amp_k / step_k)
+        spots, durs, fits = [], [], []
+        for _ in range(n):
+            spot, dur = scan_statistics(scan, s, IntensityWeighted)
+            spots.append(spot)
+            durs.append(dur)
+            fits.append(spot**2 * dur if OptFor == "intensity" else (dur if OptFor == "duration" else spot))
+            s += step_k
+        ind = fits.index(min(fits))
+        opt_spot = spots[ind] if OptFor != "duration" else float("nan")
+        opt_dur = durs[ind] if OptFor in ("intensity", "duration") else float("nan")
+        s -= (n - ind) * step_k
+    return s, opt_spot, opt_dur, Amplitude
 
 
 def detector_from_row(row):

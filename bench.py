@@ -340,9 +340,11 @@ def run_b200(args, w, oes):
         n_total = n * world                     # the bundle all ranks share (weak scaling)
         sp = source_properties(w, n_total)
         n_src_total = n_total - 1 if sp["Divergence"] == 0 else n_total
-        first = rank * n
-        count = min(n, n_src_total - first)
-        src = msrc.synthetic_source(sp, device=dev, first=first, count=count, group=True if world > 1 else None)
+        # rays are dealt round-robin over the ranks (rank, rank + world, ...): every rank sees the whole
+        # aperture, so masks that block a contiguous range of spiral indices do not unbalance the ranks
+        first, count, stride = ad.shard_strided(n_src_total, rank, world)
+        src = msrc.synthetic_source(sp, device=dev, first=first, count=count, stride=stride,
+                                    group=True if world > 1 else None)
         chain = engine.DeviceChain(oes, device=dev)
         # buffers of one step, allocated once and reused (no allocator traffic inside the timed region)
         out = chain.new_output(src, want_incidence=True)

@@ -142,6 +142,19 @@ enum {
   ART_MOMENTS_LEN = 24 /* [21..23] reserved, written as 0 */
 };
 
+/* scan sums for the detector-distance optimiser, one row of ART_SCAN_LEN doubles.  Moving the
+ * detector by s along the beam (Detector.shiftByDistance(s), ART/ModuleDetector.py:175) moves a ray's
+ * in-plane point to (x + s ax, y + s ay) and its path to L + s (1 + gp), with ax, ay the in-plane
+ * components of u / (cvec.u) and gp = 1/(cvec.u) - 1, so spot and duration variances are quadratics in
+ * s whose coefficients are these sums (d = L - l0; second block: the same weighted by intensity): */
+enum {
+  ART_S_N = 0, ART_S_SW = 1,
+  ART_S_X = 2, ART_S_Y, ART_S_AX, ART_S_AY, ART_S_XX, ART_S_YY, ART_S_AXAX, ART_S_AYAY, ART_S_XAX, ART_S_YAY,
+  ART_S_D, ART_S_G, ART_S_DD, ART_S_GG, ART_S_DG,
+  ART_S_WEIGHTED = 17, /* ART_S_WEIGHTED + (k - ART_S_X) = intensity-weighted sum k */
+  ART_SCAN_LEN = 32
+};
+
 /* trace flags */
 #define ART_TRACE_IGNORE_DEFECTS 1u /* IgnoreDefects=True of RayTracingCalculation (its default) */
 #define ART_TRACE_NO_INCIDENCE 2u   /* do not compute Ray.incidence (saves an atan2 per ray)      */
@@ -226,6 +239,17 @@ int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bundle, int32
                              const ArtDetector* det, double* x_out, double* y_out, double* l_out,
                              double* moments_out, void* stream);
 
+/*
+ * Sums behind FindOptimalDistance, ART/ModuleProcessing.py:317-460: one pass over the stored bundle
+ * gives the ART_SCAN_LEN sums from which the spot size and duration standard deviations at ANY
+ * detector shift follow in closed form, so the reference's scan (4 decades x 20 detector positions,
+ * each recomputing every hit) becomes host arithmetic on 32 numbers -- over all rays instead of the
+ * 1000-ray random subsample of ARTmain.py:168.  Arguments as art_detector_moments; scan_out: device,
+ * n_variants x ART_SCAN_LEN.  Rows are additive over ranks (all-reduce SUM).
+ */
+int32_t art_detector_scan_moments(ArtChain* chain, const ArtBundleView* bundle, int32_t n_variants,
+                                  const ArtDetector* det, double* scan_out, void* stream);
+
 /* Multi-GPU: merge the moments rows that an all-gather collected from every rank
  * (rows: device, n_ranks x n_variants x ART_MOMENTS_LEN) into out (n_variants x ART_MOMENTS_LEN):
  * sums added in rank order, extents by min / max.  The statistics of the sharded bundle then follow
@@ -264,16 +288,18 @@ int32_t art_delays(const double* l, const uint8_t* alive, int64_t n, int32_t n_v
                    const double* moments, double* delays_out, void* stream);
 
 /*
- * Synthetic source bundles in closed form (device): rows [first, first + count) of the n_total-ray
- * Vogel-spiral bundle written to bundle[0 .. count).
+ * Synthetic source bundles in closed form (device): rays first, first + stride, first + 2 stride, ...
+ * (count of them) of the n_total-ray Vogel-spiral bundle written to bundle[0 .. count).  stride = 1
+ * gives a contiguous index range; stride = number of ranks deals the rays round-robin, which
+ * balances the work when an aperture blocks a contiguous range of spiral indices.
  *   kind 0  PointSource(origin, axis, Divergence, n_total)  ART/ModuleSource.py:54-81, rho = tan(Divergence)
  *   kind 1  PlaneWaveDisk(origin, axis, Radius, n_total)    ART/ModuleSource.py:135-169, rho = Radius
  *           (the reference emits rays 0 .. n_total-2 of the n_total-point spiral)
  * axis: the bundle is rotated ez -> axis with RotationPoint semantics.
  */
-int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t first, int64_t count, double rho,
-                            const double axis[3], const double origin[3], const ArtBundleView* bundle,
-                            void* stream);
+int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t first, int64_t count, int64_t stride,
+                            double rho, const double axis[3], const double origin[3],
+                            const ArtBundleView* bundle, void* stream);
 /* ApplyGaussianIntensityToRayList, ART/ModuleSource.py:219-261, in two calls so that sharded
  * bundles can all-reduce in between: art_source_extents writes {max angle(axis, u), max |P|} of
  * the bundle to extents_out (device, 2 doubles); art_source_intensity then fills bundle->intensity

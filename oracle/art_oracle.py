@@ -591,6 +591,47 @@ def result_summary(det, P, U, path):
     return standard_deviation(xy), standard_deviation(detector_delays(det, P, U, path))
 
 
+def find_optimal_distance(det, P, U, path, opt_for="intensity", amplitude=None, precision=3, weights=None):
+    """FindOptimalDistance + _FindOptimalDistanceBIS, ART/ModuleProcessing.py:317-460, by brute force as
+    the reference does it (every trial detector re-intersects every ray).  Returns
+    (detector dict moved, OptSizeSpot, OptDuration)."""
+    det = {k: np.array(v, dtype=np.float64) for k, v in det.items()}
+
+    def distance(d):
+        return abs(np.dot(d["normal"], d["centre"] - d["refpoint"]))
+
+    def stats(d):
+        xy = detector_points2d_centre(d, P, U)
+        dl = detector_delays(d, P, U, path)
+        if weights is None:
+            return standard_deviation(xy), standard_deviation(dl)
+        return weighted_standard_deviation(xy, weights), weighted_standard_deviation(dl, weights)
+
+    first = distance(det)
+    size = 2 * standard_deviation(detector_points2d_centre(det, P, U))
+    na = numerical_aperture(U)
+    if amplitude is None:
+        amplitude = min(4 * np.ceil(size / np.tan(np.arcsin(na))), first)
+    step = amplitude / 10
+    spot = dur = np.nan
+    for k in range(precision + 1):
+        a_k, s_k = amplitude * 0.1**k, step * 0.1**k
+        det["centre"] = det["centre"] - (-a_k) * det["normal"]  # shiftByDistance(-Amplitude)
+        n = int(2 * a_k / s_k)
+        spots, durs, fits = [], [], []
+        for _ in range(n):
+            sp, du = stats(det)
+            spots.append(sp)
+            durs.append(du)
+            fits.append(sp**2 * du if opt_for == "intensity" else (du if opt_for == "duration" else sp))
+            det["centre"] = det["centre"] - s_k * det["normal"]
+        ind = fits.index(min(fits))
+        spot = spots[ind] if opt_for != "duration" else np.nan
+        dur = durs[ind] if opt_for in ("intensity", "duration") else np.nan
+        det["centre"] = det["centre"] - (-(n - ind) * s_k) * det["normal"]
+    return det, spot, dur
+
+
 def numerical_aperture(U, refractive_index=1.0):
     """ReturnNumericalAperture, ART/ModuleProcessing.py:536-566."""
     cv = normalize(np.mean(U, axis=0))

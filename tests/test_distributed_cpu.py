@@ -115,6 +115,19 @@ def test_shard_ranges_tile_the_bundle():
                 assert f0 + c0 == f1
 
 
+def test_strided_shards_partition_the_bundle():
+    from attosecondraytracing_b200 import distributed as ad
+    for n in (0, 1, 7, 1001, 10**7 + 1):
+        for world in (1, 2, 3, 8):
+            seen = 0
+            for r in range(world):
+                first, count, stride = ad.shard_strided(n, r, world)
+                assert stride == world and first == r
+                assert count == len(range(r, n, world))
+                seen += count
+            assert seen == n
+
+
 def test_merge_moments_matches_all_reduce_semantics():
     from attosecondraytracing_b200 import distributed as ad
     rng = np.random.default_rng(5)

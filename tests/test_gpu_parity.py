@@ -216,6 +216,11 @@ def test_device_sources_match_oracle():
         part = msrc.synthetic_source(sp, device="cuda", first=1000, count=512)
         pd = part.to_numpy()
         assert np.array_equal(pd["P"], d["P"][1000:1512]) and np.array_equal(pd["U"], d["U"][1000:1512])
+        # a round-robin share (rank 3 of 8) holds rays 3, 11, 19, ...
+        share = msrc.synthetic_source(sp, device="cuda", first=3, stride=8)
+        sd = share.to_numpy()
+        assert np.array_equal(sd["number"], num[3::8])
+        assert np.array_equal(sd["P"], d["P"][3::8]) and np.array_equal(sd["U"], d["U"][3::8])
 
 
 @pytest.mark.parametrize("name", ["cfg3_2tor", "cfg1_par", "sph_zern2_def", "mask_rrh_plane"])
@@ -314,3 +319,40 @@ def test_sweep_statistics_matches_individual_chains():
         assert st["n_rays"] == len(final)
     assert abs(stats[3]["SpotSizeSD"] - g["SpotSizeSD"]) <= 3e-8  # 5 m telescope noise floor
     assert abs(stats[3]["DurationSD"] - g["DurationSD"]) <= DELAY_TOL_FS
+
+
+def _optdist():
+    import os
+    from golden_util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "optdist.npz"))
+    return z, sorted(k for k in z.files if k != "meta" and not k.endswith("__centre"))
+
+
+@pytest.mark.parametrize("key", _optdist()[1])
+def test_find_optimal_distance_on_device(key):
+    """ModuleProcessing.FindOptimalDistance (scan-sum kernel + closed-form search over ALL rays) lands where
+    the reference's brute-force optimiser did (fixtures from oracle/gen_golden_optdist.py)."""
+    import attosecondraytracing_b200.ModuleProcessing as mp
+    import attosecondraytracing_b200.ModuleDetector as mdet
+    z, _ = _optdist()
+    name, opt_for, wflag = key.split("__")
+    ref_dist, ref_spot, ref_dur = z[key]
+    g = Golden(name)
+    eng = _engine()
+    chain = eng.DeviceChain(golden_optical_elements(g))
+    src = _source_bundle(g)
+    outs, _ = chain.trace(src, ignore_defects=True, history=False)
+    final = outs[0]
+    det = mdet.Detector(g["det_refpoint"].copy(), g["det_centre"].copy(), g["det_normal"].copy())
+    first = det.get_distance()
+    moved, spot, dur = mp.FindOptimalDistance(det, final, OptFor=opt_for, IntensityWeighted=(wflag == "w"))
+    assert abs(moved.get_distance() - ref_dist) <= 2.5e-4 * first
+    if opt_for != "duration":
+        assert abs(spot - ref_spot) <= 1e-6 * max(ref_spot, 1e-9) + 1e-9
+    else:
+        assert np.isnan(spot)
+    assert abs(dur - ref_dur) <= 1e-5 * max(ref_dur, 1.0)
+    assert det.get_distance() == first  # the input detector is not moved
+    with pytest.raises(NameError):
+        mp.FindOptimalDistance(det, final, OptFor="brightness")
+    chain.close()

@@ -86,3 +86,70 @@ def test_subset_sources_are_the_full_bundle_rows():
     k = np.array([0, 17, 4998])
     Pk, Uk, numk, ik = orc.source_for(sp, k=k)
     assert np.array_equal(Pk, P[k]) and np.max(np.abs(ik - inten[k])) <= 1e-15
+
+
+# ----------------------------------------------------------------------------------------------
+# detector-distance optimiser
+# ----------------------------------------------------------------------------------------------
+def _optdist_cases():
+    import os
+    from golden_util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "optdist.npz"))
+    return z, sorted(k for k in z.files if k != "meta" and not k.endswith("__centre"))
+
+
+def numpy_scan_sums(det, l0, P, U, path, w):
+    """The ART_S_* scan sums (include/art_b200.h) by oracle arithmetic -- what scan_kernel accumulates."""
+    xy = orc.detector_points2d(det, P, U)
+    L = orc.detector_optical_paths(det, P, U, path)
+    d = L - l0
+    cv = -np.asarray(det["normal"])
+    cu = U @ cv
+    g = 1.0 / cu
+    gp = 0.5 * np.sum((U - cv) ** 2, axis=1) * g
+    M = orc.rotation_matrix(det["normal"], orc.EZ)
+    ru = U @ M.T
+    ax, ay = g * ru[:, 0], g * ru[:, 1]
+    x, y = xy[:, 0], xy[:, 1]
+    t = [x, y, ax, ay, x * x, y * y, ax * ax, ay * ay, x * ax, y * ay, d, gp, d * d, gp * gp, d * gp]
+    row = np.zeros(32)
+    row[0], row[1] = P.shape[0], w.sum()
+    for j, v in enumerate(t):
+        row[2 + j] = v.sum()
+        row[17 + j] = (w * v).sum()
+    return row
+
+
+@pytest.mark.parametrize("key", _optdist_cases()[1])
+def test_find_optimal_distance_matches_reference(key):
+    """Both the oracle's brute-force restatement and the product's closed-form search
+    (engine.optimal_shift_from_scan on the 32 scan sums) land where the reference's FindOptimalDistance did."""
+    from attosecondraytracing_b200.engine import optimal_shift_from_scan
+    z, _ = _optdist_cases()
+    name, opt_for, wflag = key.split("__")
+    ref_dist, ref_spot, ref_dur = z[key]
+    g = Golden(name)
+    last = g.out(g.n_elements - 1)
+    P, U, path = last["P"], last["U"], last["path"]
+    det = {"centre": g["det_centre"], "normal": g["det_normal"], "refpoint": g["det_refpoint"]}
+    w = g["src_I"][np.searchsorted(g["src_num"], last["num"])]
+    weights = w if wflag == "w" else None
+    # finest step of the search = Amplitude * 1e-4; neighbouring positions can tie within rounding
+    first = float(abs(np.dot(det["normal"], det["centre"] - det["refpoint"])))
+    d2, spot, dur = orc.find_optimal_distance(det, P, U, path, opt_for, None, 3, weights)
+    dist = abs(np.dot(d2["normal"], d2["centre"] - d2["refpoint"]))
+    tol_d = 2.5e-4 * first
+    assert abs(dist - ref_dist) <= tol_d, (dist, ref_dist)
+    if opt_for != "duration":
+        assert abs(spot - ref_spot) <= 1e-6 * max(ref_spot, 1e-9) + 1e-9
+    assert abs(dur - ref_dur) <= 1e-5 * max(ref_dur, 1.0)
+    # closed form on the scan sums
+    l0 = path.mean() + first
+    scan = numpy_scan_sums(det, l0, P, U, path, w)
+    sd0 = orc.standard_deviation(orc.detector_points2d_centre(det, P, U))
+    s, spot2, dur2, amp = optimal_shift_from_scan(scan, first, sd0, orc.numerical_aperture(U), opt_for, None, 3,
+                                                  wflag == "w")
+    assert abs((first + s) - ref_dist) <= tol_d, (first + s, ref_dist)
+    if opt_for != "duration":
+        assert abs(spot2 - ref_spot) <= 1e-6 * max(ref_spot, 1e-9) + 1e-9
+    assert abs(dur2 - ref_dur) <= 1e-5 * max(ref_dur, 1.0)
