@@ -91,8 +91,6 @@ class OpticalChain:
         key = self._key(kwargs)
         if key != self._last_key or self._output_rays is None:
             self._output_rays = mp.RayTracingCalculation(self.source_rays, self.optical_elements, **kwargs)
-            if self.source_rays.device.type != "cuda":
-                pass
             self._last_key = key
         return self._output_rays
 
