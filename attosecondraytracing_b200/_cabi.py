@@ -49,6 +49,14 @@ class ArtElementDesc(C.Structure):
         ("centre", C.c_double * 3), ("position", C.c_double * 3),
         ("normal", C.c_double * 3), ("majoraxis", C.c_double * 3),
         ("n_defects", C.c_int32), ("first_defect", C.c_int32),
+        ("n_gridmaps", C.c_int32), ("first_gridmap", C.c_int32),
+    ]
+
+
+class ArtGridMapDesc(C.Structure):
+    _fields_ = [
+        ("nx", C.c_int32), ("ny", C.c_int32), ("x0", C.c_double), ("x1", C.c_double), ("y0", C.c_double),
+        ("y1", C.c_double), ("h", C.c_void_p), ("dx", C.c_void_p), ("dy", C.c_void_p),
     ]
 
 
@@ -94,7 +102,7 @@ _SIGNATURES = {
     "art_device_count": (C.c_int32, [C.POINTER(C.c_int32)]),
     "art_element_rotation": (C.c_int32, [c_double_p, c_double_p, c_double_p]),
     "art_chain_create": (C.c_int32, [C.POINTER(ArtElementDesc), C.c_int32, C.c_int32, C.POINTER(ArtZernikeDesc),
-                                     C.c_int32, C.POINTER(C.c_void_p)]),
+                                     C.c_int32, C.POINTER(ArtGridMapDesc), C.c_int32, C.POINTER(C.c_void_p)]),
     "art_chain_destroy": (C.c_int32, [C.c_void_p]),
     "art_trace": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(ArtBundleView), C.POINTER(ArtBundleView),
                               C.POINTER(ArtBundleView), C.c_uint32, C.c_void_p, C.c_void_p]),
@@ -144,9 +152,9 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        sizes = (C.c_int32 * 4)()
+        sizes = (C.c_int32 * 5)()
         L.art_abi_sizes(sizes)
-        mine = [C.sizeof(t) for t in (ArtElementDesc, ArtZernikeDesc, ArtBundleView, ArtDetector)]
+        mine = [C.sizeof(t) for t in (ArtElementDesc, ArtZernikeDesc, ArtBundleView, ArtDetector, ArtGridMapDesc)]
         if list(sizes) != mine:
             raise RuntimeError(f"struct layout mismatch between _cabi.py {mine} and libart_b200.so {list(sizes)}")
         _lib = L

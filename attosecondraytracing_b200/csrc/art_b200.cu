@@ -56,6 +56,7 @@ struct ArtChain {
   ElemDev* d_elems = nullptr;
   double* d_ztab = nullptr;
   int* d_zoff = nullptr;
+  MapDev* d_maps = nullptr;
   int ztab_len = 0;
   size_t smem_bytes = 0;
   bool has_defects = false;
@@ -111,12 +112,13 @@ extern "C" int32_t art_version(void) { return ART_B200_VERSION; }
 extern "C" const char* art_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t art_launch_count(void) { return g_launches.load(); }
 
-extern "C" int32_t art_abi_sizes(int32_t sizes_out[4]) {
+extern "C" int32_t art_abi_sizes(int32_t sizes_out[5]) {
   if (!sizes_out) return fail(ART_E_INVALID, "sizes_out is NULL");
   sizes_out[0] = (int32_t)sizeof(ArtElementDesc);
   sizes_out[1] = (int32_t)sizeof(ArtZernikeDesc);
   sizes_out[2] = (int32_t)sizeof(ArtBundleView);
   sizes_out[3] = (int32_t)sizeof(ArtDetector);
+  sizes_out[4] = (int32_t)sizeof(ArtGridMapDesc);
   return ART_OK;
 }
 
@@ -159,6 +161,7 @@ extern "C" int32_t art_chain_destroy(ArtChain* c) {
   cudaFree(c->d_elems);
   cudaFree(c->d_ztab);
   cudaFree(c->d_zoff);
+  cudaFree(c->d_maps);
   cudaFree(c->d_partials);
   cudaFree(c->d_central);
   cudaFree(c->d_moments);
@@ -181,13 +184,15 @@ static cudaError_t allow_smem(K kernel, size_t bytes) {
 }
 
 extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_elements, int32_t n_variants,
-                                    const ArtZernikeDesc* defects, int32_t n_defects, ArtChain** chain_out) {
+                                    const ArtZernikeDesc* defects, int32_t n_defects, const ArtGridMapDesc* gridmaps,
+                                    int32_t n_gridmaps, ArtChain** chain_out) {
   if (!chain_out) return fail(ART_E_INVALID, "chain_out is NULL");
   *chain_out = nullptr;
   if (!elements || n_elements < 1 || n_elements > ART_MAX_ELEMENTS)
     return fail(ART_E_INVALID, "n_elements must be in [1, " + std::to_string(ART_MAX_ELEMENTS) + "]");
   if (n_variants < 1) return fail(ART_E_INVALID, "n_variants must be >= 1");
   if (n_defects < 0 || (n_defects > 0 && !defects)) return fail(ART_E_INVALID, "bad defect list");
+  if (n_gridmaps < 0 || (n_gridmaps > 0 && !gridmaps)) return fail(ART_E_INVALID, "bad grid-map list");
 
   std::vector<ElemDev> h((size_t)n_elements * n_variants);
   bool any_def = false;
@@ -202,10 +207,15 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
         if (d.first_defect + d.n_defects > n_defects)
           return fail(ART_E_INVALID, "element " + std::to_string(k) + " refers to defects beyond the list");
       }
+      if (d.n_gridmaps > 0) {
+        any_def = true;
+        if (d.first_gridmap + d.n_gridmaps > n_gridmaps)
+          return fail(ART_E_INVALID, "element " + std::to_string(k) + " refers to grid maps beyond the list");
+      }
       if (v > 0) {
         const ArtElementDesc& d0 = elements[k];
         if (d0.surface != d.surface || d0.support != d.support || d0.n_defects != d.n_defects ||
-            d0.first_defect != d.first_defect)
+            d0.first_defect != d.first_defect || d0.n_gridmaps != d.n_gridmaps || d0.first_gridmap != d.first_gridmap)
           return fail(ART_E_INVALID, "variants must share surface / support kinds and defects");
       }
     }
@@ -217,6 +227,12 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
     if (!why.empty()) return fail(ART_E_INVALID, "defect " + std::to_string(i) + ": " + why);
     zoff.push_back((int)ztab.size());
     ztab.insert(ztab.end(), t.begin(), t.end());
+  }
+
+  std::vector<MapDev> hmaps((size_t)n_gridmaps);
+  for (int i = 0; i < n_gridmaps; ++i) {
+    std::string why = lower_gridmap(gridmaps[i], hmaps[i]);
+    if (!why.empty()) return fail(ART_E_INVALID, "grid map " + std::to_string(i) + ": " + why);
   }
 
   ArtChain* c = new (std::nothrow) ArtChain();
@@ -281,6 +297,10 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
     CK(cudaMalloc(&c->d_zoff, zoff.size() * sizeof(int)));
     CK(cudaMemcpy(c->d_zoff, zoff.data(), zoff.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
+  if (!hmaps.empty()) {
+    CK(cudaMalloc(&c->d_maps, hmaps.size() * sizeof(MapDev)));
+    CK(cudaMemcpy(c->d_maps, hmaps.data(), hmaps.size() * sizeof(MapDev), cudaMemcpyHostToDevice));
+  }
   c->partial_rows = (size_t)c->sm_count * 8 + (size_t)n_variants + 8;
   CK(cudaMalloc(&c->d_partials, c->partial_rows * PLEN_FUSED * sizeof(double)));
   CK(cudaMalloc(&c->d_central, (size_t)n_variants * ART_CENTRAL_LEN * sizeof(double)));
@@ -323,6 +343,7 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
   a.zoff = c->d_zoff;
   a.ztab_len = c->ztab_len;
   a.n_defects = c->n_defects;
+  a.maps = c->d_maps;
   a.in = to_dev(in);
   a.out = to_dev(out_final);
   a.has_out = out_final != nullptr;

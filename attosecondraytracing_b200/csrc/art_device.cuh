@@ -34,6 +34,15 @@ struct __align__(16) ElemDev {
   int32_t support;
   int32_t n_defects;
   int32_t first_defect;
+  int32_t n_maps;      // gridded defects
+  int32_t first_map;
+};
+
+// one gridded defect (ArtGridMapDesc, pre-digested): cell index = (x - x0) * sx
+struct MapDev {
+  const double *h, *dx, *dy;
+  double x0, sx, y0, sy;
+  int32_t nx, ny;
 };
 
 struct BundleDev {

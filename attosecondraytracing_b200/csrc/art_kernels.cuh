@@ -36,6 +36,7 @@ struct TraceArgs {
   const int* zoff;       // offset (in doubles) of each defect's table
   int ztab_len;          // doubles
   int n_defects;
+  const MapDev* maps;    // gridded defects (global memory)
   BundleDev in;
   BundleDev out;         // final bundle (rows v*n + i), pointers may be null
   BundleDev hist[ART_MAX_ELEMENTS];
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
       RayT<D2> pr = pack_rays(r[0], r[N - 1]);
       for (int k = 0; k < a.n_elements; ++k) {
         const bool inc_here = WANT_INC && (k == last || a.has_hist);
-        if (any(pr.alive)) apply_element<WANT_INC, HAS_DEF, SURFS, D2>(sE[k], pr, sZ, sZoff, ignore_defects, inc_here);
+        if (any(pr.alive)) apply_element<WANT_INC, HAS_DEF, SURFS, D2>(sE[k], pr, sZ, sZoff, ignore_defects, inc_here, a.maps);
         if (a.has_hist) {
           unpack_rays(pr, r[0], r[N - 1]);
           store_bundle<N>(a.hist[k], row + i, out_vec, two, r, WANT_INC);
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
 #pragma unroll
         for (int q = 0; q < N; ++q)
           if (r[q].alive)
-            apply_element<WANT_INC, HAS_DEF, SURFS, double>(sE[k], r[q], sZ, sZoff, ignore_defects, inc_here);
+            apply_element<WANT_INC, HAS_DEF, SURFS, double>(sE[k], r[q], sZ, sZoff, ignore_defects, inc_here, a.maps);
         if (a.has_hist) store_bundle<N>(a.hist[k], row + i, out_vec, two, r, WANT_INC);
       }
     }

@@ -103,8 +103,22 @@ inline std::string lower_element(const ArtElementDesc& d, ElemDev& e) {
     default:
       return "unknown support kind";
   }
-  if (d.n_defects < 0 || d.first_defect < 0) return "negative defect index";
-  if (d.n_defects > 0 && (d.surface == ART_SURF_MASK)) return "a mask cannot carry defects";
+  if (d.n_defects < 0 || d.first_defect < 0 || d.n_gridmaps < 0 || d.first_gridmap < 0) return "negative defect index";
+  if ((d.n_defects > 0 || d.n_gridmaps > 0) && (d.surface == ART_SURF_MASK)) return "a mask cannot carry defects";
+  e.n_maps = d.n_gridmaps;
+  e.first_map = d.first_gridmap;
+  return std::string();
+}
+
+inline std::string lower_gridmap(const ArtGridMapDesc& g, MapDev& m) {
+  if (g.nx < 2 || g.ny < 2) return "a grid map needs at least 2 x 2 points";
+  if (!(g.x1 > g.x0) || !(g.y1 > g.y0)) return "grid extents must be increasing";
+  if (!g.h || !g.dx || !g.dy) return "grid map arrays are NULL";
+  m.h = g.h; m.dx = g.dx; m.dy = g.dy;
+  m.x0 = g.x0; m.y0 = g.y0;
+  m.sx = (g.nx - 1) / (g.x1 - g.x0);
+  m.sy = (g.ny - 1) / (g.y1 - g.y0);
+  m.nx = g.nx; m.ny = g.ny;
   return std::string();
 }
 

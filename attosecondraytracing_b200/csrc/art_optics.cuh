@@ -346,6 +346,34 @@ ART_HD void zernike_eval(const double* __restrict__ zt, T X, T Y, T& val, T& gx,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Gridded defect (MeasuredMap / Fourrier, ART/ModuleDefects.py:34-146): bilinear interpolation of the
+// height map (WHICH = 0) or of the two slope maps (WHICH = 1) at (X, Y) relative to the optic centre,
+// as scipy's RegularGridInterpolator(method="linear") does on the reference's grids.
+// ---------------------------------------------------------------------------------------------
+template <int WHICH>
+ART_HD void gridmap_eval(const MapDev& M, double X, double Y, double& a, double& b) {
+  const double fx = (X - M.x0) * M.sx, fy = (Y - M.y0) * M.sy;
+  int ix = (int)floor(fx), iy = (int)floor(fy);
+  ix = ix < 0 ? 0 : (ix > M.nx - 2 ? M.nx - 2 : ix);
+  iy = iy < 0 ? 0 : (iy > M.ny - 2 ? M.ny - 2 : iy);
+  const double tx = fx - ix, ty = fy - iy;
+  const double w00 = (1.0 - tx) * (1.0 - ty), w10 = tx * (1.0 - ty), w01 = (1.0 - tx) * ty, w11 = tx * ty;
+  const long long o = (long long)ix * M.ny + iy;
+  if (WHICH == 0) {
+    a = w00 * M.h[o] + w10 * M.h[o + M.ny] + w01 * M.h[o + 1] + w11 * M.h[o + M.ny + 1];
+    b = 0.0;
+  } else {
+    a = w00 * M.dx[o] + w10 * M.dx[o + M.ny] + w01 * M.dx[o + 1] + w11 * M.dx[o + M.ny + 1];
+    b = w00 * M.dy[o] + w10 * M.dy[o + M.ny] + w01 * M.dy[o + 1] + w11 * M.dy[o + M.ny + 1];
+  }
+}
+template <int WHICH>
+ART_HD void gridmap_eval(const MapDev& M, D2 X, D2 Y, D2& a, D2& b) {
+  gridmap_eval<WHICH>(M, X.a, Y.a, a.a, b.a);
+  gridmap_eval<WHICH>(M, X.b, Y.b, a.b, b.b);
+}
+
+// ---------------------------------------------------------------------------------------------
 // surface normal, `get_normal` of each mirror class (unit vector)
 // ---------------------------------------------------------------------------------------------
 template <class T>
@@ -419,7 +447,8 @@ enum { SURFS_ANY = 0, SURFS_TOROID = 1, SURFS_QUADRIC = 2 };
 // ---------------------------------------------------------------------------------------------
 template <bool WANT_INC, bool HAS_DEF, int SURFS, class T>
 ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict__ ztab,
-                          const int* __restrict__ zoff, bool ignore_defects, bool inc_here) {
+                          const int* __restrict__ zoff, bool ignore_defects, bool inc_here,
+                          const MapDev* __restrict__ maps = nullptr) {
   typedef typename MaskOf<T>::type M;
   const M act = r.alive;
   // lab -> element frame (:289-295): p_e = R (p - pos) + centre, u_e = R u
@@ -489,13 +518,18 @@ ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict
   } else {
     T nx, ny, nz;
     surface_normal(E, hx, hy, hz, nx, ny, nz);
-    if (HAS_DEF && E.n_defects > 0) {
+    if (HAS_DEF && (E.n_defects > 0 || E.n_maps > 0)) {
       // DeformedMirror._get_intersection, ART/ModuleMirror.py:969-980:
       //   h = sum offsets(P - C); alpha = angle(-u, n_base(P)); P -= u h / cos(alpha)
       T h = splat<T>(0.0);
       for (int d = 0; d < E.n_defects; ++d) {
         T v, g0, g1;
         zernike_eval<true, false>(ztab + zoff[E.first_defect + d], hx - E.ctr[0], hy - E.ctr[1], v, g0, g1);
+        h = h + v;
+      }
+      for (int d = 0; d < E.n_maps; ++d) {
+        T v, unused;
+        gridmap_eval<0>(maps[E.first_map + d], hx - E.ctr[0], hy - E.ctr[1], v, unused);
         h = h + v;
       }
       const T cosa = -mfma(nx, e.ux, mfma(ny, e.uy, nz * e.uz));
@@ -513,6 +547,14 @@ ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict
           zernike_eval<false, true>(ztab + zoff[E.first_defect + d], hx - E.ctr[0], hy - E.ctr[1], v, g0, g1);
           sx = sx + g0;
           sy = sy + g1;
+        }
+        for (int d = 0; d < E.n_maps; ++d) {
+          // MeasuredMap / Fourrier.get_normal returns (+dX, +dY, 1)/norm (ART/ModuleDefects.py:52-58,119-129),
+          // so normal_add's slope -n_x/n_z is MINUS the interpolated derivative
+          T g0, g1;
+          gridmap_eval<1>(maps[E.first_map + d], hx - E.ctr[0], hy - E.ctr[1], g0, g1);
+          sx = sx - g0;
+          sy = sy - g1;
         }
         const T inv = frsqrt(mfma(sx, sx, mfma(sy, sy, 1.0)));
         nx = -(sx * inv); ny = -(sy * inv); nz = inv;

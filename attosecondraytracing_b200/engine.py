@@ -50,13 +50,14 @@ class DeviceChain:
         if variants and not isinstance(variants[0], (list, tuple)):
             variants = [variants]
         self.device = require_cuda(device)
-        self.lowered = LoweredChain(variants)
+        self.lowered = LoweredChain(variants, map_device=self.device)
         self.n_elements = self.lowered.n_elements
         self.n_variants = self.lowered.n_variants
         self._handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().art_chain_create(self.lowered.elements, self.n_elements, self.n_variants,
                                                      self.lowered.defects, self.lowered.n_defects,
+                                                     self.lowered.gridmaps, self.lowered.n_gridmaps,
                                                      C.byref(self._handle)))
 
     def close(self):

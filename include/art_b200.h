@@ -71,8 +71,10 @@ typedef struct ArtElementDesc {
   double position[3];        /* OpticalElement.position, lab frame                      */
   double normal[3];          /* OpticalElement.normal                                   */
   double majoraxis[3];       /* OpticalElement.majoraxis                                */
-  int32_t n_defects;         /* DeformedMirror.DeformationList length (Zernike only)    */
-  int32_t first_defect;      /* index of this element's first defect in the defect list */
+  int32_t n_defects;         /* Zernike defects in DeformedMirror.DeformationList       */
+  int32_t first_defect;      /* index of this element's first Zernike defect in the list */
+  int32_t n_gridmaps;        /* gridded defects (MeasuredMap / Fourrier) of this element */
+  int32_t first_gridmap;     /* index of the first one in the grid-map list              */
 } ArtElementDesc;
 
 /*
@@ -88,6 +90,23 @@ typedef struct ArtZernikeDesc {
   const int32_t* m;
   const double* c;
 } ArtZernikeDesc;
+
+/*
+ * One gridded defect = ART/ModuleDefects.py:34 MeasuredMap or :69 Fourrier: a height map and its two
+ * slope maps on the regular grid X = linspace(x0, x1, nx), Y = linspace(y0, y1, ny), evaluated by
+ * bilinear interpolation exactly like the scipy RegularGridInterpolator(method="linear") objects the
+ * reference builds (:45-47, :108-110; points outside the grid are clamped to its edge cell).
+ * h, dx, dy: DEVICE pointers owned by the caller, nx*ny doubles each, value at (ix, iy) in [ix*ny + iy]
+ * (the arrays the reference hands to the interpolators: np.transpose(deformation) etc.).
+ * get_normal of these classes is (dX, dY, 1)/norm -- not negated, unlike Zernike's.
+ */
+typedef struct ArtGridMapDesc {
+  int32_t nx, ny;
+  double x0, x1, y0, y1;
+  const double* h;
+  const double* dx;
+  const double* dy;
+} ArtGridMapDesc;
 
 /*
  * Structure-of-arrays FP64 ray bundle: the `list[Ray]` of ART/ModuleOpticalRay.py:11.
@@ -167,9 +186,10 @@ typedef struct ArtChain ArtChain;
 int32_t art_version(void);
 const char* art_last_error(void);
 
-/* sizeof(ArtElementDesc), sizeof(ArtZernikeDesc), sizeof(ArtBundleView), sizeof(ArtDetector) as this
- * library was compiled -- lets a binding in another language verify its struct layouts. */
-int32_t art_abi_sizes(int32_t sizes_out[4]);
+/* sizeof(ArtElementDesc), sizeof(ArtZernikeDesc), sizeof(ArtBundleView), sizeof(ArtDetector),
+ * sizeof(ArtGridMapDesc) as this library was compiled -- lets a binding in another language verify its
+ * struct layouts. */
+int32_t art_abi_sizes(int32_t sizes_out[5]);
 
 /* CUDA device count (plumbing for the host; no reference counterpart). */
 int32_t art_device_count(int32_t* count);
@@ -189,7 +209,8 @@ int32_t art_element_rotation(const double normal[3], const double majoraxis[3], 
  * Replaces the `optical_elements` argument of RayTracingCalculation, ART/ModuleProcessing.py:250.
  */
 int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_elements, int32_t n_variants,
-                         const ArtZernikeDesc* defects, int32_t n_defects, ArtChain** chain_out);
+                         const ArtZernikeDesc* defects, int32_t n_defects, const ArtGridMapDesc* gridmaps,
+                         int32_t n_gridmaps, ArtChain** chain_out);
 int32_t art_chain_destroy(ArtChain* chain);
 
 /*

@@ -23,7 +23,7 @@ class ArtElementDesc(C.Structure):
     _fields_ = [("surface", C.c_int32), ("support", C.c_int32), ("surface_params", C.c_double * 4),
                 ("support_params", C.c_double * 6), ("centre", C.c_double * 3), ("position", C.c_double * 3),
                 ("normal", C.c_double * 3), ("majoraxis", C.c_double * 3), ("n_defects", C.c_int32),
-                ("first_defect", C.c_int32)]
+                ("first_defect", C.c_int32), ("n_gridmaps", C.c_int32), ("first_gridmap", C.c_int32)]
 
 
 class ArtZernikeDesc(C.Structure):
@@ -46,11 +46,11 @@ def load(path):
     L = C.CDLL(path)
     L.art_last_error.restype = C.c_char_p
     L.art_chain_create.argtypes = [C.POINTER(ArtElementDesc), C.c_int32, C.c_int32, C.POINTER(ArtZernikeDesc), C.c_int32,
-                                   C.POINTER(C.c_void_p)]
+                                   C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
     L.art_chain_destroy.argtypes = [C.c_void_p]
     L.art_trace_host.argtypes = [C.c_void_p, C.POINTER(ArtBundleView), C.POINTER(ArtBundleView),
                                  C.POINTER(ArtBundleView), C.c_uint32]
-    sizes = (C.c_int32 * 4)()
+    sizes = (C.c_int32 * 5)()
     L.art_abi_sizes(sizes)
     assert list(sizes)[:3] == [C.sizeof(ArtElementDesc), C.sizeof(ArtZernikeDesc), C.sizeof(ArtBundleView)], "ABI mismatch"
     _lib = L
@@ -143,7 +143,8 @@ def trace_columns(P, U, optical_elements, IgnoreDefects=True, path=None):
     n = P.shape[0]
     els, zd, nz, keep = lower(optical_elements)
     chain = C.c_void_p()
-    _check(_lib.art_chain_create(els, len(optical_elements), 1, zd, nz, C.byref(chain)))
+    # gridded defects (MeasuredMap / Fourrier) need their maps in device memory: not bound here
+    _check(_lib.art_chain_create(els, len(optical_elements), 1, zd, nz, None, 0, C.byref(chain)))
     try:
         names = ("px", "py", "pz", "ux", "uy", "uz")
         U = U / np.linalg.norm(U, axis=1)[:, None]  # the Ray.vector setter normalises

@@ -418,6 +418,45 @@ def zernike_normal(defect, Q):
     return np.stack([-dX, -dY, np.ones_like(dX)], axis=-1)
 
 
+# --------------------------------------------------------------------------------------
+# gridded defects (ART/ModuleDefects.py:34-146: MeasuredMap, Fourrier)
+# --------------------------------------------------------------------------------------
+def _bilinear(V, x0, x1, y0, y1, x, y):
+    """scipy.interpolate.RegularGridInterpolator((X, Y), V, method="linear") on the uniform grid
+    X = linspace(x0, x1, V.shape[0]), Y = linspace(y0, y1, V.shape[1]) (ART/ModuleDefects.py:108-110)."""
+    nx, ny = V.shape
+    fx = (np.asarray(x) - x0) / (x1 - x0) * (nx - 1)
+    fy = (np.asarray(y) - y0) / (y1 - y0) * (ny - 1)
+    ix = np.clip(np.floor(fx).astype(int), 0, nx - 2)
+    iy = np.clip(np.floor(fy).astype(int), 0, ny - 2)
+    tx, ty = fx - ix, fy - iy
+    return ((1 - tx) * (1 - ty) * V[ix, iy] + tx * (1 - ty) * V[ix + 1, iy]
+            + (1 - tx) * ty * V[ix, iy + 1] + tx * ty * V[ix + 1, iy + 1])
+
+
+def gridmap_offset(defect, Q):
+    """get_offset of MeasuredMap / Fourrier, ART/ModuleDefects.py:60-61,131-137."""
+    return _bilinear(defect["h"], defect["x0"], defect["x1"], defect["y0"], defect["y1"], Q[:, 0], Q[:, 1])
+
+
+def gridmap_normal(defect, Q):
+    """get_normal of MeasuredMap / Fourrier, ART/ModuleDefects.py:52-58,119-129: (dX, dY, 1)/norm --
+    NOT negated, unlike Zernike.get_normal."""
+    dX = _bilinear(defect["dx"], defect["x0"], defect["x1"], defect["y0"], defect["y1"], Q[:, 0], Q[:, 1])
+    dY = _bilinear(defect["dy"], defect["x0"], defect["x1"], defect["y0"], defect["y1"], Q[:, 0], Q[:, 1])
+    nrm = np.sqrt(dX**2 + dY**2 + 1)
+    dX, dY = dX / nrm, dY / nrm
+    return np.stack([dX, dY, np.sqrt(1 - dX**2 - dY**2)], axis=-1)
+
+
+def defect_offset(D, Q):
+    return gridmap_offset(D, Q) if D["kind"] == "gridmap" else zernike_offset(D, Q)
+
+
+def defect_normal(D, Q):
+    return gridmap_normal(D, Q) if D["kind"] == "gridmap" else zernike_normal(D, Q)
+
+
 def normal_add(N1, N2):
     """ART/ModuleGeometry.py:394-407."""
     n1 = normalize(N1)
@@ -473,7 +512,7 @@ def trace_chain(P, U, elements, ignore_defects=True, numbers=None):
                 # DeformedMirror._get_intersection, ART/ModuleMirror.py:969-980
                 h = np.zeros(Ph.shape[0])
                 for D in defects:
-                    h = h + zernike_offset(D, Ph - C)
+                    h = h + defect_offset(D, Ph - C)
                 alpha = angle_between(-u1, optic_normal(optic, Ph))
                 Ph = Ph - u1 * (h / np.cos(alpha))[:, None]
             # ReflectionMirrorRayList / _ReflectionMirrorRay, ART/ModuleMirror.py:878-939
@@ -481,7 +520,7 @@ def trace_chain(P, U, elements, ignore_defects=True, numbers=None):
             if defects and not ignore_defects:
                 # DeformedMirror.get_normal, ART/ModuleMirror.py:952-961
                 for D in defects:
-                    nrm = normal_add(nrm, zernike_normal(D, Ph - C))
+                    nrm = normal_add(nrm, defect_normal(D, Ph - C))
                     nrm = nrm / norm(nrm)[:, None]
             # SymmetricalVector(-u, n): rotation of -u by pi about n == u - 2 (n.u) n
             u2 = normalize(u1 - 2.0 * np.sum(nrm * u1, axis=1)[:, None] * nrm)

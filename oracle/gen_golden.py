@@ -31,6 +31,7 @@ import art_oracle as orc  # noqa: E402
 
 GOLDEN_DIR = os.path.join(os.path.dirname(HERE), "tests", "golden")
 REF = None
+EXTRA_ARRAYS = {}  # arrays of gridded defects collected by derived_optic for the fixture being written
 
 
 def ref():
@@ -76,9 +77,16 @@ def build_optic(spec):
     if spec.get("defects"):
         dl = []
         for d in spec["defects"]:
-            assert d["kind"] == "zernike"
-            coeffs = {(int(n), int(mm_)): c for n, mm_, c in d["coefficients"]}
-            dl.append(R.mdef.Zernike(sup, coeffs))
+            if d["kind"] == "zernike":
+                coeffs = {(int(n), int(mm_)): c for n, mm_, c in d["coefficients"]}
+                dl.append(R.mdef.Zernike(sup, coeffs))
+            elif d["kind"] == "measuredmap":
+                dl.append(R.mdef.MeasuredMap(sup, sc.measured_map(d["nx"], d["ny"], d["amplitude"])))
+            elif d["kind"] == "fourier":
+                np.random.seed(d["seed"])  # the reference draws its phases from the global numpy RNG
+                dl.append(R.mdef.Fourrier(sup, d["rms"], slope=d["slope"], smallest=d["smallest"]))
+            else:
+                raise ValueError(d["kind"])
         m = mm.DeformedMirror(m, dl)
     return m
 
@@ -98,9 +106,27 @@ def derived_optic(spec, obj):
         d.update(a=float(base.a), b=float(base.b), offaxisangle=float(base._offaxisangle))
     if spec.get("defects"):
         d["defects"] = []
-        for ds, dobj in zip(spec["defects"], obj.DeformationList):
-            d["defects"].append({"kind": "zernike", "R": float(dobj.R), "max_order": int(dobj.max_order),
-                                 "coefficients": ds["coefficients"]})
+        for i, (ds, dobj) in enumerate(zip(spec["defects"], obj.DeformationList)):
+            if ds["kind"] == "zernike":
+                d["defects"].append({"kind": "zernike", "R": float(dobj.R), "max_order": int(dobj.max_order),
+                                     "coefficients": ds["coefficients"]})
+            else:
+                # gridded defect: the arrays the reference built go into the fixture (EXTRA_ARRAYS); the
+                # interpolation grid is what its RegularGridInterpolators were given
+                rect = dobj.Support._CircumRect() if hasattr(dobj, "Support") else base.support._CircumRect()
+                h = np.asarray(dobj.deformation, dtype=np.float64)
+                if ds["kind"] == "measuredmap":
+                    X = np.linspace(-rect[0], rect[0], num=h.shape[0])
+                    Y = np.linspace(-rect[1], rect[1], num=h.shape[1])
+                else:
+                    X = np.linspace(-rect[0] / 2, rect[0] / 2, num=h.shape[1])
+                    Y = np.linspace(-rect[1] / 2, rect[1] / 2, num=h.shape[0])
+                key = f"map{len(EXTRA_ARRAYS) // 3}"
+                EXTRA_ARRAYS[key + "_h"] = np.transpose(h)
+                EXTRA_ARRAYS[key + "_dx"] = np.transpose(np.asarray(dobj.DerivX, dtype=np.float64))
+                EXTRA_ARRAYS[key + "_dy"] = np.transpose(np.asarray(dobj.DerivY, dtype=np.float64))
+                d["defects"].append({"kind": "gridmap", "source": ds["kind"], "arrays": key,
+                                     "x0": float(X[0]), "x1": float(X[-1]), "y0": float(Y[0]), "y1": float(Y[-1])})
     d["centre"] = [float(v) for v in obj.get_centre()]
     return d
 
@@ -129,6 +155,7 @@ def bundle_arrays(rays):
 
 def run_scene(scene, ignore_defects=True, source_rays=None, extra=None):
     R = ref()
+    EXTRA_ARRAYS.clear()
     chain = build_chain(scene)
     if source_rays is not None:
         chain.source_rays = source_rays
@@ -177,6 +204,7 @@ def run_scene(scene, ignore_defects=True, source_rays=None, extra=None):
         )
     if extra:
         spec.update(extra)
+    data.update(EXTRA_ARRAYS)
     data["spec"] = np.array(json.dumps(spec))
     return data, [len(o) for o in out], dt
 
@@ -267,7 +295,10 @@ def main(argv):
             continue
         scene = sc.resolve(name)
         has_def = any(o.get("defects") for o in scene["optics"])
-        for ign in ([True, False] if has_def else [True]):
+        # gridded defects: the reference's get_normal raises under numpy >= 2 (inhomogeneous list in
+        # np.linalg.norm, ART/ModuleDefects.py:126), so only its default IgnoreDefects=True path can be run
+        gridded = any(d["kind"] != "zernike" for o in scene["optics"] for d in o.get("defects", []))
+        for ign in ([True] if (gridded or not has_def) else [True, False]):
             tag = name + (("_ign" if ign else "_def") if has_def else "")
             data, counts, dt = run_scene(scene, ignore_defects=ign)
             p = save(tag, data)

@@ -159,6 +159,26 @@ SCENES = {
 }
 
 
+def measured_map(nx, ny, amplitude):
+    """A deterministic synthetic 'measured' height map (mm), shape (nx, ny) as MeasuredMap takes it."""
+    i = np.arange(nx)[:, None] / (nx - 1)
+    j = np.arange(ny)[None, :] / (ny - 1)
+    return amplitude * (np.sin(5.1 * i + 0.3) * np.cos(3.7 * j - 0.2) + 0.5 * np.sin(9.0 * i * j) + 0.25 * (i - 0.5) ** 2)
+
+
+SCENES.update({
+    # gridded defects (SURVEY.md 8(f) rank 3): ModuleDefects.Fourrier (+ a Zernike term) on the cfg4 geometry.
+    # (ModuleDefects.MeasuredMap cannot be run: its np.gradient call raises TypeError under numpy >= 2.)
+    "par_fourier": {
+        "source": {"Divergence": 0, "SourceSize": 100, "Wavelength": 800e-6, "NumberRays": 800},
+        "optics": [{"kind": "parabolic", "feff": 25.4, "offaxisangle_deg": 0, "support": ["rect", 40, 40],
+                    "defects": [{"kind": "fourier", "rms": 1e-4, "slope": -2, "smallest": 1.0, "seed": 3},
+                                {"kind": "zernike", "coefficients": [[2, 1, 5e-5], [3, 0, -4e-5]]}]}],
+        "distances": [15], "incidences": [0], "plane_angles": [0], "post": [], "detector_distance": 25.4,
+    },
+})
+
+
 def resolve(name):
     """Return the full scene dict for `name` (following 'base')."""
     s = dict(SCENES[name])

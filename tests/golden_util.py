@@ -46,10 +46,17 @@ class Golden:
             optic = dict(d)
             optic["support"] = tuple(d["support"])
             if d.get("defects"):
-                optic["defects"] = [
-                    {"kind": "zernike", "R": dd["R"], "max_order": dd["max_order"],
-                     "coefficients": {(int(n), int(m)): c for n, m, c in dd["coefficients"]}}
-                    for dd in d["defects"]]
+                optic["defects"] = []
+                for dd in d["defects"]:
+                    if dd["kind"] == "gridmap":
+                        key = dd["arrays"]
+                        optic["defects"].append({"kind": "gridmap", "h": self.z[key + "_h"], "dx": self.z[key + "_dx"],
+                                                 "dy": self.z[key + "_dy"], "x0": dd["x0"], "x1": dd["x1"],
+                                                 "y0": dd["y0"], "y1": dd["y1"]})
+                    else:
+                        optic["defects"].append(
+                            {"kind": "zernike", "R": dd["R"], "max_order": dd["max_order"],
+                             "coefficients": {(int(n), int(m)): c for n, m, c in dd["coefficients"]}})
             els.append({"optic": optic, "position": self.z[f"el{k}_position"],
                         "normal": self.z[f"el{k}_normal"], "majoraxis": self.z[f"el{k}_majoraxis"]})
         return els
@@ -88,8 +95,9 @@ def build_support(spec):
             "recthole": msupp.SupportRectangleHole, "rectrecthole": msupp.SupportRectangleRectHole}[kind](*p)
 
 
-def build_optic(spec):
-    """The package's optic object for a scene-catalogue optic spec (oracle/scenes.py)."""
+def build_optic(spec, fixture=None, derived=None):
+    """The package's optic object for a scene-catalogue optic spec (oracle/scenes.py).  Gridded defects
+    take the very maps the reference generated (stored in the fixture) when `fixture` is given."""
     import attosecondraytracing_b200.ModuleDefects as mdef
     import attosecondraytracing_b200.ModuleMask as mmask
     import attosecondraytracing_b200.ModuleMirror as mmirror
@@ -114,7 +122,19 @@ def build_optic(spec):
     else:
         raise ValueError(k)
     if spec.get("defects"):
-        dl = [mdef.Zernike(sup, {(int(n), int(mm_)): c for n, mm_, c in d["coefficients"]}) for d in spec["defects"]]
+        dl = []
+        for i, d in enumerate(spec["defects"]):
+            if d["kind"] == "zernike":
+                dl.append(mdef.Zernike(sup, {(int(n), int(mm_)): c for n, mm_, c in d["coefficients"]}))
+            elif fixture is not None:
+                dd = derived["defects"][i]
+                key = dd["arrays"]
+                dl.append(mdef.RawGridMap(fixture[key + "_h"], fixture[key + "_dx"], fixture[key + "_dy"],
+                                          dd["x0"], dd["x1"], dd["y0"], dd["y1"]))
+            elif d["kind"] == "fourier":
+                dl.append(mdef.Fourrier(sup, d["rms"], slope=d["slope"], smallest=d["smallest"], seed=d["seed"]))
+            else:
+                raise ValueError(d["kind"])
         m = mmirror.DeformedMirror(m, dl)
     return m
 
@@ -124,7 +144,8 @@ def golden_optical_elements(g):
     import attosecondraytracing_b200.ModuleOpticalElement as moe
     out = []
     for k, spec in enumerate(g.spec["optics"]):
-        out.append(moe.OpticalElement(build_optic(spec), g[f"el{k}_position"].copy(), g[f"el{k}_normal"].copy(),
+        optic = build_optic(spec, fixture=g.z, derived=g.spec["derived_optics"][k])
+        out.append(moe.OpticalElement(optic, g[f"el{k}_position"].copy(), g[f"el{k}_normal"].copy(),
                                       g[f"el{k}_majoraxis"].copy()))
     return out
 

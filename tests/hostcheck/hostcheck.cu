@@ -15,7 +15,8 @@ static std::string g_msg;
 extern "C" const char* hc_last_error() { return g_msg.c_str(); }
 
 // out_* arrays: n_elements x n, row k = bundle after element k (alive flags in out_alive)
-extern "C" int hc_trace(const ArtElementDesc* els, int n_el, const ArtZernikeDesc* defs, int n_def, long long n,
+extern "C" int hc_trace(const ArtElementDesc* els, int n_el, const ArtZernikeDesc* defs, int n_def,
+                        const ArtGridMapDesc* gmaps, int n_maps, long long n,
                         const double* px, const double* py, const double* pz, const double* ux, const double* uy,
                         const double* uz, unsigned flags, double* opx, double* opy, double* opz, double* oux,
                         double* ouy, double* ouz, double* opath, double* oinc, uint8_t* oalive) {
@@ -39,6 +40,14 @@ extern "C" int hc_trace(const ArtElementDesc* els, int n_el, const ArtZernikeDes
     zoff.push_back((int)ztab.size());
     ztab.insert(ztab.end(), t.begin(), t.end());
   }
+  std::vector<MapDev> maps(n_maps);
+  for (int i = 0; i < n_maps; ++i) {
+    std::string why = lower_gridmap(gmaps[i], maps[i]);  // host pointers here
+    if (!why.empty()) {
+      g_msg = why;
+      return -1;
+    }
+  }
   const bool ign = (flags & ART_TRACE_IGNORE_DEFECTS) != 0;
   for (long long i = 0; i < n; ++i) {
     Ray r;
@@ -48,7 +57,7 @@ extern "C" int hc_trace(const ArtElementDesc* els, int n_el, const ArtZernikeDes
     r.inc = ART_NAN;
     r.alive = true;
     for (int k = 0; k < n_el; ++k) {
-      if (r.alive) apply_element<true, true, SURFS_ANY, double>(E[k], r, ztab.data(), zoff.data(), ign, true);
+      if (r.alive) apply_element<true, true, SURFS_ANY, double>(E[k], r, ztab.data(), zoff.data(), ign, true, maps.data());
       const long long o = (long long)k * n + i;
       oalive[o] = r.alive;
       opx[o] = r.px; opy[o] = r.py; opz[o] = r.pz;

@@ -34,7 +34,8 @@ def trace(lowered, P, U, flags):
     outs = [np.empty(ne * n) for _ in range(8)]
     alive = np.zeros(ne * n, dtype=np.uint8)
     dp = C.POINTER(C.c_double)
-    rc = L.hc_trace(lowered.elements, C.c_int(ne), lowered.defects, C.c_int(lowered.n_defects), C.c_longlong(n),
+    rc = L.hc_trace(lowered.elements, C.c_int(ne), lowered.defects, C.c_int(lowered.n_defects), lowered.gridmaps,
+                    C.c_int(lowered.n_gridmaps), C.c_longlong(n),
                     *[c.ctypes.data_as(dp) for c in cols], C.c_uint(flags),
                     *[o.ctypes.data_as(dp) for o in outs], alive.ctypes.data_as(C.POINTER(C.c_uint8)))
     if rc != 0:

@@ -356,3 +356,49 @@ def test_find_optimal_distance_on_device(key):
     with pytest.raises(NameError):
         mp.FindOptimalDistance(det, final, OptFor="brightness")
     chain.close()
+
+
+def test_gridded_defects_against_oracle():
+    """Fourrier / MeasuredMap defects with IgnoreDefects=False (the reference's own get_normal raises
+    under numpy >= 2, so only the oracle can arbitrate) and the package's own Fourrier generator."""
+    eng = _engine()
+    import attosecondraytracing_b200.ModuleDefects as mdef
+    import attosecondraytracing_b200.ModuleMirror as mmirror
+    import attosecondraytracing_b200.ModuleSupport as msupp
+    import attosecondraytracing_b200.ModuleOpticalElement as moe
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
+    g = Golden("par_fourier_ign")
+    src = _source_bundle(g)
+    els = g.oracle_elements()
+    for ignore in (True, False):
+        chain = eng.DeviceChain(golden_optical_elements(g))
+        outs, _ = chain.trace(src, ignore_defects=ignore, history=False)
+        d = outs[0].to_numpy()
+        ref = orc.trace_chain(g["src_P"], g["src_U"], els, ignore_defects=ignore, numbers=g["src_num"])[-1]
+        assert np.array_equal(d["number"], ref["number"])
+        assert np.max(np.abs(d["P"] - ref["P"])) <= 1e-9 and np.max(np.abs(d["U"] - ref["U"])) <= 1e-11
+        assert np.max(np.abs(d["path"] - ref["path"])) <= 2e-9
+        chain.close()
+    # a measured map + the package's Fourier generator stacked on a sphere
+    sup = msupp.SupportRound(20)
+    i = np.arange(40)[:, None] / 39.0
+    j = np.arange(56)[None, :] / 55.0
+    mm_ = mdef.MeasuredMap(sup, 2e-4 * (np.sin(5.1 * i + 0.3) * np.cos(3.7 * j - 0.2)))
+    ff = mdef.Fourrier(sup, 5e-5, smallest=2.0, seed=11)
+    mirror = mmirror.DeformedMirror(mmirror.MirrorSpherical(800, sup), [mm_, ff])
+    oe = moe.OpticalElement(mirror, np.array([0.0, 0, 400.0]), np.array([0.0, 0.05, -1.0]), np.array([1.0, 0, 0]))
+    rng = np.random.default_rng(2)
+    n = 5000
+    P = np.column_stack([rng.uniform(-15, 15, n), rng.uniform(-15, 15, n), np.zeros(n)])
+    U = np.tile([0.0, 0, 1.0], (n, 1))
+    chain = eng.DeviceChain([oe])
+    outs, _ = chain.trace(RayBundle.from_numpy(P, U, device="cuda"), ignore_defects=False, history=False)
+    d = outs[0].to_numpy()
+    odefs = [{"kind": "gridmap", "h": x._h, "dx": x._dx, "dy": x._dy, "x0": x._extent[0], "x1": x._extent[1],
+              "y0": x._extent[2], "y1": x._extent[3]} for x in (mm_, ff)]
+    oel = [{"optic": {"kind": "spherical", "radius": 800.0, "support": ("round", 20), "defects": odefs},
+            "position": oe.position, "normal": oe.normal, "majoraxis": oe.majoraxis}]
+    ref = orc.trace_chain(P, U, oel, ignore_defects=False)[-1]
+    assert np.array_equal(d["number"], ref["number"]) and ref["number"].size > 1000
+    assert np.max(np.abs(d["P"] - ref["P"])) <= 1e-9 and np.max(np.abs(d["U"] - ref["U"])) <= 1e-11
+    chain.close()

@@ -28,10 +28,10 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"libart_b200.so does not export {name}"
     assert declared == set(_cabi.EXPORTED_SYMBOLS), declared ^ set(_cabi.EXPORTED_SYMBOLS)
     assert lib.art_version() == 100
-    sizes = (C.c_int32 * 4)()
+    sizes = (C.c_int32 * 5)()
     assert lib.art_abi_sizes(sizes) == 0
     assert list(sizes) == [C.sizeof(t) for t in (_cabi.ArtElementDesc, _cabi.ArtZernikeDesc, _cabi.ArtBundleView,
-                                                  _cabi.ArtDetector)] == [192, 40, 88, 184]
+                                                  _cabi.ArtDetector, _cabi.ArtGridMapDesc)] == [200, 40, 88, 184, 64]
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
@@ -229,3 +229,41 @@ def test_statistics_from_moments_row(name):
     assert abs(s["Diameter"] - g["Diameter"]) <= 1e-9
     assert abs(s["NA"] - g["NA"]) <= 1e-10
     assert summary_from_moments(np.zeros(24))["n_rays"] == 0
+
+
+def test_fourier_defect_generator_reproduces_reference_maps():
+    """ModuleDefects.Fourrier with the same numpy seed builds the maps the reference built
+    (tests/golden/par_fourier_ign.npz holds the reference's deformation / DerivX / DerivY)."""
+    import attosecondraytracing_b200.ModuleDefects as mdef
+    import attosecondraytracing_b200.ModuleSupport as msupp
+    g = Golden("par_fourier_ign")
+    d = g.spec["optics"][0]["defects"][0]
+    f = mdef.Fourrier(msupp.SupportRectangle(40, 40), d["rms"], slope=d["slope"], smallest=d["smallest"], seed=d["seed"])
+    for mine, key in ((f._h, "map0_h"), (f._dx, "map0_dx"), (f._dy, "map0_dy")):
+        ref = g[key]
+        assert mine.shape == ref.shape
+        assert np.max(np.abs(mine - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref)))
+    dd = g.spec["derived_optics"][0]["defects"][0]
+    assert f._extent == (dd["x0"], dd["x1"], dd["y0"], dd["y1"])
+    assert abs(f.RMS() - d["rms"]) < 1e-15
+    # host single-point evaluation == oracle bilinear interpolation
+    od = g.oracle_elements()[0]["optic"]["defects"][0]
+    pts = np.array([[3.3, -7.1, 0.0], [-19.9, 19.9, 0.0], [0.0, 0.0, 0.0]])
+    for p in pts:
+        assert abs(f.get_offset(p) - orc.gridmap_offset(od, p[None, :])[0]) <= 1e-18 + 1e-12 * abs(f.get_offset(p))
+        assert np.max(np.abs(f.get_normal(p) - orc.gridmap_normal(od, p[None, :])[0])) <= 1e-14
+
+
+def test_measured_map_slopes():
+    import attosecondraytracing_b200.ModuleDefects as mdef
+    import attosecondraytracing_b200.ModuleSupport as msupp
+    sup = msupp.SupportRectangle(40, 20)
+    i = np.arange(50)[:, None]
+    j = np.arange(30)[None, :]
+    Map = 1e-4 * (0.02 * i + 0.05 * j)  # a tilted plane: constant slopes
+    m = mdef.MeasuredMap(sup, Map)
+    assert np.allclose(m.DerivX, 1e-4 * 0.02 / (40 / 50)) and np.allclose(m.DerivY, 1e-4 * 0.05 / (20 / 30))
+    assert m._extent == (-40.0, 40.0, -20.0, 20.0) and m._h.shape == (50, 30)
+    p = np.array([1.0, 2.0, 0.0])
+    n = m.get_normal(p)
+    assert abs(n[0] / n[2] - 1e-4 * 0.02 / (40 / 50)) < 1e-15
