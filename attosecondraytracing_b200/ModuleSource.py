@@ -19,7 +19,7 @@ from .ModuleOpticalRay import RayBundle
 _SRC_COLUMNS = ("px", "py", "pz", "ux", "uy", "uz", "intensity")
 
 
-def _generate(kind, n_total, first, count, rho, axis, origin, wavelength, device, stride=1):
+def _generate(kind, n_total, first, count, rho, axis, origin, wavelength, device, stride=1, extended=(0, 0, 0.0)):
     device = require_cuda(device)
     # a point source keeps ONE origin for all rays instead of three point columns (24 B/ray less)
     cols = _SRC_COLUMNS[3:] if kind == 0 else _SRC_COLUMNS
@@ -34,7 +34,8 @@ def _generate(kind, n_total, first, count, rho, axis, origin, wavelength, device
         v.px = v.py = v.pz = None  # the generator writes directions only
     with torch.cuda.device(device):
         _cabi.check(_cabi.lib().art_source_generate(kind, n_total, first, count, stride, float(rho), _cabi.vec3(axis),
-                                                    _cabi.vec3(origin), C.byref(v), _stream()))
+                                                    _cabi.vec3(origin), int(extended[0]), int(extended[1]),
+                                                    float(extended[2]), C.byref(v), _stream()))
     b.col("intensity").fill_(1.0)
     return b
 
@@ -49,6 +50,20 @@ def PointSource(S, Axis, Divergence, NbRays, Wavelength=None, device=None, first
     of the NbRays-ray bundle (one rank's share)."""
     count = _slice_count(NbRays, first, stride) if count is None else count
     return _generate(0, NbRays, first, count, np.tan(Divergence), Axis, S, Wavelength, device, stride)
+
+
+def ExtendedSource(S, Axis, Diameter, Divergence, NbRays, Wavelength=None, device=None, first=0, count=None,
+                   stride=1):
+    """An extended source (ART/ModuleSource.py:85-131): max(30, 250*Diameter) -- at most NbRays/300 --
+    point sources on a Vogel spiral over a disk of the given Diameter, each emitting the same cone of
+    max(300, NbRays / n_sources) rays.  The bundle holds n_sources * rays_per_source rays (not exactly
+    NbRays, as in the reference), numbered source by source."""
+    n_ps = min(max(30, int(250 * Diameter)), int(NbRays / 300))
+    per = max(300, int(NbRays / n_ps))
+    n_total = n_ps * per
+    count = _slice_count(n_total, first, stride) if count is None else count
+    return _generate(2, n_total, first, count, np.tan(Divergence), Axis, S, Wavelength, device, stride,
+                     extended=(n_ps, per, Diameter / 2))
 
 
 def PlaneWaveDisk(Centre, Axis, Radius, NbRays, Wavelength=None, device=None, first=0, count=None, stride=1):
@@ -103,7 +118,7 @@ def synthetic_source(SourceProperties, first_optic_support=None, device=None, fi
     """The source bundle `OEPlacement` launches (ART/ModuleProcessing.py:55-79): from the origin along
     +x; a plane-wave disk when Divergence == 0 (radius SourceSize/2, or from the first optic's
     support when SourceSize == 0), else a point source; Gaussian intensities down to 1/e^2 at the edge.
-    ExtendedSource (Divergence and SourceSize both non-zero) is not part of the synthetic bundles."""
+    Divergence and SourceSize both non-zero give an ExtendedSource."""
     div = SourceProperties["Divergence"]
     size = SourceProperties["SourceSize"]
     n = int(SourceProperties["NumberRays"])
@@ -119,8 +134,10 @@ def synthetic_source(SourceProperties, first_optic_support=None, device=None, fi
         b = PlaneWaveDisk(origin, axis, radius, n, Wavelength=wl, device=device, first=first, count=count, stride=stride)
     else:
         if size != 0:
-            raise NotImplementedError("ExtendedSource bundles are not generated on the device")
-        b = PointSource(origin, axis, div, n, Wavelength=wl, device=device, first=first, count=count, stride=stride)
+            b = ExtendedSource(origin, axis, size, div, n, Wavelength=wl, device=device, first=first, count=count,
+                               stride=stride)
+        else:
+            b = PointSource(origin, axis, div, n, Wavelength=wl, device=device, first=first, count=count, stride=stride)
     if intensity:
         ApplyGaussianIntensityToRayList(b, 1 / np.e**2, group=group)
     return b

@@ -121,7 +121,8 @@ _SIGNATURES = {
     "art_delays": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p]),
     "art_source_generate": (C.c_int32, [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_double_p,
-                                        c_double_p, C.POINTER(ArtBundleView), C.c_void_p]),
+                                        c_double_p, C.c_int64, C.c_int64, C.c_double, C.POINTER(ArtBundleView),
+                                        C.c_void_p]),
     "art_source_extents": (C.c_int32, [C.POINTER(ArtBundleView), c_double_p, C.c_void_p, C.c_void_p]),
     "art_source_intensity": (C.c_int32, [C.POINTER(ArtBundleView), c_double_p, C.c_int32, C.c_double, C.c_double,
                                          C.c_void_p]),

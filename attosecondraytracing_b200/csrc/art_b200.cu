@@ -577,9 +577,13 @@ extern "C" int32_t art_delays(const double* l, const uint8_t* alive, int64_t n, 
 // -------------------------------------------------------------------------------------------------
 extern "C" int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t first, int64_t count, int64_t stride,
                                        double rho, const double axis[3], const double origin[3],
+                                       int64_t n_point_sources, int64_t rays_per_source, double source_radius,
                                        const ArtBundleView* bundle, void* stream) {
   if (!bundle || !axis || !origin) return fail(ART_E_INVALID, "NULL argument");
-  if (kind != 0 && kind != 1) return fail(ART_E_INVALID, "kind must be 0 (point source) or 1 (plane wave)");
+  if (kind < 0 || kind > 2)
+    return fail(ART_E_INVALID, "kind must be 0 (point source), 1 (plane wave) or 2 (extended source)");
+  if (kind == 2 && (n_point_sources < 1 || rays_per_source < 1 || n_point_sources * rays_per_source != n_total))
+    return fail(ART_E_INVALID, "extended source: n_total must equal n_point_sources * rays_per_source");
   if (n_total < 1 || first < 0 || count < 0 || stride < 1 || bundle->n < count ||
       (count > 0 && first + (count - 1) * stride >= n_total))
     return fail(ART_E_INVALID, "bad index range");
@@ -593,6 +597,9 @@ extern "C" int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t fi
   a.first = first;
   a.count = count;
   a.stride = stride;
+  a.per = kind == 2 ? rays_per_source : 1;
+  a.n_ps = kind == 2 ? n_point_sources : 1;
+  a.ps_radius = source_radius;
   a.rho = rho;
   const double ez[3] = {0.0, 0.0, 1.0};
   rotation_from_to(ez, axis, a.rot);  // RotationRayList(RayList, ez, Axis), ART/ModuleSource.py:79,167

@@ -838,10 +838,14 @@ __global__ void delays_kernel(const double* __restrict__ l, const uint8_t* __res
 // PlaneWaveDisk :135-169.  Ray k of n_total: (x,y) = sqrt(k/n_total) rho (cos k phi, sin k phi).
 //   kind 0 point source: direction normalise(x, y, 1) rotated by rot, point = origin
 //   kind 1 plane wave : point = rot (x, y, 0) + origin, direction = rot ez
+//   kind 2 extended source (ExtendedSource ART/ModuleSource.py:85-131): ray k*per + l = cone ray l of
+//          `per` from point source k of n_ps on a Vogel spiral of radius ps_radius
 // ---------------------------------------------------------------------------------------------
 struct SourceArgs {
   int kind;
   long long n_total, first, count, stride;
+  long long per, n_ps;   // kind 2: rays per point source, number of point sources
+  double ps_radius;
   double rho;
   double rot[9];
   double origin[3];
@@ -851,13 +855,30 @@ __global__ void source_kernel(const SourceArgs a) {
   const double golden = 3.141592653589793 * (3.0 - sqrt(5.0));
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.count;
        j += (long long)gridDim.x * blockDim.x) {
-    const double k = (double)(a.first + j * a.stride);
-    const double rad = sqrt(k / (double)a.n_total) * a.rho;
+    const long long idx = a.first + j * a.stride;
+    // the Vogel point that shapes the direction (kinds 0, 2) or the position (kind 1)
+    const double k = (double)(a.kind == 2 ? idx % a.per : idx);
+    const double kn = (double)(a.kind == 2 ? a.per : a.n_total);
+    const double rad = sqrt(k / kn) * a.rho;
     double s, c;
     sincos(golden * k, &s, &c);
     const double x = c * rad, y = s * rad;
     double px, py, pz, ux, uy, uz;
-    if (a.kind == 0) {
+    if (a.kind == 2) {
+      const double ks = (double)(idx / a.per);
+      const double rs = sqrt(ks / (double)a.n_ps) * a.ps_radius;
+      double ss, cs;
+      sincos(golden * ks, &ss, &cs);
+      const double xs = cs * rs, ys = ss * rs;
+      const double inv = 1.0 / sqrt(fma(x, x, fma(y, y, 1.0)));
+      const double vx = x * inv, vy = y * inv, vz = inv;
+      ux = a.rot[0] * vx + a.rot[1] * vy + a.rot[2] * vz;
+      uy = a.rot[3] * vx + a.rot[4] * vy + a.rot[5] * vz;
+      uz = a.rot[6] * vx + a.rot[7] * vy + a.rot[8] * vz;
+      px = a.rot[0] * xs + a.rot[1] * ys + a.origin[0];
+      py = a.rot[3] * xs + a.rot[4] * ys + a.origin[1];
+      pz = a.rot[6] * xs + a.rot[7] * ys + a.origin[2];
+    } else if (a.kind == 0) {
       const double inv = 1.0 / sqrt(fma(x, x, fma(y, y, 1.0)));
       const double vx = x * inv, vy = y * inv, vz = inv;
       ux = a.rot[0] * vx + a.rot[1] * vy + a.rot[2] * vz;

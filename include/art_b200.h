@@ -316,10 +316,15 @@ int32_t art_delays(const double* l, const uint8_t* alive, int64_t n, int32_t n_v
  *   kind 0  PointSource(origin, axis, Divergence, n_total)  ART/ModuleSource.py:54-81, rho = tan(Divergence)
  *   kind 1  PlaneWaveDisk(origin, axis, Radius, n_total)    ART/ModuleSource.py:135-169, rho = Radius
  *           (the reference emits rays 0 .. n_total-2 of the n_total-point spiral)
+ *   kind 2  ExtendedSource(origin, axis, Diameter, Divergence, ...)  ART/ModuleSource.py:85-131:
+ *           n_point_sources point sources on a Vogel spiral of radius source_radius, each emitting
+ *           rays_per_source cone rays (rho = tan(Divergence)); n_total = their product, ray number
+ *           k * rays_per_source + l.  (For kinds 0 and 1 the three extra arguments are ignored.)
  * axis: the bundle is rotated ez -> axis with RotationPoint semantics.
  */
 int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t first, int64_t count, int64_t stride,
                             double rho, const double axis[3], const double origin[3],
+                            int64_t n_point_sources, int64_t rays_per_source, double source_radius,
                             const ArtBundleView* bundle, void* stream);
 /* ApplyGaussianIntensityToRayList, ART/ModuleSource.py:219-261, in two calls so that sharded
  * bundles can all-reduce in between: art_source_extents writes {max angle(axis, u), max |P|} of

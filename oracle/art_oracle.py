@@ -718,6 +718,25 @@ def plane_wave_disk(centre, axis, radius, nb_rays, k=None):
     return P + np.asarray(centre, dtype=np.float64), U, kk
 
 
+def extended_source_layout(diameter, nb_rays):
+    """(number of point sources, rays per point source) of ExtendedSource, ART/ModuleSource.py:105-113."""
+    n_ps = max(30, int(250 * diameter))
+    n_ps = min(n_ps, int(nb_rays / 300))
+    return n_ps, max(300, int(nb_rays / n_ps))
+
+
+def extended_source(S, axis, diameter, divergence, nb_rays):
+    """ExtendedSource, ART/ModuleSource.py:85-131: point sources on a Vogel spiral over a disk, each
+    emitting the same cone; ray number = k * rays_per_source + l.  Returns (P, U, number)."""
+    n_ps, per = extended_source_layout(diameter, nb_rays)
+    centres = spiral_vogel(n_ps, diameter / 2)
+    cone = normalize(np.column_stack([spiral_vogel(per, np.tan(divergence)), np.ones(per)]))
+    P = np.repeat(np.column_stack([centres, np.zeros(n_ps)]), per, axis=0)
+    U = np.tile(cone, (n_ps, 1))
+    P, U = _rotate_rays(P, U, EZ, np.asarray(axis, dtype=np.float64))
+    return P + np.asarray(S, dtype=np.float64), U, np.arange(n_ps * per)
+
+
 def gaussian_intensity(P, U, fraction=1 / np.e**2):
     """ApplyGaussianIntensityToRayList, ART/ModuleSource.py:219-261."""
     axis = normalize(np.mean(U, axis=0))

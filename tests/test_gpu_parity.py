@@ -402,3 +402,23 @@ def test_gridded_defects_against_oracle():
     assert np.array_equal(d["number"], ref["number"]) and ref["number"].size > 1000
     assert np.max(np.abs(d["P"] - ref["P"])) <= 1e-9 and np.max(np.abs(d["U"] - ref["U"])) <= 1e-11
     chain.close()
+
+
+def test_extended_source_on_device():
+    """K0 kind 2: ModuleSource.ExtendedSource == the reference's ExtendedSource + Gaussian intensities."""
+    import os
+    from golden_util import GOLDEN_DIR
+    from attosecondraytracing_b200 import ModuleSource as msrc
+    z = np.load(os.path.join(GOLDEN_DIR, "extsource.npz"))
+    for case in ("a", "b"):
+        diameter, divergence, nb = z[case + "_params"]
+        b = msrc.synthetic_source({"Divergence": float(divergence), "SourceSize": float(diameter), "NumberRays": int(nb),
+                                   "Wavelength": 800e-6}, device="cuda")
+        d = b.to_numpy()
+        assert np.array_equal(d["number"], z[case + "_num"])
+        assert np.max(np.abs(d["P"] - z[case + "_P"])) <= 1e-13 and np.max(np.abs(d["U"] - z[case + "_U"])) <= 1e-14
+        assert np.max(np.abs(d["intensity"] - z[case + "_I"])) <= 1e-11
+        part = msrc.ExtendedSource(np.zeros(3), np.array([1.0, 0, 0]), float(diameter), float(divergence), int(nb),
+                                   device="cuda", first=5, stride=7)
+        pd = part.to_numpy()
+        assert np.array_equal(pd["number"], z[case + "_num"][5::7]) and np.array_equal(pd["P"], d["P"][5::7])

@@ -153,3 +153,15 @@ def test_find_optimal_distance_matches_reference(key):
     if opt_for != "duration":
         assert abs(spot2 - ref_spot) <= 1e-6 * max(ref_spot, 1e-9) + 1e-9
     assert abs(dur2 - ref_dur) <= 1e-5 * max(ref_dur, 1.0)
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_extended_source_matches_reference(case):
+    import os
+    from golden_util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "extsource.npz"))
+    diameter, divergence, nb = z[case + "_params"]
+    P, U, num = orc.extended_source(np.zeros(3), orc.EX, float(diameter), float(divergence), int(nb))
+    assert np.array_equal(num, z[case + "_num"])
+    assert np.max(np.abs(P - z[case + "_P"])) <= 1e-14 and np.max(np.abs(U - z[case + "_U"])) <= 1e-14
+    assert np.max(np.abs(orc.gaussian_intensity(P, U) - z[case + "_I"])) <= 1e-12
