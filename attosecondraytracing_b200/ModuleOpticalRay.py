@@ -310,6 +310,21 @@ class RayBundle:
                       Wavelength=self.wavelength, Incidence=inc,
                       Intensity=None if d["intensity"] is None else float(d["intensity"][j]))
 
+    # ---- persistence: bundles pickle as host columns (ModuleProcessing.save_compressed) -----------------
+    def __getstate__(self):
+        return {"n": self.n, "names": self._names, "wavelength": self.wavelength,
+                "storage": self._storage[:, : self.n].cpu().numpy(),
+                "alive": None if self.alive is None else self.alive.cpu().numpy(),
+                "number": None if self.number is None else self.number.cpu().numpy(),
+                "origin": None if self.origin is None else self.origin.cpu().numpy()}
+
+    def __setstate__(self, st):
+        self.__init__(st["n"], device="cpu", columns=st["names"], wavelength=st["wavelength"])
+        self._storage[:, : self.n] = torch.from_numpy(st["storage"])
+        self.alive = None if st["alive"] is None else torch.from_numpy(st["alive"])
+        self.number = None if st["number"] is None else torch.from_numpy(st["number"])
+        self.origin = None if st["origin"] is None else torch.from_numpy(st["origin"])
+
     def content_key(self):
         """Cheap identity of the bundle's content for OpticalChain's result cache."""
         return (id(self._storage), self.n, self.version, None if self.origin is None else tuple(self.origin.tolist()))

@@ -244,6 +244,34 @@ def FindOptimalDistance(Detector, RayList, OptFor="intensity", Amplitude=None, P
     return moving, spot, dur
 
 
+def save_compressed(obj, filename: str = None):
+    """Pickle `obj` into an lzma-compressed file `<filename>_<i>.xz` (ART/ModuleProcessing.py:612-627).
+    RayBundles inside `obj` are stored as host columns (not as millions of Ray objects)."""
+    import lzma
+    import os
+    import pickle
+    from datetime import datetime
+    if not type(filename) == str:
+        filename = "kept_data_" + datetime.now().strftime("%Y-%m-%d-%Hh%M")
+    i = 0
+    while os.path.exists(filename + f"_{i}.xz"):
+        i += 1
+    filename = filename + f"_{i}"
+    with lzma.open(filename + ".xz", "wb") as f:
+        pickle.dump(obj, f)
+    print("Saved results to " + filename + ".xz.")
+    print("->To reload from disk do: kept_data = mp.load_compressed('" + filename + "')")
+    return filename
+
+
+def load_compressed(filename: str):
+    """Load an object saved by save_compressed (ART/ModuleProcessing.py:630-635); bundles come back on the host."""
+    import lzma
+    import pickle
+    with lzma.open(filename + ".xz", "rb") as f:
+        return pickle.load(f)
+
+
 def _hash_list_of_objects(objs):
     """Summed hashes, as ART/ModuleProcessing.py:597-602 (kept for small host-side lists)."""
     return sum(hash(o) for o in objs)

@@ -267,3 +267,21 @@ def test_measured_map_slopes():
     p = np.array([1.0, 2.0, 0.0])
     n = m.get_normal(p)
     assert abs(n[0] / n[2] - 1e-4 * 0.02 / (40 / 50)) < 1e-15
+
+
+def test_save_and_load_compressed_round_trip(tmp_path, capsys):
+    import attosecondraytracing_b200.ModuleProcessing as mp
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
+    import torch
+    g = Golden("cfg3_2tor")
+    b = RayBundle.from_numpy(g["src_P"], g["src_U"], intensity=g["src_I"])
+    b.alive = torch.ones(b.n, dtype=torch.uint8)
+    b.alive[100:] = 0
+    b.invalidate()
+    name = mp.save_compressed({"rays": b, "SpotSizeSD": 1.25}, str(tmp_path / "kept"))
+    assert name.endswith("kept_0")
+    assert mp.save_compressed({"x": 1}, str(tmp_path / "kept")).endswith("kept_1")  # never overwrites
+    back = mp.load_compressed(name)
+    assert back["SpotSizeSD"] == 1.25 and len(back["rays"]) == 100
+    assert np.array_equal(back["rays"].to_numpy()["P"], g["src_P"][:100])
+    assert "Saved results" in capsys.readouterr().out
