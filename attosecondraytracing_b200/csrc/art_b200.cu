@@ -179,7 +179,7 @@ extern "C" int32_t art_chain_destroy(ArtChain* c) {
 
 template <typename K>
 static cudaError_t allow_smem(K kernel, size_t bytes) {
-  if (bytes <= 48 * 1024) return cudaSuccess;
+  if (bytes <= 32 * 1024) return cudaSuccess;  // static + dynamic stay below the default 48 KB limit
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
@@ -318,7 +318,10 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
                             const ArtBundleView* out_final, const ArtBundleView* out_history, uint32_t flags,
                             const ArtDetector* det, double* x_out, double* y_out, double* l_out,
                             double* central_out, double* moments_out, cudaStream_t st, bool keep_l2 = false,
-                            double place_distance = 0.0, ArtDetector* place_det = nullptr) {
+                            double place_distance = 0.0, ArtDetector* place_det = nullptr, int chunk_blocks = 0,
+                            int chunk_row0 = 0) {
+  // chunk_blocks > 0: this launch is one chunk of a pipelined trace -- it uses exactly chunk_blocks
+  // blocks, writes its partial rows at chunk_row0 and leaves the fold to the caller
   if (!c) return fail(ART_E_INVALID, "chain is NULL");
   if (!in) return fail(ART_E_INVALID, "input bundle is NULL");
   if (variant_first < 0 || n_variants < 1 || variant_first + n_variants > c->n_variants)
@@ -371,8 +374,10 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
   a.y_out = y_out;
   a.l_out = l_out;
 
-  const int bpv = blocks_per_variant(c, in->n, n_variants, ART_RPT);
-  if ((size_t)bpv * n_variants > c->partial_rows) return fail(ART_E_INVALID, "internal: partial buffer too small");
+  const int bpv = chunk_blocks > 0 ? chunk_blocks : blocks_per_variant(c, in->n, n_variants, ART_RPT);
+  if ((size_t)bpv * n_variants + chunk_row0 > c->partial_rows)
+    return fail(ART_E_INVALID, "internal: partial buffer too small");
+  if (chunk_blocks > 0) a.partials = c->d_partials + (size_t)chunk_row0 * PLEN_TRACE;
   const dim3 grid(bpv, n_variants);
   a.moments_smem_offset = (int)c->smem_bytes;
   a.stage_smem_offset = (int)c->smem_bytes;
@@ -402,7 +407,7 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
     if (want_inc) ART_TRACE_LAUNCH(true, false);
     else ART_TRACE_LAUNCH(false, false);
     ART_LAUNCHED();
-    if (central_out) {
+    if (central_out && chunk_blocks == 0) {
       // place_det: fold the central sums and place the variant's detector in the same launch
       fold_kernel<<<n_variants, TPB, 0, st>>>(c->d_partials, bpv, place_det ? 3 : 0, central_out, nullptr,
                                               place_distance, place_det);
@@ -706,20 +711,16 @@ extern "C" int32_t art_run_host(ArtChain* c, const ArtBundleView* in_host, const
   auto col = [&](int j) { return w.cols + (size_t)j * cap; };
   cudaStream_t st = w.stream;
 
-  ArtBundleView din = {};
-  din.n = (int64_t)n;
-  const double* src[7] = {in_host->px, in_host->py, in_host->pz, in_host->ux,
-                          in_host->uy, in_host->uz, in_host->intensity};
-  double** dst[7] = {&din.px, &din.py, &din.pz, &din.ux, &din.uy, &din.uz, &din.intensity};
-  const bool uniform_point = (flags & ART_TRACE_UNIFORM_POINT) != 0;
-  for (int j = 0; j < 7; ++j) {
-    if (!src[j]) continue;
-    *dst[j] = col(j);
-    const size_t cnt = (uniform_point && j < 3) ? 1 : n;  // point source: one origin for all rays
-    if (cnt) ART_CUDA(cudaMemcpyAsync(col(j), src[j], sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
-  }
   if (in_host->path || in_host->alive)
     return fail(ART_E_UNSUPPORTED, "art_run_host starts from a fresh source bundle (no path / alive columns)");
+  const bool uniform_point = (flags & ART_TRACE_UNIFORM_POINT) != 0;
+  const double* src[7] = {in_host->px, in_host->py, in_host->pz, in_host->ux,
+                          in_host->uy, in_host->uz, in_host->intensity};
+  ArtBundleView din = {};
+  din.n = (int64_t)n;
+  double** dst[7] = {&din.px, &din.py, &din.pz, &din.ux, &din.uy, &din.uz, &din.intensity};
+  for (int j = 0; j < 7; ++j)
+    if (src[j]) *dst[j] = col(j);
 
   ArtBundleView dout = {};
   dout.n = (int64_t)n;
@@ -731,9 +732,44 @@ extern "C" int32_t art_run_host(ArtChain* c, const ArtBundleView* in_host, const
   dout.alive = w.alive;
   dout.intensity = din.intensity;
 
-  rc = launch_trace(c, 0, 1, &din, &dout, nullptr, flags, nullptr, nullptr, nullptr, nullptr, c->d_central,
-                    nullptr, st);
-  if (rc) return rc;
+  // Pipelined upload: the bundle goes over PCIe in chunks on the copy stream while the compute stream
+  // traces the chunks that have arrived; the chunks' partial rows are folded once at the end.
+  const int n_chunks = n >= (size_t)1 << 20 ? 8 : 1;
+  size_t chunk = ((n + n_chunks - 1) / n_chunks + 1) & ~size_t(1);  // even: pairs stay aligned
+  if (chunk == 0) chunk = 2;
+  int chunk_blocks = c->sm_count * 8 / n_chunks;
+  if (chunk_blocks < 1) chunk_blocks = 1;
+  if (uniform_point)
+    for (int j = 0; j < 3; ++j)
+      ART_CUDA(cudaMemcpyAsync(col(j), src[j], sizeof(double), cudaMemcpyHostToDevice, w.copy_stream));
+  int launched_chunks = 0;
+  for (int k = 0; k < n_chunks; ++k) {
+    const size_t off = (size_t)k * chunk;
+    if (off >= n && !(n == 0 && k == 0)) break;
+    const size_t len = n == 0 ? 0 : (off + chunk <= n ? chunk : n - off);
+    for (int j = uniform_point ? 3 : 0; j < 7; ++j)
+      if (src[j] && len)
+        ART_CUDA(cudaMemcpyAsync(col(j) + off, src[j] + off, sizeof(double) * len, cudaMemcpyHostToDevice, w.copy_stream));
+    ART_CUDA(cudaEventRecord(w.ev[k], w.copy_stream));
+    ART_CUDA(cudaStreamWaitEvent(st, w.ev[k], 0));
+    ArtBundleView cin = din, cout = dout;
+    cin.n = cout.n = (int64_t)len;
+    double** ci[4] = {&cin.ux, &cin.uy, &cin.uz, &cin.intensity};
+    for (auto p : ci)
+      if (*p) *p += off;
+    if (!uniform_point) { cin.px += off; cin.py += off; cin.pz += off; }
+    double** co[8] = {&cout.px, &cout.py, &cout.pz, &cout.ux, &cout.uy, &cout.uz, &cout.path, &cout.incidence};
+    for (auto p : co)
+      if (*p) *p += off;
+    cout.alive += off;
+    cout.intensity = nullptr;
+    rc = launch_trace(c, 0, 1, &cin, &cout, nullptr, flags, nullptr, nullptr, nullptr, nullptr, c->d_central,
+                      nullptr, st, false, 0.0, nullptr, chunk_blocks, k * chunk_blocks);
+    if (rc) return rc;
+    ++launched_chunks;
+  }
+  fold_kernel<<<1, TPB, 0, st>>>(c->d_partials, launched_chunks * chunk_blocks, 0, c->d_central, nullptr);
+  ART_LAUNCHED();
   if (manual_det) {
     ART_CUDA(cudaMemcpyAsync(c->d_det, manual_det, sizeof(ArtDetector), cudaMemcpyHostToDevice, st));
   } else {

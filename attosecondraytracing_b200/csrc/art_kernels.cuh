@@ -7,7 +7,7 @@
 namespace art {
 
 #ifndef ART_TPB
-#define ART_TPB 256
+#define ART_TPB 192  // 192 threads x 2 blocks/SM leaves 170 registers per thread: the lock-step pair needs ~164, no spills
 #endif
 constexpr int TPB = ART_TPB;   // threads per block
 constexpr int RPT = 2;         // rays per thread: adjacent rays -> 128-bit column accesses
@@ -225,6 +225,9 @@ __device__ __forceinline__ void moments_add(ACC& m, const DetHit& h, double l0, 
 #ifndef ART_STAGE
 #define ART_STAGE 1
 #endif
+#ifndef ART_STAGE_INC
+#define ART_STAGE_INC 1  // staging also in the kernels that compute incidences (pays off once nothing spills)
+#endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Input staging: every thread copies the 16-byte column slices of its NEXT ray pair into its own
@@ -300,9 +303,9 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
   constexpr bool PACK = (N == 2) && !HAS_DEF;
   // cp.async input staging: plain trace only (the fused-detector kernels spend their shared memory on
   // the moment slots and read an L2-resident source bundle)
-  // and, by measurement, only where Ray.incidence is not computed (with it the extra live state of the
-  // staging loop costs more in spills than the hidden latency gains: 0.469 vs 0.430 ms on cfg2)
-  constexpr bool STAGE = (N == 2) && !WITH_DET && !WANT_INC && (ART_STAGE != 0);
+  // (with 256-thread blocks / 128 registers the staging loop's extra live state made the incidence
+  // kernels spill and lose: 0.469 vs 0.430 ms on cfg2; with 192-thread blocks it wins: 0.394 vs 0.428)
+  constexpr bool STAGE = (N == 2) && !WITH_DET && (!WANT_INC || ART_STAGE_INC != 0) && (ART_STAGE != 0);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ElemDev* sE = reinterpret_cast<ElemDev*>(smem_raw);
   double* sZ = reinterpret_cast<double*>(smem_raw + sizeof(ElemDev) * ART_MAX_ELEMENTS);
