@@ -225,6 +225,9 @@ __device__ __forceinline__ void moments_add(ACC& m, const DetHit& h, double l0, 
 #ifndef ART_STAGE
 #define ART_STAGE 1
 #endif
+#ifndef ART_UPT_HOIST
+#define ART_UPT_HOIST 1
+#endif
 #ifndef ART_STAGE_INC
 #define ART_STAGE_INC 1  // staging also in the kernels that compute incidences (pays off once nothing spills)
 #endif
@@ -338,6 +341,19 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
 #pragma unroll
   for (int j = 0; j < ART_CENTRAL_LEN; ++j) ART_ACC(j) = 0.0;
   __syncthreads();
+  // point source: the one origin in the frame of the first element, computed once per block with the
+  // very FMA sequence apply_element uses per ray
+  __shared__ double sOrg[3];
+  if (UPT && ART_UPT_HOIST) {
+    if (threadIdx.x < 3) {
+      const ElemDev& E = sE[0];
+      const int q = threadIdx.x;
+      const double dx = a.in.px[0] - E.pos[0], dy = a.in.py[0] - E.pos[1], dz = a.in.pz[0] - E.pos[2];
+      sOrg[q] = fma(E.rot[3 * q], dx, fma(E.rot[3 * q + 1], dy, fma(E.rot[3 * q + 2], dz, E.ctr[q])));
+    }
+    __syncthreads();
+  }
+  const double* const eorg0 = (UPT && ART_UPT_HOIST) ? sOrg : nullptr;
 
   const bool ignore_defects = (a.flags & ART_TRACE_IGNORE_DEFECTS) != 0;
   const long long n = a.n;
@@ -447,7 +463,8 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
       RayT<D2> pr = pack_rays(r[0], r[N - 1]);
       for (int k = 0; k < a.n_elements; ++k) {
         const bool inc_here = WANT_INC && (k == last || a.has_hist);
-        if (any(pr.alive)) apply_element<WANT_INC, HAS_DEF, SURFS, D2>(sE[k], pr, sZ, sZoff, ignore_defects, inc_here, a.maps);
+        if (any(pr.alive)) apply_element<WANT_INC, HAS_DEF, SURFS, D2>(sE[k], pr, sZ, sZoff, ignore_defects, inc_here, a.maps,
+                                                                         k == 0 ? eorg0 : nullptr);
         if (a.has_hist) {
           unpack_rays(pr, r[0], r[N - 1]);
           store_bundle<N>(a.hist[k], row + i, out_vec, two, r, WANT_INC);
@@ -460,7 +477,8 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
 #pragma unroll
         for (int q = 0; q < N; ++q)
           if (r[q].alive)
-            apply_element<WANT_INC, HAS_DEF, SURFS, double>(sE[k], r[q], sZ, sZoff, ignore_defects, inc_here, a.maps);
+            apply_element<WANT_INC, HAS_DEF, SURFS, double>(sE[k], r[q], sZ, sZoff, ignore_defects, inc_here, a.maps,
+                                                            k == 0 ? eorg0 : nullptr);
         if (a.has_hist) store_bundle<N>(a.hist[k], row + i, out_vec, two, r, WANT_INC);
       }
     }

@@ -235,12 +235,21 @@ ART_HD TorEval<T> tor_eval(const RayT<T>& r, T t, double R, double r2) {
 // step after dt is at most dt^2 / |F'|; at the noise floor of F (~ eps r^2) dt itself is ~1e-13 mm
 // and the test holds as well.  Lanes that are done are frozen; a lane that walks past the minimum of
 // F without meeting a zero (the line misses the solid) or needs more than 64 steps yields NaN.
-template <int DIR, class T>
+// PRE leading steps are taken without the convergence test (the start is known to need them: from
+// the tangent plane a ray needs three evaluations); only their slope signs are accumulated.  They are
+// taken by every lane alike, so a ray's result still never depends on its partner.
+template <int DIR, int PRE, class T>
 ART_HD T tor_newton(const RayT<T>& r, T t, TorEval<T> e, double R, double r2, double scale,
                     typename MaskOf<T>::type active) {
   typedef typename MaskOf<T>::type M;
   T result = splat<T>(ART_NAN);
   M todo = active;
+#pragma unroll
+  for (int p = 0; p < PRE; ++p) {
+    todo = mand(todo, (DIR > 0 ? e.dF : -e.dF) > 0.0);
+    t = t - e.F * fast_rcp(e.dF);
+    e = tor_eval(r, t, R, r2);
+  }
   for (int it = 0; it < 64 && any(todo); ++it) {
     const T slope = DIR > 0 ? e.dF : -e.dF;
     const M good = slope > 0.0;
@@ -255,6 +264,12 @@ ART_HD T tor_newton(const RayT<T>& r, T t, TorEval<T> e, double R, double r2, do
   return result;
 }
 
+#ifndef ART_NEWTON_PRE
+#define ART_NEWTON_PRE 2
+#endif
+#ifndef ART_CHEAP_INSIDE
+#define ART_CHEAP_INSIDE 1
+#endif
 template <class T>
 ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>::type act) {
   typedef typename MaskOf<T>::type M;
@@ -271,15 +286,41 @@ ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>
     e0.F = sel(fine, e0.F, e1.F);
     e0.dF = sel(fine, e0.dF, e1.dF);
   }
-  const T tb = tor_newton<+1>(r, t0, e0, R, r2, rr, act);
-  T ta = splat<T>(ART_NAN);
-  const TorEval<T> o = tor_eval(r, splat<T>(0.0), R, r2);
-  const M outside = o.F > 0.0;  // origin outside the solid: a second, nearer root may exist
-  const M away = mand(outside, mnot(o.dF < 0.0));  // ... but not if we move away from the solid
-  if (any(mand(act, mand(outside, mnot(away))))) {
-    ta = tor_newton<-1>(r, splat<T>(0.0), o, R, r2, rr, mand(act, mand(outside, mnot(away))));
+  const T tb = tor_newton<+1, ART_NEWTON_PRE>(r, t0, e0, R, r2, rr, act);
+  // the far root as a candidate: t > 1e-12, z < -R, on the support (pick_candidate's rule for one root)
+  M cb = tb > 1e-12;
+  {
+    const T x = mfma(tb, r.ux, r.px), y = mfma(tb, r.uy, r.py), z = mfma(tb, r.uz, r.pz);
+    cb = mand(mand(cb, z < -R), in_support(E, x, y));
   }
-  const T t = pick_candidate<true>(E, r, ta, tb, -R);
+  // A second, nearer root exists only when the origin lies OUTSIDE the solid (F(0) > 0).  Sign of F(0)
+  // without the square root: with A = x^2 + y^2 + z^2 + R^2 - r^2 the origin is inside iff y^2 <= r^2 and
+  // (rho <= R or A <= 2 R rho); a relative margin of 1e-9 (1e7 times the rounding error of either side)
+  // decides "clearly inside", anything closer to the surface takes the exact evaluation below.
+  M maybe_out = act;
+#if ART_CHEAP_INSIDE
+  {
+    const T s = mfma(r.px, r.px, r.pz * r.pz), yy = r.py * r.py;
+    const T A = s + yy + E.sp[3];
+    const M in_y = yy < 0.999999999 * r2;
+    const M in_rho = mor(mor(s <= E.sp[4], A <= 0.0), A * A < (3.999999996 * E.sp[4]) * s);
+    maybe_out = mand(act, mnot(mand(in_y, in_rho)));
+  }
+#endif
+  if (!any(maybe_out)) return sel(cb, tb, ART_NAN);
+  const TorEval<T> o = tor_eval(r, splat<T>(0.0), R, r2);
+  const M outside = mand(maybe_out, o.F > 0.0);    // origin outside the solid: a second, nearer root may exist
+  const M away = mand(outside, mnot(o.dF < 0.0));  // ... but not if we move away from the solid
+  const M need = mand(outside, mnot(away));
+  T ta = splat<T>(ART_NAN);
+  if (any(need)) ta = tor_newton<-1, 0>(r, splat<T>(0.0), o, R, r2, rr, need);
+  M ca = mand(need, ta > 1e-12);
+  {
+    const T x = mfma(ta, r.ux, r.px), y = mfma(ta, r.uy, r.py), z = mfma(ta, r.uz, r.pz);
+    ca = mand(mand(ca, z < -R), in_support(E, x, y));
+  }
+  // one candidate -> it, two -> the nearer (ta <= tb)
+  const T t = sel(ca, ta, sel(cb, tb, ART_NAN));
   return sel(away, ART_NAN, t);
 }
 
@@ -408,7 +449,34 @@ ART_HD void surface_normal(const ElemDev& E, T x, T y, T z, T& nx, T& ny, T& nz)
 }
 
 // atan2(y, x) for y >= 0 (result in [0, pi]), branch-free: one division for the reduced argument
-// z (|z| <= tan(pi/8)) and the Maclaurin series of atan to z^41 (truncation < 2e-18 z).
+// z (|z| <= tan(pi/8)) and atan(z) = z - z w P(w), w = z^2, P of degree 11 interpolating (1 - atan(z)/z)/w
+// at the Chebyshev nodes of [0, tan^2(pi/8)] (relative error of atan below 3.2e-18 with the coefficients
+// rounded to double; fitted with mpmath at 60 digits).  Estrin evaluation: dependency depth 5 instead of
+// 12 -- this kernel is bound by dependent-FP64 latency, not by the FMA count.  The coefficients are
+// constant-bank operands of the FMAs on the device (no UMOV pairs to materialise 64-bit immediates).
+#ifndef ART_ATAN_SERIES
+#define ART_ATAN_SERIES 0
+#endif
+#define ART_ATAN_COEFFS                                                                                     \
+  {0.3333333333333333, -0.19999999999999804, 0.14285714285659828, -0.11111111105155447,                     \
+   0.09090908753500877, -0.07692296375032143, 0.06666424885738255, -0.05878928997834775,                    \
+   0.05230454270650244, -0.04551593220626549, 0.034570561981427744, -0.016285756855221028}
+#ifdef __CUDACC__
+__constant__ double c_atan[12] = ART_ATAN_COEFFS;
+#endif
+template <class T>
+ART_HD T atan_poly(T w) {
+#ifdef __CUDA_ARCH__
+  const double* c = c_atan;
+#else
+  const double c[12] = ART_ATAN_COEFFS;
+#endif
+  const T w2 = w * w, w4 = w2 * w2, w8 = w4 * w4;
+  const T p01 = mfma(w, c[1], c[0]), p23 = mfma(w, c[3], c[2]), p45 = mfma(w, c[5], c[4]);
+  const T p67 = mfma(w, c[7], c[6]), p89 = mfma(w, c[9], c[8]), pab = mfma(w, c[11], c[10]);
+  const T q0 = mfma(p23, w2, p01), q1 = mfma(p67, w2, p45), q2 = mfma(pab, w2, p89);
+  return mfma(q2, w8, mfma(q1, w4, q0));
+}
 template <class T>
 ART_HD T fatan2_ypos(T y, T x) {
   typedef typename MaskOf<T>::type M;
@@ -418,12 +486,16 @@ ART_HD T fatan2_ypos(T y, T x) {
   const M big = lo > 0.41421356237309503 * hi;               // beyond tan(pi/8): rotate by pi/4
   const T z = fdiv(sel(big, lo - hi, lo), sel(big, lo + hi, hi));
   const T w = z * z;
+#if ART_ATAN_SERIES
   T p = splat<T>(-1.0 / 41.0);
   p = mfma(p, w, 1.0 / 39.0);  p = mfma(p, w, -1.0 / 37.0); p = mfma(p, w, 1.0 / 35.0);  p = mfma(p, w, -1.0 / 33.0);
   p = mfma(p, w, 1.0 / 31.0);  p = mfma(p, w, -1.0 / 29.0); p = mfma(p, w, 1.0 / 27.0);  p = mfma(p, w, -1.0 / 25.0);
   p = mfma(p, w, 1.0 / 23.0);  p = mfma(p, w, -1.0 / 21.0); p = mfma(p, w, 1.0 / 19.0);  p = mfma(p, w, -1.0 / 17.0);
   p = mfma(p, w, 1.0 / 15.0);  p = mfma(p, w, -1.0 / 13.0); p = mfma(p, w, 1.0 / 11.0);  p = mfma(p, w, -1.0 / 9.0);
   p = mfma(p, w, 1.0 / 7.0);   p = mfma(p, w, -1.0 / 5.0);  p = mfma(p, w, 1.0 / 3.0);
+#else
+  const T p = atan_poly(w);
+#endif
   T a = mfma(-(z * w), p, z);                                // atan(z)
   a = a + sel(big, 0.78539816339744831, 0.0);
   a = sel(swap, 1.5707963267948966 - a, a);
@@ -448,16 +520,22 @@ enum { SURFS_ANY = 0, SURFS_TOROID = 1, SURFS_QUADRIC = 2 };
 template <bool WANT_INC, bool HAS_DEF, int SURFS, class T>
 ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict__ ztab,
                           const int* __restrict__ zoff, bool ignore_defects, bool inc_here,
-                          const MapDev* __restrict__ maps = nullptr) {
+                          const MapDev* __restrict__ maps = nullptr,
+                          const double* __restrict__ eorg = nullptr) {
   typedef typename MaskOf<T>::type M;
   const M act = r.alive;
   // lab -> element frame (:289-295): p_e = R (p - pos) + centre, u_e = R u
+  // eorg: the origin shared by all rays (point source), already in this element's frame
   RayT<T> e;
-  {
+  if (eorg) {
+    e.px = splat<T>(eorg[0]); e.py = splat<T>(eorg[1]); e.pz = splat<T>(eorg[2]);
+  } else {
     const T dx = r.px - E.pos[0], dy = r.py - E.pos[1], dz = r.pz - E.pos[2];
     e.px = mfma(E.rot[0], dx, mfma(E.rot[1], dy, mfma(E.rot[2], dz, E.ctr[0])));
     e.py = mfma(E.rot[3], dx, mfma(E.rot[4], dy, mfma(E.rot[5], dz, E.ctr[1])));
     e.pz = mfma(E.rot[6], dx, mfma(E.rot[7], dy, mfma(E.rot[8], dz, E.ctr[2])));
+  }
+  {
     e.ux = mfma(E.rot[0], r.ux, mfma(E.rot[1], r.uy, E.rot[2] * r.uz));
     e.uy = mfma(E.rot[3], r.ux, mfma(E.rot[4], r.uy, E.rot[5] * r.uz));
     e.uz = mfma(E.rot[6], r.ux, mfma(E.rot[7], r.uy, E.rot[8] * r.uz));
