@@ -145,10 +145,11 @@ __device__ __forceinline__ DetHit detector_ray(const ArtDetector& D, const Ray& 
   h.x = fma(D.rot[0], hx, fma(D.rot[1], hy, D.rot[2] * hz));
   h.y = fma(D.rot[3], hx, fma(D.rot[4], hy, D.rot[5] * hz));
   h.L = fabs(t) + r.path;
-  // tan^2(angle(u, central vector)/2) from Kahan's form (ART/ModuleGeometry.py:40-44) with unit vectors
+  // Kahan's angle (ART/ModuleGeometry.py:40-44) between unit vectors: tan^2(angle/2) = |u-c|^2 / |u+c|^2
+  // and |u+c|^2 = 4 - |u-c|^2, so the largest angle is the largest |u-c|^2: only that is tracked per ray and
+  // moments_finish() turns the per-thread maximum into tan^2 (monotone, so it commutes with the max).
   const double dx = r.ux - D.cvec[0], dy = r.uy - D.cvec[1], dz = r.uz - D.cvec[2];
-  const double sx = r.ux + D.cvec[0], sy = r.uy + D.cvec[1], sz = r.uz + D.cvec[2];
-  h.tan2 = fdiv(fma(dx, dx, fma(dy, dy, dz * dz)), fma(sx, sx, fma(sy, sy, sz * sz)));
+  h.tan2 = fma(dx, dx, fma(dy, dy, dz * dz));
   return h;
 }
 
@@ -187,13 +188,21 @@ __device__ __forceinline__ void moments_add(ACC& m, const DetHit& h, double l0, 
   m[ART_M_SWYY] = fma(wy, h.y, m[ART_M_SWYY]);
   m[ART_M_SWD] += wd;
   m[ART_M_SWDD] = fma(wd, d, m[ART_M_SWDD]);
-  m[ART_M_XMIN] = fmin(m[ART_M_XMIN], h.x);
-  m[ART_M_XMAX] = fmax(m[ART_M_XMAX], h.x);
-  m[ART_M_YMIN] = fmin(m[ART_M_YMIN], h.y);
-  m[ART_M_YMAX] = fmax(m[ART_M_YMAX], h.y);
-  m[ART_M_DMIN] = fmin(m[ART_M_DMIN], d);
-  m[ART_M_DMAX] = fmax(m[ART_M_DMAX], d);
-  m[ART_M_TMAX] = fmax(m[ART_M_TMAX], h.tan2);
+  // compare + select (3 instructions); fmin / fmax expand to an 8-instruction NaN-quieting sequence
+#define ART_MIN(j, x) { const double o_ = m[j]; m[j] = (x) < o_ ? (x) : o_; }
+#define ART_MAX(j, x) { const double o_ = m[j]; m[j] = (x) > o_ ? (x) : o_; }
+  ART_MIN(ART_M_XMIN, h.x) ART_MAX(ART_M_XMAX, h.x)
+  ART_MIN(ART_M_YMIN, h.y) ART_MAX(ART_M_YMAX, h.y)
+  ART_MIN(ART_M_DMIN, d) ART_MAX(ART_M_DMAX, d)
+  ART_MAX(ART_M_TMAX, h.tan2)
+#undef ART_MIN
+#undef ART_MAX
+}
+// per-thread epilogue: the tracked max |u-c|^2 becomes max tan^2(angle/2)
+template <class ACC>
+__device__ __forceinline__ void moments_finish(ACC& m) {
+  const double n2 = m[ART_M_TMAX];
+  m[ART_M_TMAX] = n2 > 0.0 ? n2 / (4.0 - n2) : n2;  // -inf (no rays) stays
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -276,6 +285,24 @@ __device__ __forceinline__ void store_bundle(const BundleDev& O, long long at, b
   double v[N];
 #pragma unroll
   for (int q = 0; q < N; ++q) w[q] = r[q].alive;
+  if (N == 2 && vec && two && w[0] && w[N - 1]) {
+    // the common case -- both rays of an aligned pair survive: straight-line 128-bit stores
+#define ART_ST2(colp, field)                                                                   \
+  {                                                                                            \
+    double2* const dp = reinterpret_cast<double2*>(colp + at);                                 \
+    const double2 dv = make_double2(r[0].field, r[N - 1].field);                               \
+    if (keep) *dp = dv; else __stcs(dp, dv);                                                   \
+  }
+    if (O.px) {
+      ART_ST2(O.px, px) ART_ST2(O.py, py) ART_ST2(O.pz, pz)
+      ART_ST2(O.ux, ux) ART_ST2(O.uy, uy) ART_ST2(O.uz, uz)
+    }
+    if (O.path) ART_ST2(O.path, path)
+    if (want_inc && O.inc) ART_ST2(O.inc, inc)
+#undef ART_ST2
+    if (O.alive) *reinterpret_cast<uchar2*>(O.alive + at) = make_uchar2(1, 1);
+    return;
+  }
 #define ART_ST(colp, field)                         \
   {                                                 \
     _Pragma("unroll") for (int q = 0; q < N; ++q) v[q] = r[q].field; \
@@ -523,6 +550,7 @@ __global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a)
   }
   if constexpr (WITH_DET) {
     __syncthreads();  // sRed is reused
+    moments_finish(m);
     block_reduce_row<ART_MOMENTS_LEN>(m, [](int j) { return moment_op(j); }, sRed, prow + ART_CENTRAL_LEN);
   }
 #undef ART_ACC
@@ -579,18 +607,19 @@ __global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetAr
 
   if (vec) {
     double2* const sStage = reinterpret_cast<double2*>(smem_raw) + threadIdx.x;
-    // alive flags of pair p as bits (bit 0 / bit 1); pairs beyond the end -> 0
-    auto flags_of = [&](long long p) -> unsigned {
+    // alive flags of pair p: the RAW bytes (byte 0 / byte 1; pairs beyond the end -> 0) are fetched three
+    // pairs ahead and stay untouched in a register for a whole loop trip, decoded (bit 0 / bit 1) only at
+    // the top of the next one -- decoding at the load site made every trip wait for the load (37 % of
+    // the kernel's stall samples sat on that one instruction)
+    auto flags_raw = [&](long long p) -> unsigned {
       if (p >= npairs) return 0u;
       const long long i = p << 1;
       const bool two = i + 1 < n;
-      if (!a.b.alive) return two ? 3u : 1u;
-      if (two) {
-        const uchar2 f = *reinterpret_cast<const uchar2*>(a.b.alive + row + i);
-        return (f.x ? 1u : 0u) | (f.y ? 2u : 0u);
-      }
-      return a.b.alive[row + i] ? 1u : 0u;
+      if (!a.b.alive) return two ? 0x0101u : 0x01u;
+      if (two) return *reinterpret_cast<const unsigned short*>(a.b.alive + row + i);
+      return a.b.alive[row + i];
     };
+    auto decode = [](unsigned raw) -> unsigned { return ((raw & 0xffu) ? 1u : 0u) | ((raw & 0xff00u) ? 2u : 0u); };
     auto issue = [&](int stage, long long p) {  // only full pairs are staged
       const long long at = row + (p << 1);
       double2* bs = sStage + stage * STAGE_COLS * TPB;
@@ -601,16 +630,18 @@ __global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetAr
       cp_async_commit();
     };
     long long pair = (long long)blockIdx.x * TPB + threadIdx.x;
-    unsigned fl = flags_of(pair);
+    unsigned fl = decode(flags_raw(pair));
     bool staged = fl != 0 && ((pair << 1) + 1 < n);
     if (staged) issue(0, pair);
-    unsigned fl_next = flags_of(pair + stride);
+    unsigned fl_next = decode(flags_raw(pair + stride));
+    unsigned raw_next2 = flags_raw(pair + 2 * stride);
     int stage = 0;
     for (; pair < npairs; pair += stride, stage ^= 1) {
       const long long nxt = pair + stride;
       const bool staged_next = fl_next != 0 && nxt < npairs && ((nxt << 1) + 1 < n);
       if (staged_next) issue(stage ^ 1, nxt);
-      const unsigned fl_next2 = flags_of(nxt + stride);  // in flight during this pair's arithmetic
+      const unsigned fl_next2 = decode(raw_next2);       // loaded one trip ago
+      raw_next2 = flags_raw(nxt + 2 * stride);           // in flight during this and the next pair's arithmetic
       if (fl != 0) {
         const long long i = pair << 1;
         Ray r[RPT];
@@ -667,6 +698,7 @@ __global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetAr
       detector_pair(a, sDet, row + i, r, w, al, m);
     }
   }
+  moments_finish(m);
   block_reduce_row<PLEN_DET>(m, [](int j) { return moment_op(j); }, sRed,
                              a.partials + ((size_t)v * gridDim.x + blockIdx.x) * PLEN_DET);
 }
