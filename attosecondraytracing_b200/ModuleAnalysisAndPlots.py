@@ -1,5 +1,6 @@
-"""Result summaries of ART/ModuleAnalysisAndPlots.py (:62-129).  The plotting / rendering functions
-of that module (matplotlib, pyvista) are out of scope of this package."""
+"""Result summaries of ART/ModuleAnalysisAndPlots.py (:62-129) and the DATA of its SpotDiagram /
+DelayGraph figures as device-side histograms.  The matplotlib / pyvista drawing itself is out of scope
+of this package."""
 from __future__ import annotations
 
 import numpy as np
@@ -31,3 +32,27 @@ def GetResultSummary(Detector, RayListAnalysed, verbose=False):
               + "Spatial std : {:.3f} μm and min-max: {:.3f} μm\n".format(s["SpotSizeSD"] * 1e3, s["Diameter"] * 1e3)
               + "Temporal std : {:.3e} fs and min-max : {:.3e} fs".format(s["DurationSD"], s["delay_max_fs"] - s["delay_min_fs"]))
     return s["SpotSizeSD"], s["DurationSD"]
+
+
+def SpotDiagramData(RayListAnalysed, Detector, bins=(64, 64), ColorCoded=None):
+    """The content of SpotDiagram (ART/ModuleAnalysisAndPlots.py:133-250) as a 2-D histogram instead of one
+    scatter point per ray: returns (x_edges_um, y_edges_um, count, colour) with the axes in micrometres
+    centred on the bounding-box midpoint like the reference's figure; `colour` is the per-bin mean of the
+    quantity named by ColorCoded ("Intensity": arb. u., "Delay": fs) or None."""
+    if ColorCoded not in (None, "Intensity", "Delay"):
+        raise ValueError('ColorCoded must be None, "Intensity" or "Delay" (incidences are not binned)')
+    h = Detector.get_histograms(RayListAnalysed, bins=bins, delay_bins=1)
+    colour = None
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if ColorCoded == "Intensity":
+            colour = h["spot_intensity"] / h["spot_count"]
+        elif ColorCoded == "Delay":
+            colour = h["spot_delay"]
+    return h["x_edges"] * 1e3, h["y_edges"] * 1e3, h["spot_count"], colour
+
+
+def DelayGraphData(RayListAnalysed, Detector, delay_bins=128):
+    """Delay distribution of the bundle on the detector (the third axis of DelayGraph,
+    ART/ModuleAnalysisAndPlots.py:360-440): (delay_edges_fs, count, summed_intensity)."""
+    h = Detector.get_histograms(RayListAnalysed, bins=(1, 1), delay_bins=delay_bins)
+    return h["delay_edges"], h["delay_count"], h["delay_intensity"]

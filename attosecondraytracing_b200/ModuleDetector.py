@@ -166,6 +166,18 @@ class Detector:
         torch.cuda.current_stream().synchronize()
         return scan.cpu().numpy()[0]
 
+    def get_histograms(self, RayList, bins=(64, 64), delay_bins=128):
+        """Binned detector response (art_detector_histogram) as the dict of `engine.split_histogram`: what
+        SpotDiagram / DelayGraph (ART/ModuleAnalysisAndPlots.py:133, 360) scatter ray by ray, as
+        fixed-size arrays that do not grow with the ray count."""
+        from .engine import DeviceChain, split_histogram
+        r = self._evaluate(RayList)
+        b = r["bundle"]
+        hist = DeviceChain.histogram(_Scratchless(b.device), b, r["det"], r["moments"], bins=bins,
+                                     delay_bins=delay_bins)
+        torch.cuda.current_stream().synchronize()
+        return split_histogram(hist.cpu().numpy(), r["moments"].cpu().numpy()[0], bins=bins, delay_bins=delay_bins)
+
     def get_statistics(self, RayList, RayListIn=None):
         """All bundle statistics from ONE kernel pass (dict: SpotSizeSD mm, DurationSD fs, weighted
         variants, Diameter, NA, ...) without materialising per-ray lists."""

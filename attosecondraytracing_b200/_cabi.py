@@ -86,6 +86,14 @@ class ArtDetector(C.Structure):
 DETECTOR_DOUBLES = C.sizeof(ArtDetector) // 8  # 23
 
 
+HIST_FIXED_ONE = 67108864.0  # ART_HIST_FIXED_ONE
+
+
+def hist_len(nx, ny, nt):
+    """ART_HIST_LEN of the header."""
+    return 3 * nx * ny + 2 * nt
+
+
 class ArtError(RuntimeError):
     """A libart_b200 call returned a negative status."""
 
@@ -115,6 +123,8 @@ _SIGNATURES = {
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "art_detector_scan_moments": (C.c_int32, [C.c_void_p, C.POINTER(ArtBundleView), C.c_int32, C.c_void_p, C.c_void_p,
                                               C.c_void_p]),
+    "art_detector_histogram": (C.c_int32, [C.POINTER(ArtBundleView), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
     "art_moments_merge": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "art_sweep": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(ArtBundleView), C.c_uint32, C.c_double,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -502,6 +502,39 @@ extern "C" int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bu
   return ART_OK;
 }
 
+extern "C" int32_t art_detector_histogram(const ArtBundleView* bundle, const ArtDetector* det, const double* moments,
+                                          int32_t nx, int32_t ny, int32_t nt, double wscale, int64_t* hist_out,
+                                          void* stream) {
+  if (!bundle || !det || !moments || !hist_out) return fail(ART_E_INVALID, "NULL argument");
+  if (nx < 1 || ny < 1 || nt < 1 || (int64_t)nx * ny > (int64_t)1 << 26 || nt > 1 << 26)
+    return fail(ART_E_INVALID, "bin counts must be in [1, 2^26]");
+  if (!(wscale > 0.0)) return fail(ART_E_INVALID, "wscale must be positive");
+  if (const char* why = check_columns(bundle, true)) return fail(ART_E_INVALID, std::string("bundle: ") + why);
+  if (bundle->n < 0) return fail(ART_E_INVALID, "negative ray count");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t len = (size_t)3 * nx * ny + (size_t)2 * nt;
+  ART_CUDA(cudaMemsetAsync(hist_out, 0, len * sizeof(int64_t), st));
+  if (bundle->n == 0) return ART_OK;
+  HistArgs a;
+  a.b = to_dev(bundle);
+  a.n = bundle->n;
+  a.det = det;
+  a.moments = moments;
+  a.nx = nx;
+  a.ny = ny;
+  a.nt = nt;
+  a.wscale = wscale;
+  a.hist = reinterpret_cast<long long*>(hist_out);
+  int dev = 0, sms = 148;
+  ART_CUDA(cudaGetDevice(&dev));
+  ART_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long blocks = (bundle->n + 255) / 256;
+  if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+  histogram_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  ART_LAUNCHED();
+  return ART_OK;
+}
+
 extern "C" int32_t art_detector_scan_moments(ArtChain* chain, const ArtBundleView* bundle, int32_t n_variants,
                                              const ArtDetector* det, double* scan_out, void* stream) {
   if (!bundle || !det || !scan_out || n_variants < 1) return fail(ART_E_INVALID, "bad argument");

@@ -749,6 +749,100 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const DetArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Binned detector response: the data behind SpotDiagram / DelayGraph (ART/ModuleAnalysisAndPlots.py:133,
+// 360, which scatter every ray) as fixed-size histograms of the detector hits over the bounding box
+// and the delay range that the moments row holds.  Integer bins only -- counts, and fixed-point sums
+// (2^-26 steps) of the intensity and of the normalised delay -- so the result does not depend on the
+// order of the atomic adds and an all-reduce(SUM) of int64 over the ranks is exact.
+// Lanes of a warp that hit the same bin are combined first (match.any + redux), then ONE lane issues
+// the 64-bit RED atomics: a focused beam puts most rays into a handful of bins.
+// Layout of hist (ART_HIST_* of the header): [nx*ny] spot counts (ix*ny + iy), [nx*ny] spot sum of
+// intensity, [nx*ny] spot sum of (d - dmin)/(dmax - dmin), [nt] delay counts, [nt] delay sum of intensity.
+// ---------------------------------------------------------------------------------------------
+struct HistArgs {
+  BundleDev b;
+  long long n;
+  const ArtDetector* det;
+  const double* moments;  // one row: extents
+  int nx, ny, nt;
+  double wscale;          // intensities are binned as round(min(w / wscale, 1) * 2^26)
+  long long* hist;
+};
+constexpr double HIST_FIXED_ONE = 67108864.0;  // 2^26
+
+__device__ __forceinline__ int hist_bin(double v, double lo, double hi, int nbins) {
+  // numpy.histogram's uniform-bin rule: floor((v - lo) * nbins / (hi - lo)), the right edge in the last bin
+  const double span = hi - lo;
+  if (!(span > 0.0)) return 0;
+  int k = (int)floor((v - lo) * ((double)nbins / span));
+  return k < 0 ? 0 : (k >= nbins ? nbins - 1 : k);
+}
+
+__global__ void __launch_bounds__(256) histogram_kernel(const HistArgs a) {
+  __shared__ ArtDetector sDet;
+  __shared__ double sExt[6];
+  {
+    const double* ds = reinterpret_cast<const double*>(a.det);
+    double* dd = reinterpret_cast<double*>(&sDet);
+    for (int i = threadIdx.x; i < (int)(sizeof(ArtDetector) / sizeof(double)); i += blockDim.x) dd[i] = ds[i];
+    if (threadIdx.x < 6) sExt[threadIdx.x] = a.moments[ART_M_XMIN + threadIdx.x];
+  }
+  __syncthreads();
+  const double xmin = sExt[0], xmax = sExt[1], ymin = sExt[2], ymax = sExt[3], dmin = sExt[4], dmax = sExt[5];
+  const double dspan = dmax - dmin;
+  const double dinv = dspan > 0.0 ? HIST_FIXED_ONE / dspan : 0.0;
+  const double winv = HIST_FIXED_ONE / a.wscale;
+  const long long nxy = (long long)a.nx * a.ny;
+  long long* const h_cnt = a.hist;
+  long long* const h_w = a.hist + nxy;
+  long long* const h_d = a.hist + 2 * nxy;
+  long long* const t_cnt = a.hist + 3 * nxy;
+  long long* const t_w = t_cnt + a.nt;
+  const unsigned lane = threadIdx.x & 31u;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // warp-uniform trip count: every lane runs the same number of trips so the warp intrinsics line up
+  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < a.n; base += stride) {
+    const long long i = base + lane;
+    const bool valid = i < a.n && (!a.b.alive || a.b.alive[i] != 0);
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    if (!valid) continue;
+    Ray r;
+    r.px = a.b.px[i]; r.py = a.b.py[i]; r.pz = a.b.pz[i];
+    r.ux = a.b.ux[i]; r.uy = a.b.uy[i]; r.uz = a.b.uz[i];
+    r.path = a.b.path ? a.b.path[i] : 0.0;
+    const double w = a.b.inten ? a.b.inten[i] : 1.0;
+    const DetHit h = detector_ray(sDet, r);
+    const double d = h.L - sDet.l0;
+    const int ix = hist_bin(h.x, xmin, xmax, a.nx), iy = hist_bin(h.y, ymin, ymax, a.ny);
+    const int it = hist_bin(d, dmin, dmax, a.nt);
+    double wq_ = w * winv;
+    wq_ = wq_ < 0.0 ? 0.0 : (wq_ > HIST_FIXED_ONE ? HIST_FIXED_ONE : wq_);
+    const unsigned wq = (unsigned)__double2uint_rn(wq_);
+    double dq_ = (d - dmin) * dinv;
+    dq_ = dq_ < 0.0 ? 0.0 : (dq_ > HIST_FIXED_ONE ? HIST_FIXED_ONE : dq_);
+    const unsigned dq = (unsigned)__double2uint_rn(dq_);
+    {
+      const int bin = ix * a.ny + iy;
+      const unsigned g = __match_any_sync(vmask, bin);
+      const unsigned sw = __reduce_add_sync(g, wq), sd = __reduce_add_sync(g, dq);
+      if (lane == (unsigned)(__ffs(g) - 1)) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(h_cnt + bin), (unsigned long long)__popc(g));
+        atomicAdd(reinterpret_cast<unsigned long long*>(h_w + bin), (unsigned long long)sw);
+        atomicAdd(reinterpret_cast<unsigned long long*>(h_d + bin), (unsigned long long)sd);
+      }
+    }
+    {
+      const unsigned g = __match_any_sync(vmask, it);
+      const unsigned sw = __reduce_add_sync(g, wq);
+      if (lane == (unsigned)(__ffs(g) - 1)) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(t_cnt + it), (unsigned long long)__popc(g));
+        atomicAdd(reinterpret_cast<unsigned long long*>(t_w + it), (unsigned long long)sw);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // second reduction stage: one block per variant folds that variant's block rows in a fixed order.
 //   mode 0: row = central            -> central_out
 //   mode 1: row = central | moments  -> central_out (nullable), moments_out

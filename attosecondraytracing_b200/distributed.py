@@ -74,6 +74,14 @@ def all_reduce_moments(moments, group=None, gather_buffer=None):
     return moments
 
 
+def all_reduce_histogram(hist, group=None):
+    """Sum the int64 histograms of every rank's shard (exact: integer bins).  Every rank must have binned
+    against the same detector and the same merged moments row (`all_reduce_moments` first)."""
+    if is_distributed(group):
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist
+
+
 def merge_moments(rows):
     """Host-side merge of moments rows from several shards (sequence of (24,) arrays / tensors)."""
     rows = torch.stack([torch.as_tensor(r, dtype=torch.float64) for r in rows])

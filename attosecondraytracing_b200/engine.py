@@ -172,6 +172,28 @@ class DeviceChain:
                                                          _ptr(l), _ptr(mom), _stream()))
         return mom, x, y, l
 
+    def histogram(self, bundle, det, moments, bins=(64, 64), delay_bins=128, intensity=None, wscale=1.0, out=None):
+        """Binned detector response of a stored bundle (art_detector_histogram): an int64 tensor of
+        hist_len(nx, ny, nt) entries -- see `split_histogram`.  `moments`: the (merged) moments row whose
+        extents span the bins; every rank of a sharded bundle must pass the same row and detector, then the
+        tensors add exactly (all-reduce SUM)."""
+        self._check_bundle(bundle)
+        bundle = bundle.materialize()
+        nx, ny = int(bins[0]), int(bins[1])
+        nt = int(delay_bins)
+        hist = out if out is not None else torch.empty((_cabi.hist_len(nx, ny, nt),), dtype=torch.int64,
+                                                       device=self.device)
+        v = bundle.view()
+        if intensity is not None:
+            v.intensity = intensity.data_ptr()
+        elif not bundle.has("intensity"):
+            shared = getattr(bundle, "shared_intensity", None)
+            v.intensity = shared.data_ptr() if shared is not None else None
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().art_detector_histogram(C.byref(v), _ptr(det), _ptr(moments), nx, ny, nt,
+                                                           float(wscale), _ptr(hist), _stream()))
+        return hist
+
     def scan_moments(self, bundle, det):
         """The ART_SCAN_LEN sums per variant from which spot / duration SDs at any detector shift follow
         (FindOptimalDistance in closed form).  Returns an (n_variants, 32) tensor."""
@@ -299,6 +321,40 @@ def summary_from_moments(m, central=None):
         c = np.asarray(central, dtype=np.float64)
         out["ETransmission"] = float(100 * c[_cabi.C_SW_OUT] / c[_cabi.C_SW_IN])   # ModuleAnalysisAndPlots.py:62-77
     return out
+
+
+def split_histogram(hist, moments_row, bins=(64, 64), delay_bins=128, wscale=1.0):
+    """The int64 vector of `DeviceChain.histogram` (numpy, possibly summed over ranks) as the binned data
+    of the reference's SpotDiagram / DelayGraph (ART/ModuleAnalysisAndPlots.py:133, 360):
+      x_edges, y_edges  mm, centred on the bounding-box midpoint like get_PointList2DCentre
+      spot_count        (nx, ny) rays per bin;  spot_intensity: sum of intensities per bin;
+      spot_delay        mean delay (fs, relative to the mean path) of the rays of a bin, NaN where empty
+      delay_edges       fs;  delay_count, delay_intensity: (nt,)"""
+    nx, ny = int(bins[0]), int(bins[1])
+    nt = int(delay_bins)
+    h = np.asarray(hist, dtype=np.int64)
+    m = np.asarray(moments_row, dtype=np.float64)
+    nxy = nx * ny
+    one = _cabi.HIST_FIXED_ONE
+    cnt = h[:nxy].reshape(nx, ny)
+    wsum = h[nxy:2 * nxy].reshape(nx, ny) * (wscale / one)
+    dmin, dmax = m[_cabi.M_DMIN], m[_cabi.M_DMAX]
+    mean_d = m[_cabi.M_SD] / m[_cabi.M_N] if m[_cabi.M_N] > 0 else 0.0
+    to_fs = 1e15 / 299792458000.0  # LightSpeed in mm/s, ART/ModuleDetector.py:21
+    with np.errstate(invalid="ignore", divide="ignore"):
+        dmean = dmin + (dmax - dmin) * (h[2 * nxy:3 * nxy].reshape(nx, ny) / one) / cnt
+    xmid = 0.5 * (m[_cabi.M_XMIN] + m[_cabi.M_XMAX])
+    ymid = 0.5 * (m[_cabi.M_YMIN] + m[_cabi.M_YMAX])
+    return {
+        "x_edges": np.linspace(m[_cabi.M_XMIN], m[_cabi.M_XMAX], nx + 1) - xmid,
+        "y_edges": np.linspace(m[_cabi.M_YMIN], m[_cabi.M_YMAX], ny + 1) - ymid,
+        "spot_count": cnt,
+        "spot_intensity": wsum,
+        "spot_delay": (dmean - mean_d) * to_fs,
+        "delay_edges": (np.linspace(dmin, dmax, nt + 1) - mean_d) * to_fs,
+        "delay_count": h[3 * nxy:3 * nxy + nt].copy(),
+        "delay_intensity": h[3 * nxy + nt:3 * nxy + 2 * nt] * (wscale / one),
+    }
 
 
 def scan_statistics(scan, s, weighted=False):

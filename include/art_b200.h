@@ -271,6 +271,28 @@ int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bundle, int32
 int32_t art_detector_scan_moments(ArtChain* chain, const ArtBundleView* bundle, int32_t n_variants,
                                   const ArtDetector* det, double* scan_out, void* stream);
 
+/*
+ * Binned detector response -- the data behind SpotDiagram and DelayGraph
+ * (ART/ModuleAnalysisAndPlots.py:133-250, 360-440, which scatter-plot every ray of the list; with 1e7+ rays
+ * the plots are drawn from these bins instead).  One pass over the stored bundle (one chain variant):
+ * every alive ray is intersected with the detector as in art_detector_moments and binned
+ *   - by its in-plane point over the bounding box [XMIN,XMAX] x [YMIN,YMAX] of the moments row
+ *     (nx x ny uniform bins, numpy.histogram2d's rule: right edges belong to the last bin), and
+ *   - by its path-length deviation d = L - l0 over [DMIN,DMAX] (nt bins; delay in fs = (d - SD/N)/c*1e15).
+ * hist_out (device, ART_HIST_LEN(nx,ny,nt) int64, zeroed by the call), consecutive blocks:
+ *   [nx*ny] ray counts (index ix*ny + iy)       [nx*ny] sum of round(min(w/wscale,1) * 2^26)
+ *   [nx*ny] sum of round((d-DMIN)/(DMAX-DMIN) * 2^26)
+ *   [nt]    ray counts                            [nt]    sum of round(min(w/wscale,1) * 2^26)
+ * Integer accumulation: the result does not depend on the order of the atomic adds, and the histograms of
+ * the shards of a bundle add exactly (all-reduce SUM of int64) provided every rank passes the same detector
+ * and the same -- merged -- moments row.  moments: device, one row of ART_MOMENTS_LEN doubles.
+ */
+#define ART_HIST_FIXED_ONE 67108864.0 /* 2^26 */
+#define ART_HIST_LEN(nx, ny, nt) (3 * (int64_t)(nx) * (int64_t)(ny) + 2 * (int64_t)(nt))
+int32_t art_detector_histogram(const ArtBundleView* bundle, const ArtDetector* det, const double* moments,
+                               int32_t nx, int32_t ny, int32_t nt, double wscale, int64_t* hist_out,
+                               void* stream);
+
 /* Multi-GPU: merge the moments rows that an all-gather collected from every rank
  * (rows: device, n_ranks x n_variants x ART_MOMENTS_LEN) into out (n_variants x ART_MOMENTS_LEN):
  * sums added in rank order, extents by min / max.  The statistics of the sharded bundle then follow

@@ -630,6 +630,26 @@ def result_summary(det, P, U, path):
     return standard_deviation(xy), standard_deviation(detector_delays(det, P, U, path))
 
 
+def detector_histograms(det, P, U, path, intensity=None, bins=(64, 64), delay_bins=128):
+    """Binned SpotDiagram / DelayGraph data (ART/ModuleAnalysisAndPlots.py:133-250, 360-440 scatter
+    get_PointList2DCentre and get_Delays ray by ray; the reference itself has no histogram): numpy's
+    histogram2d / histogram of those very lists over their bounding box / range.  Returns the dict layout
+    of attosecondraytracing_b200.engine.split_histogram."""
+    xy = detector_points2d_centre(det, P, U)
+    dl = detector_delays(det, P, U, path)
+    w = np.ones(len(dl)) if intensity is None else np.asarray(intensity, dtype=np.float64)
+    rng = [[xy[:, 0].min(), xy[:, 0].max()], [xy[:, 1].min(), xy[:, 1].max()]]
+    cnt, xe, ye = np.histogram2d(xy[:, 0], xy[:, 1], bins=bins, range=rng)
+    wsum, _, _ = np.histogram2d(xy[:, 0], xy[:, 1], bins=bins, range=rng, weights=w)
+    dsum, _, _ = np.histogram2d(xy[:, 0], xy[:, 1], bins=bins, range=rng, weights=dl)
+    tc, te = np.histogram(dl, bins=delay_bins, range=(dl.min(), dl.max()))
+    tw, _ = np.histogram(dl, bins=delay_bins, range=(dl.min(), dl.max()), weights=w)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        dmean = dsum / cnt
+    return {"x_edges": xe, "y_edges": ye, "spot_count": cnt.astype(np.int64), "spot_intensity": wsum,
+            "spot_delay": dmean, "delay_edges": te, "delay_count": tc.astype(np.int64), "delay_intensity": tw}
+
+
 def find_optimal_distance(det, P, U, path, opt_for="intensity", amplitude=None, precision=3, weights=None):
     """FindOptimalDistance + _FindOptimalDistanceBIS, ART/ModuleProcessing.py:317-460, by brute force as
     the reference does it (every trial detector re-intersects every ray).  Returns

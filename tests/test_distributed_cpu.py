@@ -14,6 +14,9 @@ import art_oracle as orc
 from golden_util import Golden
 
 
+HIST_BINS, HIST_NT = (12, 10), 16
+
+
 def oracle_central(P, U, path, w_out, w_in_sum):
     return np.array([*U.sum(axis=0), *P.sum(axis=0), path.sum(), P.shape[0], w_out.sum(), w_in_sum])
 
@@ -34,6 +37,31 @@ def oracle_moments(det, l0, P, U, path, w):
     else:
         m[14:21] = [np.inf, -np.inf, np.inf, -np.inf, np.inf, -np.inf, -np.inf]
     return m
+
+
+def oracle_hist_vector(det, l0, m, P, U, path, w, bins, nt):
+    """One shard's int64 histogram in the layout of art_detector_histogram (include/art_b200.h), binned
+    with the kernel's rule floor((v - lo) * nbins / (hi - lo)) against the MERGED extents of row m."""
+    nx, ny = bins
+    xy = orc.detector_points2d(det, P, U)
+    d = orc.detector_optical_paths(det, P, U, path) - l0
+
+    def bin_of(v, lo, hi, nb):
+        k = np.floor((v - lo) * (nb / (hi - lo))).astype(np.int64) if hi > lo else np.zeros(len(v), np.int64)
+        return np.clip(k, 0, nb - 1)
+
+    one = 2.0 ** 26
+    ix, iy = bin_of(xy[:, 0], m[14], m[15], nx), bin_of(xy[:, 1], m[16], m[17], ny)
+    it = bin_of(d, m[18], m[19], nt)
+    wq = np.rint(np.clip(w, 0.0, 1.0) * one).astype(np.int64)
+    dq = np.rint(np.clip((d - m[18]) / (m[19] - m[18]), 0.0, 1.0) * one).astype(np.int64)
+    h = np.zeros(3 * nx * ny + 2 * nt, dtype=np.int64)
+    np.add.at(h, ix * ny + iy, 1)
+    np.add.at(h, nx * ny + ix * ny + iy, wq)
+    np.add.at(h, 2 * nx * ny + ix * ny + iy, dq)
+    np.add.at(h, 3 * nx * ny + it, 1)
+    np.add.at(h, 3 * nx * ny + nt + it, wq)
+    return h
 
 
 def _free_port():
@@ -71,8 +99,12 @@ def _worker(rank, world, port, name, q):
     mom = torch.from_numpy(oracle_moments(det, l0, last["P"], last["U"], last["path"], w)).reshape(1, -1)
     ad.all_reduce_moments(mom)
     s = summary_from_moments(mom.numpy()[0], c)
+    # binned detector response: every rank bins its shard against the merged extents, int64 SUM all-reduce
+    hist = torch.from_numpy(oracle_hist_vector(det, l0, mom.numpy()[0], last["P"], last["U"], last["path"], w,
+                                               HIST_BINS, HIST_NT))
+    ad.all_reduce_histogram(hist)
     if rank == 0:
-        q.put((s, det["centre"], det["normal"]))
+        q.put((s, det["centre"], det["normal"], hist.numpy(), mom.numpy()[0]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -86,7 +118,7 @@ def test_two_ranks_reproduce_the_reference_statistics(name):
     for p in procs:
         p.start()
     try:
-        s, centre, normal = q.get(timeout=180)
+        s, centre, normal, hist, mrow = q.get(timeout=180)
     finally:
         for p in procs:
             p.join(timeout=30)
@@ -103,6 +135,22 @@ def test_two_ranks_reproduce_the_reference_statistics(name):
     assert abs(s["DurationSD_w"] - g["DurationSD_w"]) <= 1e-5
     assert abs(s["Diameter"] - g["Diameter"]) <= 1e-9
     assert abs(s["NA"] - g["NA"]) <= 1e-11
+    # the all-reduced histogram is the histogram of the whole bundle (oracle, numpy.histogram2d)
+    from attosecondraytracing_b200.engine import split_histogram
+    h = split_histogram(hist, mrow, bins=HIST_BINS, delay_bins=HIST_NT)
+    last = g.out(g.n_elements - 1)
+    odet = {"centre": g["det_centre"], "normal": g["det_normal"], "refpoint": g["det_refpoint"]}
+    w = g["src_I"][np.searchsorted(g["src_num"], last["num"])]
+    o = orc.detector_histograms(odet, last["P"], last["U"], last["path"], intensity=w, bins=HIST_BINS,
+                                delay_bins=HIST_NT)
+    n = last["num"].size
+    assert h["spot_count"].sum() == n and h["delay_count"].sum() == n
+    assert np.abs(h["spot_count"] - o["spot_count"]).sum() <= 4
+    assert np.abs(h["delay_count"] - o["delay_count"]).sum() <= 4
+    assert np.allclose(h["x_edges"], o["x_edges"], rtol=0, atol=1e-9)
+    assert np.allclose(h["delay_edges"], o["delay_edges"], rtol=0, atol=1e-5)
+    same = h["spot_count"] == o["spot_count"]
+    assert np.allclose(h["spot_intensity"][same], o["spot_intensity"][same], rtol=0, atol=n * 2.0 ** -26)
 
 
 def test_shard_ranges_tile_the_bundle():

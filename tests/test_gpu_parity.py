@@ -422,3 +422,75 @@ def test_extended_source_on_device():
                                    device="cuda", first=5, stride=7)
         pd = part.to_numpy()
         assert np.array_equal(pd["number"], z[case + "_num"][5::7]) and np.array_equal(pd["P"], d["P"][5::7])
+
+
+@pytest.mark.parametrize("name", ["cfg3_2tor", "cfg1_par", "cfg2_tor2f"])
+def test_detector_histograms_match_oracle_and_add_over_shards(name):
+    """art_detector_histogram (binned SpotDiagram / DelayGraph data) against numpy's histograms of the
+    oracle's per-ray lists; integer bins, so the histograms of two shards add exactly to the whole."""
+    import ctypes as C
+    from attosecondraytracing_b200 import _cabi
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
+    eng = _engine()
+    g = Golden(name)
+    bins, nt = (16, 12), 20
+    chain = eng.DeviceChain(golden_optical_elements(g))
+    src = _source_bundle(g)
+    outs, central = chain.trace(src, ignore_defects=g.ignore_defects, history=False)
+    final = outs[0]
+    det0 = chain.autoplace(central, g.spec["detector_distance"])
+    l0 = eng.detector_from_row(det0.cpu().numpy()[0])["l0"]
+    dref = _cabi.ArtDetector()
+    _cabi.check(_cabi.lib().art_detector_make(_cabi.vec3(g["det_centre"]), _cabi.vec3(g["det_normal"]),
+                                              _cabi.vec3(g["det_refpoint"]), float(l0), C.byref(dref)))
+    det = torch.from_numpy(np.frombuffer(bytes(dref), dtype=np.float64).copy()).cuda().reshape(1, -1)
+    w_all = src.col("intensity")
+    mom, _, _, _ = chain.moments(final, det, intensity=w_all)
+    hist = chain.histogram(final, det, mom, bins=bins, delay_bins=nt, intensity=w_all)
+    torch.cuda.synchronize()
+    m = mom.cpu().numpy()[0]
+    h = eng.split_histogram(hist.cpu().numpy(), m, bins=bins, delay_bins=nt)
+    last = g.out(g.n_elements - 1)
+    odet = {"centre": g["det_centre"], "normal": g["det_normal"], "refpoint": g["det_refpoint"]}
+    w = g["src_I"][np.searchsorted(g["src_num"], last["num"])]
+    o = orc.detector_histograms(odet, last["P"], last["U"], last["path"], intensity=w, bins=bins, delay_bins=nt)
+    n = last["num"].size
+    assert h["spot_count"].sum() == n and h["delay_count"].sum() == n
+    # a ray within rounding distance of a bin edge may fall on either side: at most two such rays
+    assert np.abs(h["spot_count"] - o["spot_count"]).sum() <= 4
+    assert np.abs(h["delay_count"] - o["delay_count"]).sum() <= 4
+    assert np.allclose(h["x_edges"], o["x_edges"], rtol=0, atol=1e-9)
+    assert np.allclose(h["y_edges"], o["y_edges"], rtol=0, atol=1e-9)
+    assert np.allclose(h["delay_edges"], o["delay_edges"], rtol=0, atol=1e-5)
+    same = h["spot_count"] == o["spot_count"]
+    q = 2.0 ** -26  # fixed-point step of the binned sums
+    assert np.allclose(h["spot_intensity"][same], o["spot_intensity"][same], rtol=0, atol=n * q)
+    span_fs = h["delay_edges"][-1] - h["delay_edges"][0]
+    filled = same & (o["spot_count"] > 0)
+    assert np.allclose(h["spot_delay"][filled], o["spot_delay"][filled], rtol=0, atol=span_fs * q + 1e-5)
+    tsame = h["delay_count"] == o["delay_count"]
+    assert np.allclose(h["delay_intensity"][tsame], o["delay_intensity"][tsame], rtol=0, atol=n * q)
+    # the same call twice gives the same integers (no dependence on the order of the atomics)
+    hist2 = chain.histogram(final, det, mom, bins=bins, delay_bins=nt, intensity=w_all)
+    assert torch.equal(hist, hist2)
+    # shards: even / odd source rays traced separately, binned against the SAME detector and the merged
+    # moments row, add up to the histogram of the whole bundle exactly
+    total = torch.zeros_like(hist)
+    for r in (0, 1):
+        sel = np.arange(r, g["src_P"].shape[0], 2)
+        part = RayBundle.from_numpy(g["src_P"][sel], g["src_U"][sel], intensity=g["src_I"][sel],
+                                    number=g["src_num"][sel], device="cuda")
+        pouts, _ = chain.trace(part, ignore_defects=g.ignore_defects, history=False)
+        total += chain.histogram(pouts[0], det, mom, bins=bins, delay_bins=nt, intensity=part.col("intensity"))
+    torch.cuda.synchronize()
+    assert torch.equal(total, hist)
+    # public API: Detector.get_histograms / SpotDiagramData / DelayGraphData
+    from attosecondraytracing_b200 import ModuleAnalysisAndPlots as mplots
+    from attosecondraytracing_b200.ModuleDetector import Detector
+    D = Detector(g["det_refpoint"], g["det_centre"], g["det_normal"])
+    xe, ye, cnt, col = mplots.SpotDiagramData(final, D, bins=bins, ColorCoded="Delay")
+    assert cnt.sum() == n and cnt.shape == bins and col.shape == bins
+    assert np.allclose(xe, o["x_edges"] * 1e3, rtol=0, atol=1e-6)
+    te, tc, tw = mplots.DelayGraphData(final, D, delay_bins=nt)
+    assert tc.sum() == n and np.abs(tc - o["delay_count"]).sum() <= 4
+    chain.close()
