@@ -528,9 +528,22 @@ extern "C" int32_t art_detector_histogram(const ArtBundleView* bundle, const Art
   int dev = 0, sms = 148;
   ART_CUDA(cudaGetDevice(&dev));
   ART_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  long long blocks = (bundle->n + 255) / 256;
-  if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
-  histogram_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  const size_t smem = hist_smem_bytes(nx, ny, nt);
+  if (smem <= (size_t)100 * 1024) {
+    // block-private bins in shared memory, two blocks per SM; enough blocks that none sees more than
+    // HIST_MAX_RAYS_PER_BLOCK rays (32-bit partial sums)
+    if (cudaError_t e = allow_smem(histogram_smem_kernel, smem + 1024)) return fail(ART_E_CUDA, cudaGetErrorString(e));
+    long long blocks = (long long)sms * 2;
+    const long long need = (bundle->n + HIST_MAX_RAYS_PER_BLOCK - 1) / HIST_MAX_RAYS_PER_BLOCK;
+    if (blocks < need) blocks = need;
+    const long long most = (bundle->n + 511) / 512;
+    if (blocks > most) blocks = most;
+    histogram_smem_kernel<<<(unsigned)blocks, 512, smem, st>>>(a);
+  } else {
+    long long blocks = (bundle->n + 255) / 256;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    histogram_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  }
   ART_LAUNCHED();
   return ART_OK;
 }

@@ -842,6 +842,89 @@ __global__ void __launch_bounds__(256) histogram_kernel(const HistArgs a) {
   }
 }
 
+// The same histogram with block-private bins in shared memory (the default whenever they fit): 32-bit
+// shared-memory atomics per ray -- counts, and the 26-bit fixed-point values split into two 13-bit
+// halves so that a block's partial sums stay below 2^32 for up to 2^19 rays per block -- and one flush of
+// the non-empty bins to the global int64 histogram.  Integer arithmetic throughout: bit-identical to
+// histogram_kernel.
+constexpr int HIST_MAX_RAYS_PER_BLOCK = 1 << 19;
+__host__ __device__ inline size_t hist_smem_bytes(int nx, int ny, int nt) {
+  return ((size_t)5 * nx * ny + (size_t)3 * nt) * sizeof(unsigned);
+}
+__global__ void __launch_bounds__(512, 2) histogram_smem_kernel(const HistArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ ArtDetector sDet;
+  __shared__ double sExt[6];
+  unsigned* const bins = reinterpret_cast<unsigned*>(smem_raw);
+  const int nxy = a.nx * a.ny;
+  const int nbins = 5 * nxy + 3 * a.nt;
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) bins[i] = 0u;
+  {
+    const double* ds = reinterpret_cast<const double*>(a.det);
+    double* dd = reinterpret_cast<double*>(&sDet);
+    for (int i = threadIdx.x; i < (int)(sizeof(ArtDetector) / sizeof(double)); i += blockDim.x) dd[i] = ds[i];
+    if (threadIdx.x < 6) sExt[threadIdx.x] = a.moments[ART_M_XMIN + threadIdx.x];
+  }
+  __syncthreads();
+  const double xmin = sExt[0], xmax = sExt[1], ymin = sExt[2], ymax = sExt[3], dmin = sExt[4], dmax = sExt[5];
+  const double dspan = dmax - dmin;
+  const double dinv = dspan > 0.0 ? HIST_FIXED_ONE / dspan : 0.0;
+  const double winv = HIST_FIXED_ONE / a.wscale;
+  unsigned* const s_cnt = bins;
+  unsigned* const s_wh = bins + nxy;
+  unsigned* const s_wl = bins + 2 * nxy;
+  unsigned* const s_dh = bins + 3 * nxy;
+  unsigned* const s_dl = bins + 4 * nxy;
+  unsigned* const s_tc = bins + 5 * nxy;
+  unsigned* const s_twh = s_tc + a.nt;
+  unsigned* const s_twl = s_twh + a.nt;
+  // contiguous slice of rays per block (at most HIST_MAX_RAYS_PER_BLOCK by the launch's grid size)
+  const long long per = (a.n + gridDim.x - 1) / gridDim.x;
+  const long long lo = (long long)blockIdx.x * per;
+  const long long hi = lo + per < a.n ? lo + per : a.n;
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    if (a.b.alive && a.b.alive[i] == 0) continue;
+    Ray r;
+    r.px = a.b.px[i]; r.py = a.b.py[i]; r.pz = a.b.pz[i];
+    r.ux = a.b.ux[i]; r.uy = a.b.uy[i]; r.uz = a.b.uz[i];
+    r.path = a.b.path ? a.b.path[i] : 0.0;
+    const double w = a.b.inten ? a.b.inten[i] : 1.0;
+    const DetHit h = detector_ray(sDet, r);
+    const double d = h.L - sDet.l0;
+    const int bin = hist_bin(h.x, xmin, xmax, a.nx) * a.ny + hist_bin(h.y, ymin, ymax, a.ny);
+    const int it = hist_bin(d, dmin, dmax, a.nt);
+    double wq_ = w * winv;
+    wq_ = wq_ < 0.0 ? 0.0 : (wq_ > HIST_FIXED_ONE ? HIST_FIXED_ONE : wq_);
+    const unsigned wq = (unsigned)__double2uint_rn(wq_);
+    double dq_ = (d - dmin) * dinv;
+    dq_ = dq_ < 0.0 ? 0.0 : (dq_ > HIST_FIXED_ONE ? HIST_FIXED_ONE : dq_);
+    const unsigned dq = (unsigned)__double2uint_rn(dq_);
+    atomicAdd(s_cnt + bin, 1u);
+    atomicAdd(s_wh + bin, wq >> 13);
+    atomicAdd(s_wl + bin, wq & 8191u);
+    atomicAdd(s_dh + bin, dq >> 13);
+    atomicAdd(s_dl + bin, dq & 8191u);
+    atomicAdd(s_tc + it, 1u);
+    atomicAdd(s_twh + it, wq >> 13);
+    atomicAdd(s_twl + it, wq & 8191u);
+  }
+  __syncthreads();
+  unsigned long long* const g = reinterpret_cast<unsigned long long*>(a.hist);
+  for (int b = threadIdx.x; b < nxy; b += blockDim.x) {
+    const unsigned c = s_cnt[b];
+    if (c == 0u) continue;
+    atomicAdd(g + b, (unsigned long long)c);
+    atomicAdd(g + nxy + b, ((unsigned long long)s_wh[b] << 13) + s_wl[b]);
+    atomicAdd(g + 2 * (long long)nxy + b, ((unsigned long long)s_dh[b] << 13) + s_dl[b]);
+  }
+  for (int b = threadIdx.x; b < a.nt; b += blockDim.x) {
+    const unsigned c = s_tc[b];
+    if (c == 0u) continue;
+    atomicAdd(g + 3 * (long long)nxy + b, (unsigned long long)c);
+    atomicAdd(g + 3 * (long long)nxy + a.nt + b, ((unsigned long long)s_twh[b] << 13) + s_twl[b]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // second reduction stage: one block per variant folds that variant's block rows in a fixed order.
 //   mode 0: row = central            -> central_out

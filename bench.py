@@ -264,6 +264,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph-nccl", action="store_true", help="multi-GPU: capture the NCCL collectives in the graph too")
+    ap.add_argument("--histograms", action="store_true",
+                    help="also bin the detector response (64x64 spot + 128 delay bins) and all-reduce the int64 bins")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of as a CUDA graph")
     args = ap.parse_args()
 
@@ -353,6 +355,7 @@ def run_b200(args, w, oes):
         mom_b = torch.empty((1, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev)
         inten = src.col("intensity")
         gather_b = torch.empty((world, 1, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev)
+        hist_b = torch.empty((_cabi.hist_len(64, 64, 128),), dtype=torch.int64, device=dev) if args.histograms else None
 
         def step():
             chain.trace(src, ignore_defects=True, history=False, want_incidence=True, out=out, central=central_b)
@@ -360,6 +363,9 @@ def run_b200(args, w, oes):
             chain.autoplace(central_b, distance, det=det_b)
             chain.moments(out, det_b, intensity=inten, out=mom_b)
             ad.all_reduce_moments(mom_b, gather_buffer=gather_b)
+            if hist_b is not None:  # SpotDiagram / DelayGraph bins over the merged extents, exact int64 SUM
+                chain.histogram(out, det_b, mom_b, bins=(64, 64), delay_bins=128, intensity=inten, out=hist_b)
+                ad.all_reduce_histogram(hist_b)
             return out, central_b, det_b, mom_b
 
         e, sv = chain.count_entering(src)
@@ -523,6 +529,8 @@ def run_b200(args, w, oes):
                               "frac": None if fl is None else flops_kernel / (k_ms * 1e-3) / fl}})
         s = engine.summary_from_moments(mom.cpu().numpy()[0], central.cpu().numpy()[0])
         cfg = workload_config(w, args, n)
+        if args.histograms and not sweep:
+            cfg["histograms"] = "64x64 spot + 128 delay bins per step, int64 all-reduce"
         if sweep:
             cfg.update({"variants_per_gpu": nv_rank, "sweep": f"{sweep['axis']} of element {sweep['element']} over "
                         f"[{sweep['lo']}, {sweep['hi']}] deg", "l2": "source bundle (56 MB) re-read per variant from L2 "

@@ -424,16 +424,19 @@ def test_extended_source_on_device():
         assert np.array_equal(pd["number"], z[case + "_num"][5::7]) and np.array_equal(pd["P"], d["P"][5::7])
 
 
+@pytest.mark.parametrize("shape", [((16, 12), 20), ((100, 90), 300)], ids=["smem_bins", "global_bins"])
 @pytest.mark.parametrize("name", ["cfg3_2tor", "cfg1_par", "cfg2_tor2f"])
-def test_detector_histograms_match_oracle_and_add_over_shards(name):
+def test_detector_histograms_match_oracle_and_add_over_shards(name, shape):
     """art_detector_histogram (binned SpotDiagram / DelayGraph data) against numpy's histograms of the
-    oracle's per-ray lists; integer bins, so the histograms of two shards add exactly to the whole."""
+    oracle's per-ray lists; integer bins, so the histograms of two shards add exactly to the whole.
+    Small bin counts take the kernel with block-private shared-memory bins, large ones the kernel with
+    warp-aggregated global atomics."""
     import ctypes as C
     from attosecondraytracing_b200 import _cabi
     from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
     eng = _engine()
     g = Golden(name)
-    bins, nt = (16, 12), 20
+    bins, nt = shape
     chain = eng.DeviceChain(golden_optical_elements(g))
     src = _source_bundle(g)
     outs, central = chain.trace(src, ignore_defects=g.ignore_defects, history=False)
