@@ -276,7 +276,7 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
     ART_ALLOW(false, SURFS_TOROID)
     ART_ALLOW(false, SURFS_QUADRIC)
 #undef ART_ALLOW
-    CK(allow_smem(detector_kernel, STAGE_BYTES));
+    CK(allow_smem(detector_kernel, DET_STAGE_BYTES));
   }
   {
     bool tor = false, quad = false;
@@ -469,7 +469,7 @@ extern "C" int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bu
   ArtChain tmp;  // launch-shape defaults when no chain lends its scratch
   if (!chain) {
     // no chain has opted this device in to the kernel's shared-memory size yet
-    ART_CUDA(cudaFuncSetAttribute(detector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
+    ART_CUDA(cudaFuncSetAttribute(detector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DET_STAGE_BYTES));
     int dev = 0;
     ART_CUDA(cudaGetDevice(&dev));
     int sms = 148;
@@ -495,7 +495,7 @@ extern "C" int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bu
   if ((size_t)bpv * n_variants > chain->partial_rows)
     return fail(ART_E_INVALID, "n_variants exceeds the chain's variant count");
   cudaStream_t st = (cudaStream_t)stream;
-  detector_kernel<<<dim3(bpv, n_variants), TPB, STAGE_BYTES, st>>>(a);
+  detector_kernel<<<dim3(bpv, n_variants), TPB, DET_STAGE_BYTES, st>>>(a);
   ART_LAUNCHED();
   fold_kernel<<<n_variants, TPB, 0, st>>>(chain->d_partials, bpv, 2, nullptr, moments_out);
   ART_LAUNCHED();

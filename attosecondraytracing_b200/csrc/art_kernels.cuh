@@ -570,6 +570,11 @@ struct DetArgs {
 #ifndef ART_DET_MINB
 #define ART_DET_MINB 2
 #endif
+#ifndef ART_DET_NSTAGE
+#define ART_DET_NSTAGE 3
+#endif
+constexpr int DET_NSTAGE = ART_DET_NSTAGE;
+constexpr int DET_STAGE_BYTES = DET_NSTAGE * STAGE_COLS * TPB * 16;
 __device__ __forceinline__ void detector_pair(const DetArgs& a, const ArtDetector& D, long long at, const Ray (&r)[RPT],
                                               const double (&w)[RPT], const bool (&al)[RPT],
                                               double (&m)[ART_MOMENTS_LEN]) {
@@ -588,7 +593,7 @@ __device__ __forceinline__ void detector_pair(const DetArgs& a, const ArtDetecto
 // shared-memory slots with cp.async while the current pair is evaluated, and the alive flags are
 // fetched two pairs ahead so that the columns of dead pairs are never requested.
 __global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];  // STAGE_BYTES of cp.async slots
+  extern __shared__ __align__(16) unsigned char smem_raw[];  // DET_STAGE_BYTES of cp.async slots
   __shared__ double sRed[NWARP * PLEN_DET];
   __shared__ ArtDetector sDet;
   const int v = blockIdx.y;
@@ -629,27 +634,33 @@ __global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetAr
       if (a.b.inten) cp_async16(bs + 7 * TPB, a.b.inten + (p << 1));
       cp_async_commit();
     };
+    // DET_NSTAGE-deep pipeline: while pair j is evaluated the column slices of pairs j+1 and j+2 are in
+    // flight (one commit group per loop trip, empty for dead / ragged pairs, so wait_group<DET_NSTAGE-1>
+    // always means "the oldest stage has landed")
     long long pair = (long long)blockIdx.x * TPB + threadIdx.x;
     unsigned fl = decode(flags_raw(pair));
-    bool staged = fl != 0 && ((pair << 1) + 1 < n);
-    if (staged) issue(0, pair);
-    unsigned fl_next = decode(flags_raw(pair + stride));
-    unsigned raw_next2 = flags_raw(pair + 2 * stride);
+    unsigned fl1 = decode(flags_raw(pair + stride));
+    unsigned fl2 = decode(flags_raw(pair + 2 * stride));
+    unsigned raw3 = flags_raw(pair + 3 * stride);
+    auto full = [&](unsigned f, long long p) { return f != 0 && p < npairs && ((p << 1) + 1 < n); };
+    if (full(fl, pair)) issue(0, pair);
+    else cp_async_commit();
+    if (full(fl1, pair + stride)) issue(1, pair + stride);
+    else cp_async_commit();
     int stage = 0;
-    for (; pair < npairs; pair += stride, stage ^= 1) {
-      const long long nxt = pair + stride;
-      const bool staged_next = fl_next != 0 && nxt < npairs && ((nxt << 1) + 1 < n);
-      if (staged_next) issue(stage ^ 1, nxt);
-      const unsigned fl_next2 = decode(raw_next2);       // loaded one trip ago
-      raw_next2 = flags_raw(nxt + 2 * stride);           // in flight during this and the next pair's arithmetic
+    for (; pair < npairs; pair += stride, stage = stage == DET_NSTAGE - 1 ? 0 : stage + 1) {
+      const long long p2 = pair + 2 * stride;
+      if (full(fl2, p2)) issue(stage >= 1 ? stage - 1 : DET_NSTAGE - 1, p2);  // (stage + 2) % 3
+      else cp_async_commit();
+      const unsigned fl3 = decode(raw3);            // loaded one trip ago
+      raw3 = flags_raw(pair + 4 * stride);          // in flight during this and the next pair's arithmetic
       if (fl != 0) {
         const long long i = pair << 1;
         Ray r[RPT];
         double w[RPT];
         const bool al[RPT] = {(fl & 1u) != 0, (fl & 2u) != 0};
-        if (staged) {
-          if (staged_next) cp_async_wait<1>();
-          else cp_async_wait<0>();
+        if (full(fl, pair)) {
+          cp_async_wait<DET_NSTAGE - 1>();
           const double2* bs = sStage + stage * STAGE_COLS * TPB;
           double2 t;
           t = bs[0 * TPB]; r[0].px = t.x; r[1].px = t.y;
@@ -670,10 +681,11 @@ __global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetAr
         }
         detector_pair(a, sDet, row + i, r, w, al, m);
       }
-      fl = fl_next;
-      fl_next = fl_next2;
-      staged = staged_next;
+      fl = fl1;
+      fl1 = fl2;
+      fl2 = fl3;
     }
+    cp_async_wait<0>();
   } else {
     // odd row offset (odd n, odd variant): 8-byte accesses
     for (long long pair = (long long)blockIdx.x * TPB + threadIdx.x; pair < npairs; pair += stride) {
