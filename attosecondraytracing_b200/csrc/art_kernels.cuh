@@ -225,6 +225,12 @@ __device__ __forceinline__ void moments_finish(ACC& m) {
 #ifndef ART_MINB
 #define ART_MINB 2
 #endif
+#ifndef ART_MINB_DEF
+#define ART_MINB_DEF 2  // blocks per SM of the one-lane kernels of chains with defects
+#endif
+#ifndef ART_PACK_DEF
+#define ART_PACK_DEF 1  // lock-step pair also in chains with defects (fits the 168 registers of 192-thread blocks)
+#endif
 #ifndef ART_SMEM_ACC
 #define ART_SMEM_ACC 1
 #endif
@@ -326,11 +332,11 @@ __device__ __forceinline__ void store_bundle(const BundleDev& O, long long at, b
 }
 
 template <bool WANT_INC, bool WITH_DET, bool HAS_DEF, int SURFS, bool UPT>
-__global__ void __launch_bounds__(TPB, ART_MINB) trace_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(TPB, HAS_DEF ? ART_MINB_DEF : ART_MINB) trace_kernel(const TraceArgs a) {
   constexpr int N = ART_RPT;
-  // two rays in lock-step (lane pack D2) unless the chain carries Zernike defects, whose evaluation
-  // would not fit two lanes in the register file
-  constexpr bool PACK = (N == 2) && !HAS_DEF;
+  // two rays in lock-step (lane pack D2).  With 256-thread blocks (128 registers) the Zernike evaluation did
+  // not fit two lanes; with 192-thread blocks it does (cfg4 trace 0.177 -> 0.150 ms per 2e6 rays)
+  constexpr bool PACK = (N == 2) && (!HAS_DEF || ART_PACK_DEF != 0);
   // cp.async input staging: plain trace only (the fused-detector kernels spend their shared memory on
   // the moment slots and read an L2-resident source bundle)
   // (with 256-thread blocks / 128 registers the staging loop's extra live state made the incidence
