@@ -88,12 +88,13 @@ ART_HD double frsqrt(double x) {
 }
 ART_HD double fsqrt(double x) {
 #ifdef __CUDA_ARCH__
+  // x + 1e-300 is x itself for every x >= 1e-284 and keeps the seed finite at x = 0 (0 * rsqrt(0) would be
+  // NaN); an addition instead of a compare and two selects.  Negative x -> NaN, as sqrt().
   double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x + 1e-300));
   y = y * fma(-0.5 * x * y, y, 1.5);
-  double s = x * y;
-  s = fma(fma(-s, s, x), 0.5 * y, s);
-  return x == 0.0 ? 0.0 : s;
+  const double s = x * y;
+  return fma(fma(-s, s, x), 0.5 * y, s);
 #else
   return sqrt(x);
 #endif

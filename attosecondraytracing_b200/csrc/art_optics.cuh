@@ -171,31 +171,34 @@ ART_HD void solve_quadratic(T a, T b, T c, T& t1, T& t2) {
   const T e = mfma(-4.0 * a, c, w);  // rounding error of w
   const T f = mfma(b, b, -w);
   const T disc = f + e;
-  const typename MaskOf<T>::type ok = disc >= 0.0;
-  const T q = -0.5 * (b + mcopysign(fsqrt(sel(ok, disc, 0.0)), b));
-  t1 = sel(ok, fdiv(q, a), ART_NAN);
-  t2 = sel(ok, fdiv(c, q), ART_NAN);
+  // disc < 0: the square root is NaN and so are q, t1 and t2 -- no masks needed
+  const T q = -0.5 * (b + mcopysign(fsqrt(disc), b));
+  t1 = fdiv(q, a);
+  t2 = fdiv(c, q);
 }
 
 // Candidate rule shared by the curved mirrors: t > 1e-12 (KeepPositiveSolution,
 // ModuleGeometry.py:110-120), surface-side test, support test; one candidate -> it, two -> the
 // nearer one (_IntersectionRayMirror ART/ModuleMirror.py:27-38, ClosestPoint ModuleGeometry.py:138-147).
+// A root that is not positive for either lane (the far root of a ray that starts inside a sphere, ...)
+// skips its hit-point evaluation altogether.
 template <bool SIDE_Z_NEG, class T>
 ART_HD T pick_candidate(const ElemDev& E, const RayT<T>& r, T t1, T t2, double zlim) {
   typedef typename MaskOf<T>::type M;
   M c1 = t1 > 1e-12, c2 = t2 > 1e-12;
-  {
+  if (any(c1)) {
     const T x = mfma(t1, r.ux, r.px), y = mfma(t1, r.uy, r.py), z = mfma(t1, r.uz, r.pz);
     if (SIDE_Z_NEG) c1 = mand(c1, z < zlim);
     c1 = mand(c1, in_support(E, x, y));
   }
-  {
+  if (any(c2)) {
     const T x = mfma(t2, r.ux, r.px), y = mfma(t2, r.uy, r.py), z = mfma(t2, r.uz, r.pz);
     if (SIDE_Z_NEG) c2 = mand(c2, z < zlim);
     c2 = mand(c2, in_support(E, x, y));
   }
-  const T nearer = sel(t1 < t2, t1, t2);
-  return sel(mand(c1, c2), nearer, sel(c1, t1, sel(c2, t2, ART_NAN)));
+  // t2 wins when it is a candidate and either t1 is none or t2 is nearer
+  const M use2 = mand(c2, mor(mnot(c1), t2 < t1));
+  return sel(use2, t2, sel(c1, t1, ART_NAN));
 }
 
 // ---------------------------------------------------------------------------------------------
