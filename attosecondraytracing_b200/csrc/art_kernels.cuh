@@ -862,10 +862,11 @@ __global__ void __launch_bounds__(256) histogram_kernel(const HistArgs a) {
 
 // The same histogram with block-private bins in shared memory (the default whenever they fit): 32-bit
 // shared-memory atomics per ray -- counts, and the 26-bit fixed-point values split into two 13-bit
-// halves so that a block's partial sums stay below 2^32 for up to 2^19 rays per block -- and one flush of
+// halves (the upper one at most 2^13) so that a block's partial sums stay below 2^32 for up to 2^18 rays per
+// block -- and one flush of
 // the non-empty bins to the global int64 histogram.  Integer arithmetic throughout: bit-identical to
 // histogram_kernel.
-constexpr int HIST_MAX_RAYS_PER_BLOCK = 1 << 19;
+constexpr int HIST_MAX_RAYS_PER_BLOCK = 1 << 18;
 __host__ __device__ inline size_t hist_smem_bytes(int nx, int ny, int nt) {
   return ((size_t)5 * nx * ny + (size_t)3 * nt) * sizeof(unsigned);
 }

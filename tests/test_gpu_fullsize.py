@@ -122,6 +122,24 @@ def test_permutation_sharding_and_chaining_invariance_10M():
     m = mom[0].cpu().numpy()
     assert np.allclose(merged[:14], m[:14], rtol=1e-11, atol=1e-9)
     assert np.array_equal(merged[14:21], m[14:21])
+    # (b') binned detector response at full size: every survivor lands in exactly one bin, the binned
+    # intensity adds up to the summed intensity of the survivors, and the histograms of the two shards
+    # (binned against the extents of the WHOLE bundle) add to the histogram of the whole bundle exactly
+    n_surv = int(full.alive.sum())
+    for bins, nt in (((64, 64), 128), ((300, 200), 4096)):  # shared-memory bins / global atomics
+        hist = chain.histogram(full, det, mom, bins=bins, delay_bins=nt, intensity=src.col("intensity"))
+        h = eng.split_histogram(hist.cpu().numpy(), m, bins=bins, delay_bins=nt)
+        assert h["spot_count"].sum() == n_surv and h["delay_count"].sum() == n_surv
+        w_out = float(src.col("intensity")[full.alive.bool()].sum())
+        assert abs(h["spot_intensity"].sum() - w_out) <= n_surv * 2.0 ** -27
+        assert abs(h["delay_intensity"].sum() - w_out) <= n_surv * 2.0 ** -27
+        total = torch.zeros_like(hist)
+        for r in range(2):
+            first, count = ad.shard_range(n, r, 2)
+            part = _gather(src, torch.arange(first, first + count, device="cuda"), RayBundle)
+            po, _ = chain.trace(part, history=False)
+            total += chain.histogram(po[0], det, mom, bins=bins, delay_bins=nt, intensity=part.col("intensity"))
+        assert torch.equal(total, hist)
     # (c) chaining: element 0, then elements 1..2 starting from the stored bundle (path + alive carried)
     first_el = eng.DeviceChain(oes[:1])
     rest = eng.DeviceChain(oes[1:])

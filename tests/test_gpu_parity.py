@@ -155,6 +155,20 @@ def test_edge_cases_empty_ragged_and_all_blocked():
     mom, _, _, _ = chain.moments(outs[0], det)
     s = eng.summary_from_moments(mom.cpu().numpy()[0])
     assert s["n_rays"] == 0 and np.isnan(s["SpotSizeSD"])
+    # histograms of nothing are all zero (both kernels); one ray (degenerate extents) lands in bin 0
+    for bins, nt in (((8, 8), 16), ((200, 200), 64)):
+        hist = chain.histogram(outs[0], det, mom, bins=bins, delay_bins=nt)
+        assert int(hist.abs().sum()) == 0
+        empty = chain.histogram(RayBundle.from_numpy(P[:0], U[:0], device="cuda"), det, mom, bins=bins, delay_bins=nt)
+        assert int(empty.abs().sum()) == 0
+        one, c1 = chain.trace(RayBundle.from_numpy(P[:1], U[:1], device="cuda"), history=False)
+        d1 = chain.autoplace(c1, 100.0)
+        m1, _, _, _ = chain.moments(one[0], d1)
+        h1 = eng.split_histogram(chain.histogram(one[0], d1, m1, bins=bins, delay_bins=nt).cpu().numpy(),
+                                 m1.cpu().numpy()[0], bins=bins, delay_bins=nt)
+        assert h1["spot_count"].sum() == 1 and h1["spot_count"][0, 0] == 1 and h1["delay_count"][0] == 1
+    with pytest.raises(Exception):
+        chain.histogram(outs[0], det, mom, bins=(0, 8), delay_bins=16)
     chain.close()
 
 
