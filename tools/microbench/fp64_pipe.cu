@@ -54,6 +54,52 @@ void run(const char* name, int per_iter_fp64, int threads, int blocks_per_sm) {
   cudaFree(out);
 }
 
+// issue-slot sharing: NI independent integer multiply-adds per DFMA (does an FP64 instruction hold the issue
+// port for its second pipe cycle, or can another pipe's instruction go in between?)
+template <int NI>
+__global__ void __launch_bounds__(256) mixk(double* out, int iters, double a, double b, double c, int m) {
+  double x[CHAINS];
+  int k[CHAINS][3];
+#pragma unroll
+  for (int j = 0; j < CHAINS; ++j) { x[j] = a + threadIdx.x + j; k[j][0] = threadIdx.x + j; k[j][1] = j * 3; k[j][2] = j * 7 + 1; }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < CHAINS; ++j) {
+      x[j] = fma(x[j], b, c);
+#pragma unroll
+      for (int q = 0; q < NI; ++q) k[j][q] = k[j][q] * m + i;
+    }
+  }
+  double s = 0;
+  int t = 0;
+#pragma unroll
+  for (int j = 0; j < CHAINS; ++j) { s += x[j]; t += k[j][0] + k[j][1] + k[j][2]; }
+  if (s == 123.456 || t == 12345) out[0] = s + t;
+}
+template <int NI>
+void run_mix() {
+  int sms = 0, khz = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+  double* out;
+  cudaMalloc(&out, 8);
+  const int iters = 20000, threads = 192, bps = 2;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  mixk<NI><<<sms * bps, threads>>>(out, 100, 1.0, 0.999999, 1e-9, 3);
+  cudaEventRecord(e0);
+  mixk<NI><<<sms * bps, threads>>>(out, iters, 1.0, 0.999999, 1e-9, 3);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double clocks = ms * 1e-3 * khz * 1e3;
+  const double groups = (double)sms * bps * (threads / 32) * (double)iters * CHAINS;  // (1 DFMA + NI IMAD) groups
+  printf("1 DFMA + %d IMAD: %.2f clk per group per SMSP (pipe alone: 2.00, issue slots: %d)\n", NI,
+         clocks * sms * 4 / groups, 1 + NI);
+  cudaFree(out);
+}
+
 // dependent-issue latency: NCH independent DFMA chains per thread, W warps per SM sub-partition
 template <int NCH>
 __global__ void __launch_bounds__(1024) lat(double* out, int iters, double a, double b, double c) {
@@ -93,6 +139,7 @@ void run_lat(int warps_per_smsp) {
 }
 
 int main() {
+  run_mix<0>(); run_mix<1>(); run_mix<2>(); run_mix<3>();
   run_lat<1>(1); run_lat<2>(1); run_lat<4>(1); run_lat<8>(1);
   run_lat<1>(3); run_lat<2>(3); run_lat<4>(3);
   run_lat<1>(4); run_lat<2>(4); run_lat<2>(6); run_lat<2>(8);
