@@ -536,9 +536,9 @@ extern "C" int32_t art_detector_histogram(const ArtBundleView* bundle, const Art
     long long blocks = (long long)sms * 2;
     const long long need = (bundle->n + HIST_MAX_RAYS_PER_BLOCK - 1) / HIST_MAX_RAYS_PER_BLOCK;
     if (blocks < need) blocks = need;
-    const long long most = (bundle->n + 511) / 512;
+    const long long most = (bundle->n + 2 * ART_HIST_TPB - 1) / (2 * ART_HIST_TPB);
     if (blocks > most) blocks = most;
-    histogram_smem_kernel<<<(unsigned)blocks, 512, smem, st>>>(a);
+    histogram_smem_kernel<<<(unsigned)blocks, ART_HIST_TPB, smem, st>>>(a);
   } else {
     long long blocks = (bundle->n + 255) / 256;
     if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
