@@ -89,6 +89,15 @@ DETECTOR_DOUBLES = C.sizeof(ArtDetector) // 8  # 23
 HIST_FIXED_ONE = 67108864.0  # ART_HIST_FIXED_ONE
 
 
+PEER_MAX_RANKS = 16       # ART_PEER_MAX_RANKS
+PEER_MAX_VARIANTS = 64    # ART_PEER_MAX_VARIANTS
+
+
+def peer_buffer_bytes(world):
+    """ART_PEER_BUFFER_BYTES of the header."""
+    return 8 * (2 * world * PEER_MAX_VARIANTS * MOMENTS_LEN + world + 2)
+
+
 def hist_len(nx, ny, nt):
     """ART_HIST_LEN of the header."""
     return 3 * nx * ny + 2 * nt
@@ -125,6 +134,9 @@ _SIGNATURES = {
                                               C.c_void_p]),
     "art_detector_histogram": (C.c_int32, [C.POINTER(ArtBundleView), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                            C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
+    "art_peer_exchange": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.c_double, C.c_void_p, C.c_void_p]),
+    "art_peer_status": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_void_p]),
     "art_moments_merge": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "art_sweep": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(ArtBundleView), C.c_uint32, C.c_double,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

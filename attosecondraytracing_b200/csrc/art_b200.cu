@@ -592,6 +592,42 @@ extern "C" int32_t art_moments_merge(const double* rows, int32_t n_ranks, int32_
   return ART_OK;
 }
 
+extern "C" int32_t art_peer_exchange(const uint64_t* peer_bufs, int32_t rank, int32_t world, int32_t kind,
+                                     int32_t n_variants, double* rows, double distance, ArtDetector* det_out,
+                                     void* stream) {
+  if (!peer_bufs || !rows) return fail(ART_E_INVALID, "NULL argument");
+  if (world < 1 || world > ART_PEER_MAX_RANKS || rank < 0 || rank >= world)
+    return fail(ART_E_INVALID, "rank / world out of range");
+  if (kind != 0 && kind != 1) return fail(ART_E_INVALID, "kind must be 0 (central) or 1 (moments)");
+  if (n_variants < 1 || n_variants > ART_PEER_MAX_VARIANTS)
+    return fail(ART_E_INVALID, "n_variants must be in [1, ART_PEER_MAX_VARIANTS]");
+  PeerArgs a;
+  for (int r = 0; r < ART_PEER_MAX_RANKS; ++r) a.bufs[r] = r < world ? (unsigned long long)peer_bufs[r] : 0ull;
+  for (int r = 0; r < world; ++r)
+    if (!a.bufs[r]) return fail(ART_E_INVALID, "peer buffer address is NULL");
+  a.rank = rank;
+  a.world = world;
+  a.kind = kind;
+  a.n_variants = n_variants;
+  a.rows = rows;
+  a.distance = distance;
+  a.det_out = kind == 0 ? det_out : nullptr;
+  a.spin_limit = 50000000ull;  // x (64 ns sleep + a system-scope load) ~ 10 s
+  peer_exchange_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+  ART_LAUNCHED();
+  return ART_OK;
+}
+
+extern "C" int32_t art_peer_status(const uint64_t* peer_bufs, int32_t rank, int32_t world, uint64_t* status_out,
+                                   void* stream) {
+  if (!peer_bufs || !status_out || world < 1 || rank < 0 || rank >= world) return fail(ART_E_INVALID, "bad argument");
+  const double* base = reinterpret_cast<const double*>(peer_bufs[rank]);
+  const uint64_t* words = reinterpret_cast<const uint64_t*>(base + (size_t)2 * world * PEER_MAX_DOUBLES);
+  ART_CUDA(cudaMemcpyAsync(status_out, words + world + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  ART_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return ART_OK;
+}
+
 // The sweep traces every ray twice (pass 1: central sums, fold + autoplace; pass 2: fused trace +
 // detector) and stores nothing per ray.  The alternative -- trace once, keep each variant's final
 // bundle (57 B/ray) in L2 and run the detector kernel on it -- was built and measured slower on B200

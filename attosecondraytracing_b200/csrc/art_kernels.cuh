@@ -1065,6 +1065,97 @@ __global__ void merge_moments_kernel(const double* __restrict__ rows, int n_rank
 }
 
 // ---------------------------------------------------------------------------------------------
+// Multi-GPU exchange of the small per-detector rows over PEER MEMORY (NVLink / NVSwitch) inside one
+// kernel: every rank stores its row into slot [rank] of EVERY rank's exchange buffer (remote stores),
+// publishes its epoch in the peers' flag words (release at system scope), waits until the flags of all
+// ranks in its OWN buffer have reached the epoch (acquire) and reduces the rows in rank order -- the same
+// arithmetic on every rank, so every rank places the identical detector.  Replaces an NCCL all-reduce /
+// all-gather of 80-200 bytes (latency-bound, ~15 us each) and the kernel that followed it (autoplace /
+// merge).  The epoch lives in device memory and is advanced by the kernel itself, so the step including
+// the exchange can be captured in a CUDA graph.  Payload slots are double-buffered by epoch parity: a rank
+// that is one exchange ahead writes the other half and cannot be two ahead (it would need this rank's next
+// flag first).
+// Buffer of one rank (identical layout on all ranks, ART_PEER_BUFFER_BYTES(world)):
+//   double payload[2][world][PEER_MAX_DOUBLES];  u64 flags[world];  u64 epoch;  u64 status;
+// ---------------------------------------------------------------------------------------------
+constexpr int PEER_MAX_DOUBLES = ART_PEER_MAX_VARIANTS * ART_MOMENTS_LEN;
+struct PeerArgs {
+  unsigned long long bufs[ART_PEER_MAX_RANKS];  // device address of each rank's exchange buffer
+  int rank, world;
+  int kind;            // 0: central rows (all sums), optionally followed by autoplace; 1: moments rows (sum/min/max)
+  int n_variants;
+  double* rows;        // in / out, n_variants x (ART_CENTRAL_LEN | ART_MOMENTS_LEN)
+  double distance;     // kind 0 with det_out
+  ArtDetector* det_out;
+  unsigned long long spin_limit;  // polls before giving up (status word set, rows left unreduced)
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
+  __shared__ unsigned long long sEpoch;
+  __shared__ int sFail;
+  const int tid = threadIdx.x;
+  const int rlen = a.kind == 0 ? ART_CENTRAL_LEN : ART_MOMENTS_LEN;
+  const int len = a.n_variants * rlen;
+  auto base = [&](int owner) { return reinterpret_cast<double*>(a.bufs[owner]); };
+  auto words = [&](int owner) {
+    return reinterpret_cast<unsigned long long*>(base(owner) + (size_t)2 * a.world * PEER_MAX_DOUBLES);
+  };
+  unsigned long long* const mine = words(a.rank);  // flags[world], epoch, status
+  if (tid == 0) {
+    sEpoch = mine[a.world] + 1ull;
+    mine[a.world] = sEpoch;
+    sFail = 0;
+  }
+  __syncthreads();
+  const unsigned long long epoch = sEpoch;
+  const size_t half = (size_t)(epoch & 1ull) * a.world * PEER_MAX_DOUBLES;
+  // 1. my row into my slot of every rank's buffer (remote stores over NVLink; the local one is a plain store)
+  for (int p = 0; p < a.world; ++p) {
+    double* dst = base(p) + half + (size_t)a.rank * PEER_MAX_DOUBLES;
+    for (int j = tid; j < len; j += blockDim.x) dst[j] = a.rows[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. publish, then wait for everybody
+  if (tid < a.world) {
+    st_release_sys(words(tid) + a.rank, epoch);
+    unsigned long long polls = 0;
+    while (ld_acquire_sys(mine + tid) < epoch) {
+      if (++polls > a.spin_limit) {
+        sFail = 1;
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (sFail) {
+    if (tid == 0) mine[a.world + 1] = epoch;  // status: the epoch that timed out
+    return;
+  }
+  // 3. the same reduction in rank order on every rank (ld.global.cg: the slots are written by peers)
+  for (int j = tid; j < len; j += blockDim.x) {
+    const int op = a.kind == 0 ? 0 : moment_op(j % ART_MOMENTS_LEN);
+    const double* src = base(a.rank) + half + j;
+    double x = __ldcg(src);
+    for (int r = 1; r < a.world; ++r) x = red_any(op, x, __ldcg(src + (size_t)r * PEER_MAX_DOUBLES));
+    a.rows[j] = x;
+  }
+  if (a.kind == 0 && a.det_out) {
+    __syncthreads();
+    for (int v = tid; v < a.n_variants; v += blockDim.x)
+      autoplace_row(a.rows + (size_t)v * ART_CENTRAL_LEN, a.distance, a.det_out + v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Detector.autoplace, ART/ModuleDetector.py:109-137 with FindCentralRay ART/ModuleProcessing.py:464-482:
 // central vector = normalised mean direction, central point = mean point of the surviving rays;
 // normal = -central vector, centre = central point - normal * distance, refpoint = central point.

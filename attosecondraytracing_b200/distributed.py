@@ -82,6 +82,77 @@ def all_reduce_histogram(hist, group=None):
     return hist
 
 
+class PeerExchange:
+    """The exchange of the central sums / moments rows done inside one kernel over peer memory
+    (art_peer_exchange) instead of NCCL: one node, every GPU reachable over NVLink / NVSwitch.  The exchange
+    buffer is torch symmetric memory (one allocation per rank, mapped into every rank's address space).
+
+        peer = PeerExchange.create(device)        # None when symmetric memory is not available -> use NCCL
+        peer.all_reduce_central(central, distance, det)   # sum over ranks + Detector.autoplace, one launch
+        peer.all_reduce_moments(moments)                  # merge over ranks, one launch
+    Every rank must issue the same sequence of calls.  No host synchronisation; CUDA-graph capturable."""
+
+    def __init__(self, buffer, handle, rank, world):
+        import ctypes as C
+        self._buffer = buffer      # keeps the symmetric allocation alive
+        self._handle = handle
+        self.rank, self.world = rank, world
+        self._ptrs = (C.c_uint64 * world)(*[int(p) for p in handle.buffer_ptrs])
+
+    @classmethod
+    def create(cls, device, group=None):
+        if not is_distributed(group):
+            return None
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world > _cabi.PEER_MAX_RANKS:
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            n = _cabi.peer_buffer_bytes(world) // 8
+            buf = symm_mem.empty(n, dtype=torch.float64, device=device)
+            handle = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            buf.zero_()
+            torch.cuda.synchronize(device)
+            ok = torch.ones(1, device=device)
+        except Exception as exc:  # no symmetric memory on this system: the caller keeps NCCL
+            import warnings
+            warnings.warn(f"peer-memory exchange unavailable ({exc}); using NCCL collectives")
+            ok = torch.zeros(1, device=device)
+            buf = handle = None
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # all ranks or none; also: every buffer is zeroed
+        if float(ok) < 1.0:
+            return None
+        return cls(buf, handle, rank, world)
+
+    def _call(self, kind, rows, distance, det):
+        import ctypes as C
+        if not rows.is_contiguous() or rows.dtype != torch.float64:
+            raise ValueError("rows must be a contiguous float64 tensor")
+        nv = rows.shape[0]
+        _cabi.check(_cabi.lib().art_peer_exchange(
+            self._ptrs, self.rank, self.world, kind, nv, C.c_void_p(rows.data_ptr()), float(distance),
+            C.c_void_p(det.data_ptr()) if det is not None else None,
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return rows
+
+    def all_reduce_central(self, central, distance=0.0, det=None):
+        """Sum the central rows (n_variants x 10) over the ranks in place; with `det` (n_variants x 23) also
+        place every variant's detector at `distance` (Detector.autoplace) in the same kernel."""
+        return self._call(0, central, distance, det)
+
+    def all_reduce_moments(self, moments):
+        """Merge the moments rows (n_variants x 24) over the ranks in place (sums / minima / maxima)."""
+        return self._call(1, moments, 0.0, None)
+
+    def status(self):
+        """0, or the epoch of an exchange in which a peer did not arrive (synchronises the stream)."""
+        import ctypes as C
+        out = C.c_uint64(0)
+        _cabi.check(_cabi.lib().art_peer_status(self._ptrs, self.rank, self.world, C.byref(out),
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return int(out.value)
+
+
 def merge_moments(rows):
     """Host-side merge of moments rows from several shards (sequence of (24,) arrays / tensors)."""
     rows = torch.stack([torch.as_tensor(r, dtype=torch.float64) for r in rows])

@@ -263,6 +263,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl", action="store_true",
+                    help="multi-GPU: exchange the central sums / moments with NCCL instead of the peer-memory kernel")
     ap.add_argument("--histograms", action="store_true",
                     help="also bin the detector response (64x64 spot + 128 delay bins) and all-reduce the int64 bins")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of as a CUDA graph")
@@ -355,13 +357,22 @@ def run_b200(args, w, oes):
         inten = src.col("intensity")
         gather_b = torch.empty((world, 1, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev)
         hist_b = torch.empty((_cabi.hist_len(64, 64, 128),), dtype=torch.int64, device=dev) if args.histograms else None
+        # multi-GPU: the two exchanges run inside one kernel each over peer memory (NVLink); NCCL when
+        # symmetric memory is unavailable or --nccl asks for it
+        peer = None if (world == 1 or args.nccl) else ad.PeerExchange.create(dev)
 
         def step():
             chain.trace(src, ignore_defects=True, history=False, want_incidence=True, out=out, central=central_b)
-            ad.all_reduce_central(central_b)
-            chain.autoplace(central_b, distance, det=det_b)
+            if peer is not None:
+                peer.all_reduce_central(central_b, distance, det_b)   # sum over ranks + autoplace
+            else:
+                ad.all_reduce_central(central_b)
+                chain.autoplace(central_b, distance, det=det_b)
             chain.moments(out, det_b, intensity=inten, out=mom_b)
-            ad.all_reduce_moments(mom_b, gather_buffer=gather_b)
+            if peer is not None:
+                peer.all_reduce_moments(mom_b)
+            else:
+                ad.all_reduce_moments(mom_b, gather_buffer=gather_b)
             if hist_b is not None:  # SpotDiagram / DelayGraph bins over the merged extents, exact int64 SUM
                 chain.histogram(out, det_b, mom_b, bins=(64, 64), delay_bins=128, intensity=inten, out=hist_b)
                 ad.all_reduce_histogram(hist_b)
@@ -389,7 +400,8 @@ def run_b200(args, w, oes):
     # for) and the captured communicator did not shut down cleanly, so the option was removed.
     run_step = step
     graphed = False
-    if not args.no_graph and world == 1:
+    peer_graph = world > 1 and not sweep and peer is not None and not args.histograms  # no NCCL call in the step
+    if not args.no_graph and (world == 1 or peer_graph):
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -421,6 +433,8 @@ def run_b200(args, w, oes):
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
+    if world > 1 and not sweep and peer is not None and peer.status() != 0:
+        raise RuntimeError("peer-memory exchange timed out (a rank did not arrive)")
 
     # ---- the dominant kernel alone, CUDA events on the launching stream ----------------------------
     ksteps = max(3, min(args.steps, 50))
@@ -532,6 +546,9 @@ def run_b200(args, w, oes):
         cfg = workload_config(w, args, n)
         if args.histograms and not sweep:
             cfg["histograms"] = "64x64 spot + 128 delay bins per step, int64 all-reduce"
+        if world > 1 and not sweep:
+            cfg["exchange"] = ("central sums and moments exchanged inside one kernel each over peer memory (NVLink)"
+                               if peer is not None else "NCCL all-reduce + all-gather")
         if sweep:
             cfg.update({"variants_per_gpu": nv_rank, "sweep": f"{sweep['axis']} of element {sweep['element']} over "
                         f"[{sweep['lo']}, {sweep['hi']}] deg", "l2": "source bundle (56 MB) re-read per variant from L2 "

@@ -300,6 +300,32 @@ int32_t art_detector_histogram(const ArtBundleView* bundle, const ArtDetector* d
 int32_t art_moments_merge(const double* rows, int32_t n_ranks, int32_t n_variants, double* out, void* stream);
 
 /*
+ * Multi-GPU (one node, NVLink / NVSwitch): the exchange of the central sums or of the moments rows between
+ * the ranks done INSIDE one kernel over peer memory instead of an NCCL collective plus a follow-up kernel.
+ * Every rank calls it with the same arguments (except rank / rows); peer_bufs[r] is the device address,
+ * valid on THIS device, of rank r's exchange buffer -- ART_PEER_BUFFER_BYTES(world) bytes of symmetric /
+ * peer-mapped memory (torch.distributed._symmetric_memory, cudaIpc or cuMem handles), zero-filled once
+ * before the first call and owned by the caller.
+ *   kind 0  rows = n_variants x ART_CENTRAL_LEN, summed over the ranks in rank order (replaces the
+ *           all-reduce after art_trace); with det_out non-NULL Detector.autoplace at `distance` follows in
+ *           the same kernel (replaces art_detector_autoplace).
+ *   kind 1  rows = n_variants x ART_MOMENTS_LEN, merged as art_moments_merge does (replaces the all-gather
+ *           + art_moments_merge after art_detector_moments).
+ * rows are reduced in place; every rank ends up with bit-identical rows.  The call sequence must be the same
+ * on all ranks.  No host synchronisation, CUDA-graph capturable (the epoch is kept in the buffer).  A peer
+ * that does not arrive within ~10 s leaves rows unreduced and sets the buffer's status word
+ * (art_peer_status reads it back; 0 = fine).
+ */
+#define ART_PEER_MAX_RANKS 16
+#define ART_PEER_MAX_VARIANTS 64
+#define ART_PEER_BUFFER_BYTES(world) \
+  ((int64_t)8 * ((int64_t)2 * (world) * ART_PEER_MAX_VARIANTS * ART_MOMENTS_LEN + (world) + 2))
+int32_t art_peer_exchange(const uint64_t* peer_bufs, int32_t rank, int32_t world, int32_t kind, int32_t n_variants,
+                          double* rows, double distance, ArtDetector* det_out, void* stream);
+/* Synchronises the stream and returns the status word of this rank's buffer in *status_out. */
+int32_t art_peer_status(const uint64_t* peer_bufs, int32_t rank, int32_t world, uint64_t* status_out, void* stream);
+
+/*
  * Trace and detector in ONE kernel (K1 with K2 as its epilogue), for detectors that are known
  * before the trace (manual detectors, the second pass of a sweep): as art_trace, and in addition
  * every surviving final ray is intersected with det[v] and the moments are reduced; no per-ray

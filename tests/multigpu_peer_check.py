@@ -1,0 +1,85 @@
+"""Run under torchrun on >= 2 GPUs of one node (tests/test_gpu_multi.py does so when they are there):
+the peer-memory exchange kernel (art_peer_exchange) against the NCCL path it replaces -- sums in rank order
+vs NCCL's all-reduce (equal to rounding), merged moments bit for bit, identical rows on every rank, detectors
+placed in the same kernel, many back-to-back epochs, and a CUDA-graph-captured sequence."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from attosecondraytracing_b200 import _cabi, engine  # noqa: E402
+from attosecondraytracing_b200 import distributed as ad  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    peer = ad.PeerExchange.create(dev)
+    assert peer is not None, "symmetric memory rendezvous failed"
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    for nv in (1, 3, 64):
+        for it in range(20):
+            # central rows: unit-ish direction sums, points, path, counts
+            c = (torch.rand((nv, _cabi.CENTRAL_LEN), generator=g, dtype=torch.float64) + 0.5).to(dev)
+            c[:, 7] = 1000 + rank  # N
+            ref = c.clone()
+            dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+            det_ref = torch.empty((nv, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=dev)
+            _cabi.check(_cabi.lib().art_detector_autoplace(ref.data_ptr(), 123.0, nv, det_ref.data_ptr(),
+                                                           torch.cuda.current_stream().cuda_stream))
+            det = torch.empty_like(det_ref)
+            peer.all_reduce_central(c, 123.0, det)
+            assert torch.allclose(c, ref, rtol=1e-14, atol=0), (nv, it)
+            assert torch.allclose(det, det_ref, rtol=1e-12, atol=1e-12), (nv, it)
+            rows = [torch.empty_like(c) for _ in range(world)]
+            dist.all_gather(rows, c)
+            assert all(torch.equal(r, rows[0]) for r in rows), "ranks disagree on the reduced central rows"
+            # moments rows
+            m = torch.randn((nv, _cabi.MOMENTS_LEN), generator=g, dtype=torch.float64).to(dev)
+            if rank == world - 1 and it % 5 == 0:  # a rank without survivors keeps the reduction identities
+                m[:, 0:14] = 0.0
+                m[:, list(_cabi.MOMENT_MIN)] = float("inf")
+                m[:, list(_cabi.MOMENT_MAX)] = float("-inf")
+            ref = m.clone()
+            ad.all_reduce_moments(ref)  # NCCL all-gather + art_moments_merge
+            peer.all_reduce_moments(m)
+            assert torch.equal(m[:, :21], ref[:, :21]), (nv, it)
+    # graph-captured sequence: the epoch lives in the buffer, so replays keep working
+    c = torch.ones((1, _cabi.CENTRAL_LEN), dtype=torch.float64, device=dev)
+    m = torch.ones((1, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev)
+    det = torch.empty((1, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=dev)
+    cin, min_ = c.clone(), m.clone()
+
+    def seq():
+        c.copy_(cin)
+        m.copy_(min_)
+        peer.all_reduce_central(c, 10.0, det)
+        peer.all_reduce_moments(m)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        seq()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        seq()
+    for _ in range(50):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert float(c[0, 0]) == world and float(m[0, 0]) == world
+    assert peer.status() == 0
+    dist.barrier()
+    if rank == 0:
+        print("peer exchange ok on %d ranks" % world, flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
