@@ -151,6 +151,9 @@ _SIGNATURES = {
     "art_run_host": (C.c_int32, [C.c_void_p, C.POINTER(ArtBundleView), C.POINTER(ArtBundleView), C.c_uint32,
                                  C.c_double, C.POINTER(ArtDetector), c_double_p, c_double_p,
                                  C.POINTER(ArtDetector)]),
+    "art_run_host_sharded": (C.c_int32, [C.c_void_p, C.POINTER(ArtBundleView), C.POINTER(ArtBundleView), C.c_uint32,
+                                         C.c_double, C.POINTER(ArtDetector), c_double_p, c_double_p,
+                                         C.POINTER(ArtDetector), C.POINTER(C.c_uint64), C.c_int32, C.c_int32]),
     "art_trace_host": (C.c_int32, [C.c_void_p, C.POINTER(ArtBundleView), C.POINTER(ArtBundleView),
                                    C.POINTER(ArtBundleView), C.c_uint32]),
     "art_probe_fp64": (C.c_int32, [c_double_p]),

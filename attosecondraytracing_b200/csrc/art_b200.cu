@@ -775,9 +775,10 @@ static int32_t ensure_workspace(ArtChain* c, size_t n) {
   return ART_OK;
 }
 
-extern "C" int32_t art_run_host(ArtChain* c, const ArtBundleView* in_host, const ArtBundleView* out_final_host,
-                                uint32_t flags, double distance, const ArtDetector* manual_det,
-                                double* moments_host, double* central_host, ArtDetector* det_host) {
+static int32_t run_host_impl(ArtChain* c, const ArtBundleView* in_host, const ArtBundleView* out_final_host,
+                             uint32_t flags, double distance, const ArtDetector* manual_det, double* moments_host,
+                             double* central_host, ArtDetector* det_host, const uint64_t* peer_bufs, int32_t rank,
+                             int32_t world) {
   if (!c || !in_host) return fail(ART_E_INVALID, "NULL argument");
   if (in_host->n < 0) return fail(ART_E_INVALID, "negative ray count");
   if (!in_host->px || !in_host->py || !in_host->pz || !in_host->ux || !in_host->uy || !in_host->uz)
@@ -852,14 +853,27 @@ extern "C" int32_t art_run_host(ArtChain* c, const ArtBundleView* in_host, const
   }
   fold_kernel<<<1, TPB, 0, st>>>(c->d_partials, launched_chunks * chunk_blocks, 0, c->d_central, nullptr);
   ART_LAUNCHED();
+  // sharded bundle: the central sums of all ranks are added (and the detector placed) inside one kernel over
+  // peer memory, likewise the moments rows below
   if (manual_det) {
     ART_CUDA(cudaMemcpyAsync(c->d_det, manual_det, sizeof(ArtDetector), cudaMemcpyHostToDevice, st));
+    if (peer_bufs) {
+      rc = art_peer_exchange(peer_bufs, rank, world, 0, 1, c->d_central, distance, nullptr, st);
+      if (rc) return rc;
+    }
+  } else if (peer_bufs) {
+    rc = art_peer_exchange(peer_bufs, rank, world, 0, 1, c->d_central, distance, c->d_det, st);
+    if (rc) return rc;
   } else {
     rc = art_detector_autoplace(c->d_central, distance, 1, c->d_det, st);
     if (rc) return rc;
   }
   rc = art_detector_moments(c, &dout, 1, c->d_det, nullptr, nullptr, nullptr, c->d_moments, st);
   if (rc) return rc;
+  if (peer_bufs) {
+    rc = art_peer_exchange(peer_bufs, rank, world, 1, 1, c->d_moments, 0.0, nullptr, st);
+    if (rc) return rc;
+  }
 
   double* pm = w.pinned;
   double* pc = pm + ART_MOMENTS_LEN;
@@ -883,6 +897,24 @@ extern "C" int32_t art_run_host(ArtChain* c, const ArtBundleView* in_host, const
     for (int j = 0; j < ART_CENTRAL_LEN; ++j) central_host[j] = pc[j];
   if (det_host) *det_host = *pd;
   return ART_OK;
+}
+
+extern "C" int32_t art_run_host(ArtChain* c, const ArtBundleView* in_host, const ArtBundleView* out_final_host,
+                                uint32_t flags, double distance, const ArtDetector* manual_det,
+                                double* moments_host, double* central_host, ArtDetector* det_host) {
+  return run_host_impl(c, in_host, out_final_host, flags, distance, manual_det, moments_host, central_host, det_host,
+                       nullptr, 0, 1);
+}
+
+extern "C" int32_t art_run_host_sharded(ArtChain* c, const ArtBundleView* in_host, const ArtBundleView* out_final_host,
+                                        uint32_t flags, double distance, const ArtDetector* manual_det,
+                                        double* moments_host, double* central_host, ArtDetector* det_host,
+                                        const uint64_t* peer_bufs, int32_t rank, int32_t world) {
+  if (!peer_bufs) return fail(ART_E_INVALID, "peer_bufs is NULL (use art_run_host for an unsharded bundle)");
+  if (world < 1 || world > ART_PEER_MAX_RANKS || rank < 0 || rank >= world)
+    return fail(ART_E_INVALID, "rank / world out of range");
+  return run_host_impl(c, in_host, out_final_host, flags, distance, manual_det, moments_host, central_host, det_host,
+                       peer_bufs, rank, world);
 }
 
 // RayTracingCalculation for a host caller: host columns in, the bundle after every element (and / or

@@ -257,9 +257,11 @@ class DeviceChain:
                                               _ptr(central), _ptr(det), _ptr(mom), _stream()))
         return mom, central, det
 
-    def run_host(self, host_bundle, distance, ignore_defects=True, out_host=None, manual_det=None):
+    def run_host(self, host_bundle, distance, ignore_defects=True, out_host=None, manual_det=None, peer=None):
         """Host buffers in (pinned or pageable torch CPU tensors), statistics out: H2D, trace,
-        autoplace, moments, D2H inside one synchronous C call.  Returns (moments, central, det) numpy."""
+        autoplace, moments, D2H inside one synchronous C call.  Returns (moments, central, det) numpy.
+        peer: a distributed.PeerExchange -- host_bundle is then this rank's shard of a bundle spread over the
+        GPUs of the node and the statistics are those of the whole bundle (art_run_host_sharded)."""
         if host_bundle.device.type != "cpu":
             raise RuntimeError("run_host takes a host-resident bundle")
         flags = (_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0) | host_bundle.trace_flags()
@@ -271,10 +273,15 @@ class DeviceChain:
         vin = host_bundle.view()
         vout = C.byref(out_host.view()) if out_host is not None else None
         dp = _cabi.c_double_p
+        md = C.byref(manual_det) if manual_det is not None else None
         with torch.cuda.device(self.device):
-            _cabi.check(_cabi.lib().art_run_host(self._handle, C.byref(vin), vout, flags, float(distance),
-                                                 C.byref(manual_det) if manual_det is not None else None,
-                                                 mom.ctypes.data_as(dp), cen.ctypes.data_as(dp), C.byref(det)))
+            if peer is None:
+                _cabi.check(_cabi.lib().art_run_host(self._handle, C.byref(vin), vout, flags, float(distance), md,
+                                                     mom.ctypes.data_as(dp), cen.ctypes.data_as(dp), C.byref(det)))
+            else:
+                _cabi.check(_cabi.lib().art_run_host_sharded(self._handle, C.byref(vin), vout, flags, float(distance),
+                                                             md, mom.ctypes.data_as(dp), cen.ctypes.data_as(dp),
+                                                             C.byref(det), peer._ptrs, peer.rank, peer.world))
         if out_host is not None:
             out_host.invalidate()
         return mom, cen, det

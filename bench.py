@@ -471,19 +471,21 @@ def run_b200(args, w, oes):
         h2d = 8 * len(src._names) * count + (24 if src.origin is not None else 0)
         d2h = 8 * (_cabi.MOMENTS_LEN + _cabi.CENTRAL_LEN) + 8 * _cabi.DETECTOR_DOUBLES
         for _ in range(2):
-            chain.run_host(host, distance)
+            chain.run_host(host, distance, peer=peer)
         barrier()
         t0 = time.perf_counter()
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(e2e_steps):
-            mom_h, cen_h, det_h = chain.run_host(host, distance)
+            mom_h, cen_h, det_h = chain.run_host(host, distance, peer=peer)
         torch.cuda.synchronize()
         t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         e2e = {"value": interactions_all * e2e_steps / float(t_e2e.cpu()[0]), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-               "api": "art_run_host (ctypes, pinned host columns in, moments/central/detector out)"}
+               "api": "art_run_host (ctypes, pinned host columns in, moments/central/detector out)" if peer is None else
+                      "art_run_host_sharded (ctypes, pinned host columns of this rank's shard in, whole-bundle "
+                      "moments/central/detector out; ranks combined over peer memory inside the call)"}
     else:
         # the sweep's per-step host traffic is the pose table in (built once) and the result rows out
         host = src.to("cpu").pin_memory()

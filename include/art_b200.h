@@ -396,6 +396,17 @@ int32_t art_run_host(ArtChain* chain, const ArtBundleView* in_host, const ArtBun
                      double* moments_host, double* central_host, ArtDetector* det_host);
 
 /*
+ * art_run_host for ONE SHARD of a bundle that is spread over the GPUs of a node (one process / thread per
+ * GPU, every rank calling with its own shard): the central sums and the moments rows of all ranks are
+ * combined inside the call over peer memory (art_peer_exchange; peer_bufs / rank / world as there), so every
+ * rank places the identical detector and returns the statistics of the WHOLE bundle.
+ */
+int32_t art_run_host_sharded(ArtChain* chain, const ArtBundleView* in_host, const ArtBundleView* out_final_host,
+                             uint32_t flags, double distance, const ArtDetector* manual_det,
+                             double* moments_host, double* central_host, ArtDetector* det_host,
+                             const uint64_t* peer_bufs, int32_t rank, int32_t world);
+
+/*
  * ART/ModuleProcessing.py:250 RayTracingCalculation for a caller that holds HOST arrays (the
  * reference's list[Ray] flattened to columns): copies the source bundle to the device, traces
  * variant 0 and copies back the bundle after EVERY element (out_history_host: n_elements views,

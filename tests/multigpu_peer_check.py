@@ -75,6 +75,25 @@ def main():
     torch.cuda.synchronize()
     assert float(c[0, 0]) == world and float(m[0, 0]) == world
     assert peer.status() == 0
+    # end to end: every rank feeds its round-robin shard of the golden cfg3 bundle (host buffers) to
+    # art_run_host_sharded; all ranks get the statistics of the WHOLE bundle, which the reference pinned
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from golden_util import Golden, golden_optical_elements
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
+    gd = Golden("cfg3_2tor")
+    chain = engine.DeviceChain(golden_optical_elements(gd), device=dev)
+    sel = np.arange(rank, gd["src_P"].shape[0], world)
+    host = RayBundle.from_numpy(gd["src_P"][sel], gd["src_U"][sel], intensity=gd["src_I"][sel], device="cpu")
+    mom, cen, det = chain.run_host(host, gd.spec["detector_distance"], ignore_defects=gd.ignore_defects, peer=peer)
+    s = engine.summary_from_moments(mom, cen)
+    assert abs(s["SpotSizeSD"] - gd["SpotSizeSD"]) <= 1e-9 and abs(s["DurationSD"] - gd["DurationSD"]) <= 1e-5, s
+    assert abs(s["ETransmission"] - gd["ETransmission"]) <= 1e-9
+    assert np.max(np.abs(np.array(det.centre[:]) - gd["det_centre"])) <= 1e-9
+    rows = [torch.empty(_cabi.MOMENTS_LEN, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(rows, torch.from_numpy(mom).to(dev))
+    assert all(torch.equal(r, rows[0]) for r in rows), "ranks disagree on the whole-bundle moments"
+    chain.close()
     dist.barrier()
     if rank == 0:
         print("peer exchange ok on %d ranks" % world, flush=True)
