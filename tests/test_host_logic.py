@@ -285,3 +285,57 @@ def test_save_and_load_compressed_round_trip(tmp_path, capsys):
     assert back["SpotSizeSD"] == 1.25 and len(back["rays"]) == 100
     assert np.array_equal(back["rays"].to_numpy()["P"], g["src_P"][:100])
     assert "Saved results" in capsys.readouterr().out
+
+
+def test_header_macros_match_the_python_constants():
+    """ART_HIST_LEN / ART_PEER_BUFFER_BYTES / ART_HIST_FIXED_ONE of the header evaluated by the C compiler
+    agree with _cabi.hist_len / peer_buffer_bytes / HIST_FIXED_ONE (sizes of caller-owned buffers)."""
+    import subprocess
+    import tempfile
+    from attosecondraytracing_b200 import _cabi
+    src = r'''
+#include <stdio.h>
+#include "art_b200.h"
+int main(void) {
+  printf("%lld %lld %lld %lld %.1f %d %d\n", (long long)ART_HIST_LEN(64, 48, 128), (long long)ART_HIST_LEN(1, 1, 1),
+         (long long)ART_PEER_BUFFER_BYTES(2), (long long)ART_PEER_BUFFER_BYTES(8), (double)ART_HIST_FIXED_ONE,
+         ART_PEER_MAX_RANKS, ART_PEER_MAX_VARIANTS);
+  return 0;
+}
+'''
+    with tempfile.TemporaryDirectory() as td:
+        cfile, exe = os.path.join(td, "m.c"), os.path.join(td, "m")
+        open(cfile, "w").write(src)
+        subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", exe, cfile], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(out[0]), int(out[1])] == [_cabi.hist_len(64, 48, 128), _cabi.hist_len(1, 1, 1)]
+    assert [int(out[2]), int(out[3])] == [_cabi.peer_buffer_bytes(2), _cabi.peer_buffer_bytes(8)]
+    assert float(out[4]) == _cabi.HIST_FIXED_ONE
+    assert [int(out[5]), int(out[6])] == [_cabi.PEER_MAX_RANKS, _cabi.PEER_MAX_VARIANTS]
+
+
+def test_split_histogram_layout_and_units():
+    """engine.split_histogram: the int64 vector of art_detector_histogram -> counts, fixed-point sums back to
+    floating point, edges centred on the bounding-box midpoint, delays in fs relative to the mean path."""
+    from attosecondraytracing_b200 import _cabi
+    from attosecondraytracing_b200.engine import split_histogram
+    nx, ny, nt = 3, 2, 4
+    m = np.zeros(_cabi.MOMENTS_LEN)
+    m[_cabi.M_N], m[_cabi.M_SD] = 4.0, 4.0 * 0.25          # mean d = 0.25 mm
+    m[_cabi.M_XMIN], m[_cabi.M_XMAX], m[_cabi.M_YMIN], m[_cabi.M_YMAX] = -1.0, 2.0, 0.0, 4.0
+    m[_cabi.M_DMIN], m[_cabi.M_DMAX] = 0.0, 1.0
+    h = np.zeros(_cabi.hist_len(nx, ny, nt), dtype=np.int64)
+    one = int(_cabi.HIST_FIXED_ONE)
+    h[1 * ny + 1] = 4                       # all four rays in spot bin (1, 1)
+    h[nx * ny + 1 * ny + 1] = 2 * one       # summed intensity 2.0
+    h[2 * nx * ny + 1 * ny + 1] = one       # summed normalised delay 1.0 -> mean d = 0.25
+    h[3 * nx * ny + 0] = 4
+    h[3 * nx * ny + nt + 0] = 2 * one
+    s = split_histogram(h, m, bins=(nx, ny), delay_bins=nt)
+    assert s["spot_count"].shape == (nx, ny) and s["spot_count"][1, 1] == 4 and s["spot_count"].sum() == 4
+    assert s["spot_intensity"][1, 1] == 2.0
+    assert abs(s["spot_delay"][1, 1]) < 1e-12 and np.isnan(s["spot_delay"][0, 0])   # mean delay of the bin = mean path
+    assert np.allclose(s["x_edges"], np.linspace(-1.5, 1.5, nx + 1)) and np.allclose(s["y_edges"], np.linspace(-2, 2, ny + 1))
+    to_fs = 1e15 / 299792458000.0
+    assert np.allclose(s["delay_edges"], (np.linspace(0, 1, nt + 1) - 0.25) * to_fs)
+    assert s["delay_count"].tolist() == [4, 0, 0, 0] and s["delay_intensity"][0] == 2.0
