@@ -84,7 +84,12 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            time.sleep(0.15)  # let the first samples arrive before the region starts
+            # wait until nvidia-smi is streaming (its start-up takes 0.1 s alone and over a second when
+            # eight ranks start theirs together), so that the 20 ms samples fall INSIDE the timed region
+            import select
+            self.first = None
+            if select.select([self.proc.stdout], [], [], 8.0)[0]:
+                self.first = self.proc.stdout.readline()
         except Exception:
             self.proc = None
 
@@ -94,7 +99,10 @@ class ClockSampler:
             try:
                 self.proc.terminate()
                 out, _ = self.proc.communicate(timeout=5)
-                for line in out.splitlines():
+                lines = out.splitlines()
+                if not lines and self.first:  # a region shorter than one sampling period: the sample taken
+                    lines = [self.first]      # right before it
+                for line in lines:
                     parts = [p.strip() for p in line.split(",")]
                     if len(parts) >= 6:
                         rows.append(parts)
