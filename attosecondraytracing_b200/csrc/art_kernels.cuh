@@ -580,6 +580,7 @@ struct DetArgs {
 #define ART_DET_NSTAGE 3
 #endif
 constexpr int DET_NSTAGE = ART_DET_NSTAGE;
+static_assert(DET_NSTAGE == 3, "the detector kernel's stage rotation is written for three stages");
 constexpr int DET_STAGE_BYTES = DET_NSTAGE * STAGE_COLS * TPB * 16;
 __device__ __forceinline__ void detector_pair(const DetArgs& a, const ArtDetector& D, long long at, const Ray (&r)[RPT],
                                               const double (&w)[RPT], const bool (&al)[RPT],
@@ -618,7 +619,7 @@ __global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetAr
 
   if (vec) {
     double2* const sStage = reinterpret_cast<double2*>(smem_raw) + threadIdx.x;
-    // alive flags of pair p: the RAW bytes (byte 0 / byte 1; pairs beyond the end -> 0) are fetched three
+    // alive flags of pair p: the RAW bytes (byte 0 / byte 1; pairs beyond the end -> 0) are fetched four
     // pairs ahead and stay untouched in a register for a whole loop trip, decoded (bit 0 / bit 1) only at
     // the top of the next one -- decoding at the load site made every trip wait for the load (37 % of
     // the kernel's stall samples sat on that one instruction)
