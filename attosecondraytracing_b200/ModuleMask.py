@@ -23,3 +23,11 @@ class Mask:
     def _lower(self):
         """(ART_SURF_* kind, four surface parameters)."""
         return _cabi.SURF_MASK, [0, 0, 0, 0]
+
+
+def TransmitMaskRayList(Mask, RayList):
+    """The rays of RayList (RayBundle or list[Ray], given in the mask's own frame) that pass the mask, moved
+    to the mask plane with incidence angle and path updated; rays that hit the support are dropped
+    (ART/ModuleMask.py:112-136).  Returns a RayBundle, computed by the CUDA trace kernel."""
+    from .ModuleMirror import _element_frame_trace
+    return _element_frame_trace(Mask, RayList, True)

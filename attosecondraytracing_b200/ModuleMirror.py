@@ -244,3 +244,23 @@ class DeformedMirror:
 
     def _lower(self):
         return self.Mirror._lower()
+
+
+def _element_frame_trace(Optic, RayList, IgnoreDefects):
+    """One optic acting on rays that are ALREADY in its own frame (what ReflectionMirrorRayList and
+    TransmitMaskRayList of the reference take): a one-element chain whose element frame is the lab frame --
+    position = the optic's centre, normal = ez, major axis = ex, so the frame rotation is the identity and
+    p_e = (p - centre) + centre."""
+    from .ModuleOpticalElement import OpticalElement
+    from . import ModuleProcessing as mp
+    element = OpticalElement(Optic, np.asarray(Optic.get_centre(), dtype=np.float64), np.array([0.0, 0.0, 1.0]),
+                             np.array([1.0, 0.0, 0.0]))
+    return mp.RayTracingCalculation(RayList, [element], IgnoreDefects=IgnoreDefects)[0]
+
+
+def ReflectionMirrorRayList(Mirror, ListRay, IgnoreDefects=False):
+    """The rays of ListRay (RayBundle or list[Ray], given in the mirror's own frame) reflected by Mirror:
+    rays that miss the surface or its support are dropped, incidence angle and path are updated
+    (ART/ModuleMirror.py:912-939; note its default IgnoreDefects=False, unlike RayTracingCalculation).
+    Returns a RayBundle, computed by the CUDA trace kernel."""
+    return _element_frame_trace(Mirror, ListRay, IgnoreDefects)

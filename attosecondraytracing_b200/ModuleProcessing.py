@@ -217,6 +217,14 @@ def ReturnNumericalAperture(RayList, RefractiveIndex: float = 1):
     return float(torch.sin(ang.max())) * RefractiveIndex
 
 
+def ReturnAiryRadius(Wavelength: float, NumericalAperture: float) -> float:
+    """Radius 1.22 * lambda / (2 NA) of the Airy disk in the unit of Wavelength; 0 for NA <= 1e-3 or an unknown
+    wavelength, where the diffraction limit is meaningless (ART/ModuleProcessing.py:570-593)."""
+    if Wavelength is None or not NumericalAperture > 1e-3:
+        return 0
+    return 1.22 * 0.5 * Wavelength / NumericalAperture
+
+
 def FindOptimalDistance(Detector, RayList, OptFor="intensity", Amplitude=None, Precision=3, IntensityWeighted=False,
                         verbose=False):
     """Detector position that minimises the spot size ("size"), the duration ("duration") or

@@ -14,7 +14,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-NOT_SCENES = {"optdist", "extsource"}  # fixtures that are not per-scene trace dumps
+NOT_SCENES = {"optdist", "extsource", "raylist"}  # fixtures that are not per-scene trace dumps
 
 
 def golden_names():
@@ -165,3 +165,30 @@ def compare_bundle(name, k, ref, number, P, U, path, inc, check_inc=True):
         dev["inc"] = float(np.max(np.abs(inc - ref["inc"])))
         assert dev["inc"] <= 1e-9, (name, k, dev)
     return dev
+
+
+class RayListGolden:
+    """tests/golden/raylist.npz (oracle/gen_golden_raylist.py): ReflectionMirrorRayList / TransmitMaskRayList of
+    the unmodified reference on rays given in the optic's own frame."""
+
+    def __init__(self):
+        self.z = np.load(os.path.join(GOLDEN_DIR, "raylist.npz"), allow_pickle=False)
+        self.cases = json.loads(str(self.z["cases"]))
+
+    def optic(self, key):
+        spec = dict(self.cases[key]["optic"])
+        spec["support"] = tuple(spec["support"])
+        return build_optic(spec)
+
+    def source(self, key):
+        return self.z[f"{key}_src_P"], self.z[f"{key}_src_U"], self.z[f"{key}_src_num"]
+
+    def out(self, key, tag="out"):
+        return {k: self.z[f"{key}_{tag}_{k}"] for k in ("num", "P", "U", "path", "inc")}
+
+    def identity_element(self, key):
+        """The optic in an element whose frame is the lab frame (position = centre, normal ez, major axis ex)."""
+        import attosecondraytracing_b200.ModuleOpticalElement as moe
+        optic = self.optic(key)
+        return moe.OpticalElement(optic, np.asarray(optic.get_centre(), dtype=np.float64), np.array([0.0, 0.0, 1.0]),
+                                  np.array([1.0, 0.0, 0.0]))

@@ -511,3 +511,28 @@ def test_detector_histograms_match_oracle_and_add_over_shards(name, shape):
     te, tc, tw = mplots.DelayGraphData(final, D, delay_bins=nt)
     assert tc.sum() == n and np.abs(tc - o["delay_count"]).sum() <= 4
     chain.close()
+
+
+@pytest.mark.parametrize("key,tag,ignore", [("toroid", "out", False), ("sphere_cx", "out", False),
+                                            ("parabola_hole", "out", False), ("mask", "out", True),
+                                            ("sphere_zernike", "out", False), ("sphere_zernike", "outign", True)])
+def test_element_frame_functions_of_the_public_api(key, tag, ignore):
+    """ModuleMirror.ReflectionMirrorRayList (default IgnoreDefects=False, as in the reference) and
+    ModuleMask.TransmitMaskRayList on rays given in the optic's own frame, against the same calls of the
+    unmodified reference (tests/golden/raylist.npz)."""
+    from golden_util import RayListGolden
+    from attosecondraytracing_b200.ModuleMask import TransmitMaskRayList
+    from attosecondraytracing_b200.ModuleMirror import ReflectionMirrorRayList
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
+    g = RayListGolden()
+    P, U, num = g.source(key)
+    rays = RayBundle.from_numpy(P, U, number=num, device="cuda")
+    optic = g.optic(key)
+    if key == "mask":
+        out = TransmitMaskRayList(optic, rays)
+    elif tag == "out":
+        out = ReflectionMirrorRayList(optic, rays)  # the reference's default: defects act on the normal too
+    else:
+        out = ReflectionMirrorRayList(optic, rays, IgnoreDefects=ignore)
+    d = out.to_numpy()
+    compare_bundle("raylist_" + key, 0, g.out(key, tag), d["number"], d["P"], d["U"], d["path"], d["incidence"])
