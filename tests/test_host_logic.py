@@ -339,3 +339,36 @@ def test_split_histogram_layout_and_units():
     to_fs = 1e15 / 299792458000.0
     assert np.allclose(s["delay_edges"], (np.linspace(0, 1, nt + 1) - 0.25) * to_fs)
     assert s["delay_count"].tolist() == [4, 0, 0, 0] and s["delay_intensity"][0] == 2.0
+
+
+def test_geometry_helpers_match_the_reference():
+    """The small helpers of ModuleGeometry under the reference's names (point lists, ray lists as RayBundle and
+    as list[Ray], root filters) against tests/golden/geometry.npz written by the unmodified reference."""
+    import attosecondraytracing_b200.ModuleGeometry as mg
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
+    from golden_util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "geometry.npz"))
+    A, u, P, n, I1, I2, T, pts2, pts3 = (z[k] for k in ("A", "u", "P", "n", "I1", "I2", "T", "pts2", "pts3"))
+    tol = dict(rtol=0, atol=1e-14)
+    assert np.allclose(mg.IntersectionLinePlane(A, u, P, n), z["ilp"], **tol)
+    assert np.allclose(np.sort(mg.SolverQuadratic(2.0, -3.0, -7.0)), z["quad"], **tol)
+    assert np.allclose(np.sort(mg.SolverQuartic(1.0, 0.5, -5.0, 0.25, 3.0)), z["quart"], rtol=0, atol=1e-12)
+    assert mg.SolverQuadratic(1.0, 0.0, 1.0) == []
+    assert mg.KeepPositiveSolution([-1.0, 1e-13, 2.0]) == [2.0] and mg.KeepNegativeSolution([-1.0, -1e-13, 2.0]) == [-1.0]
+    assert np.array_equal(mg.ClosestPoint(A, I1, I2), z["closest"]) and np.array_equal(mg.FarestPoint(A, I1, I2), z["farest"])
+    assert mg.DiameterPointList(pts2) == float(z["diam2"]) and mg.DiameterPointList(pts3) == float(z["diam3"])
+    assert mg.DiameterPointList([]) is None
+    assert np.allclose(mg.CentrePointList(pts2), z["centre2"], **tol)
+    assert np.allclose(mg.SymmetricalVector(u, n), z["symm"], **tol)
+    assert np.allclose(mg.RotationPointList(pts3, u, n), z["rotpl"], **tol)
+    assert np.allclose(mg.TranslationPointList(pts3, T), z["trpl"], **tol)
+    bundle = RayBundle.from_numpy(z["ray_P"], z["ray_U"])
+    for name, args in (("TranslationRayList", (T,)), ("RotationRayList", (u, n)), ("RotationAroundAxisRayList", (n, 0.7))):
+        got = getattr(mg, name)(bundle, *args)
+        assert isinstance(got, RayBundle) and got is not bundle
+        d = got.to_numpy()
+        assert np.allclose(d["P"], z[name + "_P"], **tol) and np.allclose(d["U"], z[name + "_U"], **tol), name
+        as_list = getattr(mg, name)(list(bundle)[:20], *args)
+        assert np.allclose(np.array([r.point for r in as_list]), z[name + "_P"][:20], **tol), name
+        assert np.allclose(np.array([r.vector for r in as_list]), z[name + "_U"][:20], **tol), name
+    assert np.array_equal(bundle.to_numpy()["P"], z["ray_P"])  # the input bundle is left untouched
