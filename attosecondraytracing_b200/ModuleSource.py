@@ -75,6 +75,27 @@ def PlaneWaveDisk(Centre, Axis, Radius, NbRays, Wavelength=None, device=None, fi
     return _generate(1, NbRays, first, count, Radius, Axis, Centre, Wavelength, device, stride)
 
 
+def PlaneWaveSquare(Centre, Axis, SideLength, NbRays, Wavelength=None, device=None):
+    """Collimated rays on a square grid of int(sqrt(NbRays))^2 points of side SideLength, plus a central ray.
+
+    ART/ModuleSource.py:173-208 is meant to build this bundle but raises for every NbRays >= 4 (it compares whole
+    coordinate arrays, `abs(x) > 1e-4`, inside the loop over their entries).  This is the evident intent of that
+    code: ray 0 on the axis, then the grid points (i, j) in row order with |i| > 1e-4 and |j| > 1e-4, numbered
+    consecutively, rotated from ez onto Axis and moved to Centre.  A small host-side construction (no kernel)."""
+    from . import ModuleGeometry as mgeo
+    from .ModuleOpticalRay import RayBundle
+    m = int(np.sqrt(NbRays))
+    grid = np.linspace(-SideLength / 2, SideLength / 2, m)
+    keep = grid[np.abs(grid) > 1e-4]
+    xx, yy = np.meshgrid(keep, keep, indexing="ij")
+    P = np.concatenate([np.zeros((1, 3)), np.stack([xx.ravel(), yy.ravel(), np.zeros(xx.size)], axis=1)])
+    U = np.tile(np.array([0.0, 0.0, 1.0]), (P.shape[0], 1))
+    bundle = RayBundle.from_numpy(P, U, wavelength=Wavelength, device="cpu")
+    bundle = mgeo.TranslationRayList(mgeo.RotationRayList(bundle, np.array([0.0, 0.0, 1.0]), np.asarray(Axis, dtype=np.float64)),
+                                     np.asarray(Centre, dtype=np.float64))
+    return bundle if device is None else bundle.to(device)
+
+
 def ApplyGaussianIntensityToRayList(RayList, IntensityFraction=1 / np.e**2, group=None, axis=None, scale=None):
     """Gaussian intensity profile, 1 on the axis falling to IntensityFraction at the edge of the
     bundle (ART/ModuleSource.py:219-261): by angle for a diverging bundle (max angle > 1e-12),

@@ -372,3 +372,18 @@ def test_geometry_helpers_match_the_reference():
         assert np.allclose(np.array([r.point for r in as_list]), z[name + "_P"][:20], **tol), name
         assert np.allclose(np.array([r.vector for r in as_list]), z[name + "_U"][:20], **tol), name
     assert np.array_equal(bundle.to_numpy()["P"], z["ray_P"])  # the input bundle is left untouched
+
+
+def test_plane_wave_square_builds_the_intended_grid():
+    """ModuleSource.PlaneWaveSquare: the reference's function raises (ART/ModuleSource.py:202 compares arrays);
+    here it builds what that code evidently intends -- a central ray plus the off-axis grid points."""
+    import attosecondraytracing_b200.ModuleSource as msrc
+    centre, axis = np.array([1.0, -2.0, 3.0]), np.array([1.0, 0.0, 0.0])
+    b = msrc.PlaneWaveSquare(centre, axis, 10.0, 50)          # 7 x 7 grid, its middle row / column on the axes
+    d = b.to_numpy()
+    assert len(b) == 1 + 6 * 6 and np.array_equal(d["number"], np.arange(37))
+    assert np.allclose(d["U"], axis) and np.allclose(d["P"][0], centre)
+    rel = d["P"] - centre
+    assert np.allclose(rel[:, 0], 0.0, atol=1e-14)             # the grid lies in the plane normal to the axis
+    assert np.isclose(np.abs(rel[1:, 1:]).max(), 5.0) and np.abs(rel[1:, 1:]).min() > 1e-4
+    assert len(msrc.PlaneWaveSquare(centre, axis, 10.0, 16)) == 17   # 4 x 4 grid, no point on the axes
