@@ -536,3 +536,29 @@ def test_element_frame_functions_of_the_public_api(key, tag, ignore):
         out = ReflectionMirrorRayList(optic, rays, IgnoreDefects=ignore)
     d = out.to_numpy()
     compare_bundle("raylist_" + key, 0, g.out(key, tag), d["number"], d["P"], d["U"], d["path"], d["incidence"])
+
+
+def test_ray_list_transforms_on_device_bundles():
+    """ModuleGeometry.TranslationRayList / RotationRayList / RotationAroundAxisRayList on a CUDA bundle (tensor
+    operations on the device) against the reference's results (tests/golden/geometry.npz); a uniform-origin
+    point-source bundle is materialised first."""
+    import os
+    import attosecondraytracing_b200.ModuleGeometry as mg
+    import attosecondraytracing_b200.ModuleSource as msrc
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle
+    from golden_util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "geometry.npz"))
+    u, n, T = z["u"], z["n"], z["T"]
+    bundle = RayBundle.from_numpy(z["ray_P"], z["ray_U"], device="cuda")
+    for name, args in (("TranslationRayList", (T,)), ("RotationRayList", (u, n)), ("RotationAroundAxisRayList", (n, 0.7))):
+        d = getattr(mg, name)(bundle, *args).to_numpy()
+        assert np.allclose(d["P"], z[name + "_P"], rtol=0, atol=1e-14), name
+        assert np.allclose(d["U"], z[name + "_U"], rtol=0, atol=1e-14), name
+    # device-generated point source (one shared origin): same rays as the reference's PointSource
+    src = msrc.PointSource(np.array([1.0, 2.0, 3.0]), np.array([0.2, 0.5, 1.0]), 0.05, 200, Wavelength=800e-6, device="cuda")
+    assert src.origin is not None
+    d = mg.RotationRayList(src, u, n).to_numpy()
+    assert np.allclose(d["P"], z["RotationRayList_P"], rtol=0, atol=1e-13)
+    assert np.allclose(d["U"], z["RotationRayList_U"], rtol=0, atol=1e-13)
+    d = mg.TranslationRayList(src, T).to_numpy()
+    assert np.allclose(d["P"], z["TranslationRayList_P"], rtol=0, atol=1e-13)
