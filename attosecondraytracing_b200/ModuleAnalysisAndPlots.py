@@ -1,5 +1,5 @@
 """Result summaries of ART/ModuleAnalysisAndPlots.py (:62-129) and the DATA of its SpotDiagram /
-DelayGraph figures as device-side histograms.  The matplotlib / pyvista drawing itself is out of scope
+DelayGraph figures as device-side histograms and of MirrorProjection as per-ray arrays.  The matplotlib / pyvista drawing itself is out of scope
 of this package."""
 from __future__ import annotations
 
@@ -56,3 +56,35 @@ def DelayGraphData(RayListAnalysed, Detector, delay_bins=128):
     ART/ModuleAnalysisAndPlots.py:360-440): (delay_edges_fs, count, summed_intensity)."""
     h = Detector.get_histograms(RayListAnalysed, bins=(1, 1), delay_bins=delay_bins)
     return h["delay_edges"], h["delay_count"], h["delay_intensity"]
+
+
+def MirrorProjectionData(OpticalChain, ReflectionNumber: int, Detector=None, ColorCoded=None):
+    """The content of MirrorProjection (ART/ModuleAnalysisAndPlots.py:443-520): the impact points of the
+    bundle after optical element `ReflectionNumber` in that element's SUPPORT frame (the element frame
+    without the shift by the optic's centre) and the quantity the figure colour-codes.  Returns (x, y, z):
+    x, y in mm; z = intensities, incidence angles in degrees, delays at `Detector` in fs, or None."""
+    from . import ModuleGeometry as mgeo
+    if ColorCoded not in (None, "Intensity", "Incidence", "Delay"):
+        raise ValueError('ColorCoded must be None, "Intensity", "Incidence" or "Delay"')
+    if ColorCoded == "Delay" and Detector is None:
+        raise ValueError("If you want to project ray delays, you must specify a detector.")
+    element = OpticalChain.optical_elements[ReflectionNumber]
+    rays = OpticalChain.get_output_rays()[ReflectionNumber]
+    ez, ex = np.array([0.0, 0.0, 1.0]), np.array([1.0, 0.0, 0.0])
+    moved = mgeo.TranslationRayList(rays, -np.asarray(element.position, dtype=np.float64))
+    moved = mgeo.RotationRayList(moved, element.normal, ez)
+    moved = mgeo.RotationRayList(moved, mgeo.RotationPoint(element.majoraxis, element.normal, ez), ex)
+    idx = moved.alive_index()
+    x = moved.col("px")[idx].cpu().numpy()
+    y = moved.col("py")[idx].cpu().numpy()
+    z = None
+    if ColorCoded == "Intensity":
+        col = rays.col("intensity") if rays.has("intensity") else getattr(rays, "shared_intensity", None)
+        if col is None:
+            raise TypeError("the bundle carries no intensities")
+        z = col[idx].cpu().numpy()
+    elif ColorCoded == "Incidence":
+        z = np.rad2deg(rays.col("incidence")[idx].cpu().numpy())
+    elif ColorCoded == "Delay":
+        z = np.asarray(Detector.get_Delays(rays))
+    return x, y, z

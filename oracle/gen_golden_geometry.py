@@ -36,6 +36,22 @@ def main():
     for name, args in (("TranslationRayList", (T,)), ("RotationRayList", (u, n)), ("RotationAroundAxisRayList", (n, 0.7))):
         res = gg.bundle_arrays(getattr(g, name)(rays, *args))
         out[name + "_P"], out[name + "_U"] = res["P"], res["U"]
+    # MirrorProjection (ART/ModuleAnalysisAndPlots.py:470-483): impact points of the bundle after an element in
+    # that element's support frame, from the reference's own ray-list transforms, on the cfg3 scene
+    import scenes as sc
+    import load_reference as lr
+    chain = gg.build_chain(sc.resolve("cfg3_2tor"))
+    with lr.quiet():
+        outs = chain.get_output_rays()
+    for k in (0, 1, 2):
+        oe = chain.optical_elements[k]
+        rl = g.TranslationRayList(outs[k], -oe.position)
+        rl = g.RotationRayList(rl, oe.normal, np.array([0, 0, 1]))
+        mp_ = g.RotationPoint(oe.majoraxis, oe.normal, np.array([0, 0, 1]))
+        rl = g.RotationRayList(rl, mp_, np.array([1, 0, 0]))
+        out[f"mproj{k}_xy"] = np.array([[r.point[0], r.point[1]] for r in rl])
+        out[f"mproj{k}_incdeg"] = np.array([np.rad2deg(r.incidence) for r in outs[k]])
+        out[f"mproj{k}_intensity"] = np.array([r.intensity for r in outs[k]])
     np.savez_compressed(os.path.join(gg.GOLDEN_DIR, "geometry.npz"), **out)
     print("written", len(out), "arrays")
 

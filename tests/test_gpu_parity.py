@@ -562,3 +562,26 @@ def test_ray_list_transforms_on_device_bundles():
     assert np.allclose(d["U"], z["RotationRayList_U"], rtol=0, atol=1e-13)
     d = mg.TranslationRayList(src, T).to_numpy()
     assert np.allclose(d["P"], z["TranslationRayList_P"], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_mirror_projection_data_matches_reference(k):
+    """ModuleAnalysisAndPlots.MirrorProjectionData: impact points of the bundle after element k in that
+    element's support frame + the colour-coded quantity, against the reference's own ray-list transforms on
+    the cfg3 scene (tests/golden/geometry.npz)."""
+    import os
+    import attosecondraytracing_b200.ModuleOpticalChain as moc
+    from attosecondraytracing_b200 import ModuleAnalysisAndPlots as mplots
+    from golden_util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "geometry.npz"))
+    g = Golden("cfg3_2tor")
+    chain = moc.OpticalChain(_source_bundle(g), golden_optical_elements(g), "cfg3")
+    x, y, inc = mplots.MirrorProjectionData(chain, k, ColorCoded="Incidence")
+    ref = z[f"mproj{k}_xy"]
+    assert x.shape[0] == ref.shape[0]
+    assert np.max(np.abs(np.stack([x, y], axis=1) - ref)) <= 1e-9
+    assert np.max(np.abs(inc - z[f"mproj{k}_incdeg"])) <= 1e-7
+    _, _, w = mplots.MirrorProjectionData(chain, k, ColorCoded="Intensity")
+    assert np.max(np.abs(w - z[f"mproj{k}_intensity"])) <= 1e-12
+    with pytest.raises(ValueError):
+        mplots.MirrorProjectionData(chain, k, ColorCoded="Delay")
