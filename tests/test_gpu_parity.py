@@ -585,3 +585,41 @@ def test_mirror_projection_data_matches_reference(k):
     assert np.max(np.abs(w - z[f"mproj{k}_intensity"])) <= 1e-12
     with pytest.raises(ValueError):
         mplots.MirrorProjectionData(chain, k, ColorCoded="Delay")
+
+
+@pytest.mark.parametrize("name", ["cfg1_par", "cfg2_tor2f", "cfg3_2tor"])
+def test_driver_run_reproduces_the_reference_summary(name, tmp_path):
+    """ARTmain.main (the reference's driver flow, ARTmain.py:248-345, without plotting): trace, automatic /
+    manual detector, result summary, loop lists, saving -- against the statistics the reference produced."""
+    import attosecondraytracing_b200.ModuleOpticalChain as moc
+    from attosecondraytracing_b200 import ARTmain
+    from attosecondraytracing_b200 import ModuleProcessing as mp
+    g = Golden(name)
+    chain = moc.OpticalChain(_source_bundle(g), golden_optical_elements(g), name)
+    quiet = {"verbose": False, "save_results": False}
+    kept = ARTmain.main(chain, {}, {"DistanceDetector": g.spec["detector_distance"]}, quiet)
+    ptol = point_tol(name)
+    assert abs(kept["SpotSizeSD"][0] - g["SpotSizeSD"]) <= ptol
+    assert abs(kept["DurationSD"][0] - g["DurationSD"]) <= DELAY_TOL_FS
+    assert abs(kept["ETransmission"][0] - g["ETransmission"]) <= 1e-9
+    det = kept["Detector"][0]
+    assert np.max(np.abs(det.centre - g["det_centre"])) <= ptol
+    # manual detector at the reference's pose: the same summary
+    manual = {"ManualDetector": True, "DetectorCentre": g["det_centre"], "DetectorNormal": g["det_normal"]}
+    kept_m = ARTmain.main(chain, {}, manual, quiet)
+    assert abs(kept_m["SpotSizeSD"][0] - g["SpotSizeSD"]) <= ptol
+    assert abs(kept_m["DurationSD"][0] - g["DurationSD"]) <= DELAY_TOL_FS
+    # a loop list, saved and loaded back
+    kept_l = ARTmain.main([chain, chain], {}, {"DistanceDetector": g.spec["detector_distance"]},
+                          {"verbose": False, "save_results": True}, save_file_name=str(tmp_path / "res"))
+    assert len(kept_l["SpotSizeSD"]) == 2 and kept_l["SpotSizeSD"][0] == kept_l["SpotSizeSD"][1] == kept["SpotSizeSD"][0]
+    files = list(tmp_path.glob("res*.xz"))
+    assert len(files) == 1
+    back = mp.load_compressed(str(files[0])[:-3])
+    assert back["SpotSizeSD"] == kept_l["SpotSizeSD"] and back["ETransmission"] == kept_l["ETransmission"]
+    # detector-distance optimisation: stays within the search range and does not make the figure of merit worse
+    kept_o = ARTmain.main(chain, {}, {"DistanceDetector": g.spec["detector_distance"], "AutoDetectorDistance": True,
+                                      "OptFor": "intensity"}, quiet)
+    s0 = det.get_statistics(chain.get_output_rays()[-1])
+    merit0 = s0["SpotSizeSD_w"] ** 2 * s0["DurationSD_w"]
+    assert kept_o["SpotSizeSD"][0] ** 2 * kept_o["DurationSD"][0] <= merit0 * (1 + 1e-9)

@@ -387,3 +387,33 @@ def test_plane_wave_square_builds_the_intended_grid():
     assert np.allclose(rel[:, 0], 0.0, atol=1e-14)             # the grid lies in the plane normal to the axis
     assert np.isclose(np.abs(rel[1:, 1:]).max(), 5.0) and np.abs(rel[1:, 1:]).min() > 1e-4
     assert len(msrc.PlaneWaveSquare(centre, axis, 10.0, 16)) == 17   # 4 x 4 grid, no point on the axes
+
+
+def test_driver_defaults_and_error_behaviour():
+    """attosecondraytracing_b200.ARTmain (the reference's ARTmain.py without plotting): option completion and
+    the errors of setup_detector / main, which need no GPU."""
+    from attosecondraytracing_b200 import ARTmain
+    from attosecondraytracing_b200.DefaultOptions import DefaultDetectorOptions, DefaultSourceProperties
+    src, det, ana = ARTmain.complete_defaults({"NumberRays": 7}, {"DistanceDetector": 50.0}, {"verbose": False})
+    assert src["NumberRays"] == 7 and src["Wavelength"] == 50e-6 and det["ReflectionNumber"] == -1
+    assert det["DistanceDetector"] == 50.0 and ana["verbose"] is False and ana["save_results"] is True
+    assert DefaultSourceProperties["NumberRays"] == 1000 and DefaultDetectorOptions["DistanceDetector"] is None
+
+    class _Chain:  # setup_detector only looks at the element positions
+        class _E:
+            position = np.zeros(3)
+        optical_elements = [_E()]
+
+    with pytest.raises(RuntimeError, match="DetectorCentre"):
+        ARTmain.setup_detector(_Chain(), dict(det, ManualDetector=True))
+    with pytest.raises(RuntimeError, match="DetectorNormal"):
+        ARTmain.setup_detector(_Chain(), dict(det, ManualDetector=True, DetectorCentre=np.ones(3)))
+    with pytest.raises(RuntimeError, match="DistanceDetector"):
+        ARTmain.setup_detector(_Chain(), dict(det, DistanceDetector=None))
+    with pytest.raises(RuntimeError, match="RayList"):
+        ARTmain.setup_detector(_Chain(), det, None)
+    manual = ARTmain.setup_detector(_Chain(), dict(det, ManualDetector=True, DetectorCentre=np.array([0.0, 0.0, 5.0]),
+                                                   DetectorNormal=np.array([0.0, 0.0, -1.0])))
+    assert abs(manual.get_distance() - 5.0) < 1e-12
+    with pytest.raises(ValueError, match="neither an OpticalChain"):
+        ARTmain.main("not a chain", {}, {}, {})
