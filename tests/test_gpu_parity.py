@@ -623,3 +623,20 @@ def test_driver_run_reproduces_the_reference_summary(name, tmp_path):
     s0 = det.get_statistics(chain.get_output_rays()[-1])
     merit0 = s0["SpotSizeSD_w"] ** 2 * s0["DurationSD_w"]
     assert kept_o["SpotSizeSD"][0] ** 2 * kept_o["DurationSD"][0] <= merit0 * (1 + 1e-9)
+
+
+def test_example_config_script_runs():
+    """examples/toroidal_2f2f_byhand.py -- a config script in the reference's style with only the imports
+    switched -- runs through ARTmain.main; 2f-2f imaging of a point source: all rays arrive, micrometre spot."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("example_cfg", os.path.join(here, "examples", "toroidal_2f2f_byhand.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from attosecondraytracing_b200 import ARTmain
+    chain, sp, do, ao = mod.build(number_rays=20000)
+    kept = ARTmain.main(chain, sp, do, dict(ao, verbose=False))
+    assert kept["ETransmission"][0] == pytest.approx(100.0, abs=1e-9)
+    assert 0 < kept["SpotSizeSD"][0] < 0.05 and 0 < kept["DurationSD"][0] < 5.0
+    assert abs(kept["Detector"][0].get_distance() - 600.0) < 1e-9
