@@ -234,9 +234,6 @@ __device__ __forceinline__ void moments_finish(ACC& m) {
 #ifndef ART_SMEM_ACC
 #define ART_SMEM_ACC 1
 #endif
-#ifndef ART_PREFETCH
-#define ART_PREFETCH 0
-#endif
 #ifndef ART_STAGE
 #define ART_STAGE 1
 #endif
@@ -246,7 +243,6 @@ __device__ __forceinline__ void moments_finish(ACC& m) {
 #ifndef ART_STAGE_INC
 #define ART_STAGE_INC 1  // staging also in the kernels that compute incidences (pays off once nothing spills)
 #endif
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Input staging: every thread copies the 16-byte column slices of its NEXT ray pair into its own
 // shared-memory slots with cp.async (LDGSTS) while it traces the current pair, so the DRAM latency of
@@ -423,16 +419,6 @@ __global__ void __launch_bounds__(TPB, HAS_DEF ? ART_MINB_DEF : ART_MINB) trace_
     const long long nxt = item + stride;
     const bool staged_next = STAGE && nxt < nitems && (nxt * 2 + 1 < n);
     if (staged_next) stage_issue(stage ^ 1, nxt);
-#if ART_PREFETCH
-    {  // pull the columns of this thread's NEXT rays into L2 while this pair is traced
-      const long long inext = (item + (long long)gridDim.x * TPB) * N;
-      if (inext < n) {
-        prefetch_l2(a.in.px + inext); prefetch_l2(a.in.py + inext); prefetch_l2(a.in.pz + inext);
-        prefetch_l2(a.in.ux + inext); prefetch_l2(a.in.uy + inext); prefetch_l2(a.in.uz + inext);
-        if (a.in.inten) prefetch_l2(a.in.inten + inext);
-      }
-    }
-#endif
     Ray r[N];
     double w[N];
     if (staged) {

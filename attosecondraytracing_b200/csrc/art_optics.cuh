@@ -497,9 +497,6 @@ ART_HD void surface_normal(const ElemDev& E, T x, T y, T z, T& nx, T& ny, T& nz)
 // rounded to double; fitted with mpmath at 60 digits).  Estrin evaluation: dependency depth 5 instead of
 // 12 -- this kernel is bound by dependent-FP64 latency, not by the FMA count.  The coefficients are
 // constant-bank operands of the FMAs on the device (no UMOV pairs to materialise 64-bit immediates).
-#ifndef ART_ATAN_SERIES
-#define ART_ATAN_SERIES 0
-#endif
 #define ART_ATAN_COEFFS                                                                                     \
   {0.3333333333333333, -0.19999999999999804, 0.14285714285659828, -0.11111111105155447,                     \
    0.09090908753500877, -0.07692296375032143, 0.06666424885738255, -0.05878928997834775,                    \
@@ -529,16 +526,7 @@ ART_HD T fatan2_ypos(T y, T x) {
   const M big = lo > 0.41421356237309503 * hi;               // beyond tan(pi/8): rotate by pi/4
   const T z = fdiv(sel(big, lo - hi, lo), sel(big, lo + hi, hi));
   const T w = z * z;
-#if ART_ATAN_SERIES
-  T p = splat<T>(-1.0 / 41.0);
-  p = mfma(p, w, 1.0 / 39.0);  p = mfma(p, w, -1.0 / 37.0); p = mfma(p, w, 1.0 / 35.0);  p = mfma(p, w, -1.0 / 33.0);
-  p = mfma(p, w, 1.0 / 31.0);  p = mfma(p, w, -1.0 / 29.0); p = mfma(p, w, 1.0 / 27.0);  p = mfma(p, w, -1.0 / 25.0);
-  p = mfma(p, w, 1.0 / 23.0);  p = mfma(p, w, -1.0 / 21.0); p = mfma(p, w, 1.0 / 19.0);  p = mfma(p, w, -1.0 / 17.0);
-  p = mfma(p, w, 1.0 / 15.0);  p = mfma(p, w, -1.0 / 13.0); p = mfma(p, w, 1.0 / 11.0);  p = mfma(p, w, -1.0 / 9.0);
-  p = mfma(p, w, 1.0 / 7.0);   p = mfma(p, w, -1.0 / 5.0);  p = mfma(p, w, 1.0 / 3.0);
-#else
   const T p = atan_poly(w);
-#endif
   T a = mfma(-(z * w), p, z);                                // atan(z)
   a = a + sel(big, 0.78539816339744831, 0.0);
   a = sel(swap, 1.5707963267948966 - a, a);
