@@ -14,7 +14,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-NOT_SCENES = {"optdist", "extsource", "raylist", "geometry"}  # fixtures that are not per-scene trace dumps
+NOT_SCENES = {"optdist", "extsource", "raylist", "geometry", "example_byhand"}  # fixtures that are not per-scene trace dumps
 
 
 def golden_names():

@@ -640,3 +640,14 @@ def test_example_config_script_runs():
     assert kept["ETransmission"][0] == pytest.approx(100.0, abs=1e-9)
     assert 0 < kept["SpotSizeSD"][0] < 0.05 and 0 < kept["DurationSD"][0] < 5.0
     assert abs(kept["Detector"][0].get_distance() - 600.0) < 1e-9
+    # the same scene with the reference's default 1000 rays, built and analysed by the unmodified reference
+    # (oracle/gen_golden_example.py)
+    from golden_util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "example_byhand.npz"))
+    chain, sp, do, ao = mod.build(number_rays=int(z["n"]))
+    kept = ARTmain.main(chain, sp, do, dict(ao, verbose=False))
+    assert len(chain.get_output_rays()[-1]) == int(z["survivors"])
+    assert abs(kept["SpotSizeSD"][0] - float(z["SpotSizeSD"])) <= 1e-9
+    assert abs(kept["DurationSD"][0] - float(z["DurationSD"])) <= DELAY_TOL_FS
+    assert abs(kept["ETransmission"][0] - float(z["ETransmission"])) <= 1e-9
+    assert np.max(np.abs(kept["Detector"][0].centre - z["det_centre"])) <= 1e-9
