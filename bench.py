@@ -256,7 +256,8 @@ def workload_config(w, args, n_total):
     return {"workload": f"{w['name']}: {w['scene']} ({', '.join(o['kind'] for o in s['optics'])}), "
                         f"{n_total} rays per GPU, detector autoplace at {s['detector_distance']} mm",
             "rays_per_gpu": int(n_total), "elements": len(s["optics"]),
-            "l2": "inputs larger than L2 (>= 320 MB of source columns + 650 MB of outputs per step)", "ignore_defects": True}
+            "l2": "inputs larger than L2 (>= 320 MB of source columns + 650 MB of outputs per step)",
+            "ignore_defects": not getattr(args, "defect_normals", False)}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -273,6 +274,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl", action="store_true",
                     help="multi-GPU: exchange the central sums / moments with NCCL instead of the peer-memory kernel")
+    ap.add_argument("--defect-normals", action="store_true",
+                    help="IgnoreDefects=False: surface defects also tilt the normals (SURVEY.md 8d, cfg4's second mode)")
     ap.add_argument("--histograms", action="store_true",
                     help="also bin the detector response (64x64 spot + 128 delay bins) and all-reduce the int64 bins")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of as a CUDA graph")
@@ -312,6 +315,7 @@ def run_b200(args, w, oes):
     distance = w["scene_spec"]["detector_distance"]
     sweep = w.get("sweep")
     n = int(w["rays"])
+    ign = not args.defect_normals  # the reference's default through get_output_rays is IgnoreDefects=True
 
     if sweep:
         # cfg5: every rank holds the full n-ray bundle and its share of the (weak-scaled) variant axis
@@ -370,7 +374,7 @@ def run_b200(args, w, oes):
         peer = None if (world == 1 or args.nccl) else ad.PeerExchange.create(dev)
 
         def step():
-            chain.trace(src, ignore_defects=True, history=False, want_incidence=True, out=out, central=central_b)
+            chain.trace(src, ignore_defects=ign, history=False, want_incidence=True, out=out, central=central_b)
             if peer is not None:
                 peer.all_reduce_central(central_b, distance, det_b)   # sum over ranks + autoplace
             else:
@@ -386,7 +390,7 @@ def run_b200(args, w, oes):
                 ad.all_reduce_histogram(hist_b)
             return out, central_b, det_b, mom_b
 
-        e, sv = chain.count_entering(src)
+        e, sv = chain.count_entering(src, ignore_defects=ign)
         entering = [int(x) for x in e[0].cpu()]
         n_surv = int(sv[0])
         kernel_name = "trace_kernel<WANT_INC=1,WITH_DET=0>"
@@ -457,7 +461,7 @@ def run_b200(args, w, oes):
     else:
         for e0, e1 in kev:
             e0.record()
-            chain.trace(src, ignore_defects=True, history=False, want_incidence=True, want_central=False, out=out)
+            chain.trace(src, ignore_defects=ign, history=False, want_incidence=True, want_central=False, out=out)
             e1.record()
     torch.cuda.synchronize()
     k_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in kev]))
@@ -479,12 +483,12 @@ def run_b200(args, w, oes):
         h2d = 8 * len(src._names) * count + (24 if src.origin is not None else 0)
         d2h = 8 * (_cabi.MOMENTS_LEN + _cabi.CENTRAL_LEN) + 8 * _cabi.DETECTOR_DOUBLES
         for _ in range(2):
-            chain.run_host(host, distance, peer=peer)
+            chain.run_host(host, distance, ignore_defects=ign, peer=peer)
         barrier()
         t0 = time.perf_counter()
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(e2e_steps):
-            mom_h, cen_h, det_h = chain.run_host(host, distance, peer=peer)
+            mom_h, cen_h, det_h = chain.run_host(host, distance, ignore_defects=ign, peer=peer)
         torch.cuda.synchronize()
         t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
