@@ -165,3 +165,18 @@ def test_extended_source_matches_reference(case):
     assert np.array_equal(num, z[case + "_num"])
     assert np.max(np.abs(P - z[case + "_P"])) <= 1e-14 and np.max(np.abs(U - z[case + "_U"])) <= 1e-14
     assert np.max(np.abs(orc.gaussian_intensity(P, U) - z[case + "_I"])) <= 1e-12
+
+
+@pytest.mark.parametrize("key,tag,ignore", [("toroid", "out", False), ("sphere_cx", "out", False),
+                                            ("parabola_hole", "out", False), ("mask", "out", True),
+                                            ("sphere_zernike", "out", False), ("sphere_zernike", "outign", True)])
+def test_oracle_element_frame_functions_match_reference(key, tag, ignore):
+    """The oracle on rays given in the optic's own frame (one element whose frame is the lab frame) against
+    ReflectionMirrorRayList / TransmitMaskRayList of the unmodified reference (tests/golden/raylist.npz)."""
+    import bench
+    from golden_util import RayListGolden, compare_bundle
+    g = RayListGolden()
+    P, U, num = g.source(key)
+    els = bench._oracle_elements([g.identity_element(key)])
+    res = orc.trace_chain(P, U, els, ignore_defects=ignore, numbers=num)[0]
+    compare_bundle("raylist_" + key, 0, g.out(key, tag), res["number"], res["P"], res["U"], res["path"], res["incidence"])
