@@ -241,7 +241,10 @@ def FindOptimalDistance(Detector, RayList, OptFor="intensity", Amplitude=None, P
     first = Detector.get_distance()
     if verbose:
         print(f"Searching optimal detector position for *{OptFor}* ...", end="", flush=True)
-    s, spot, dur, amp = optimal_shift_from_scan(scan, first, st["SpotSizeSD"], st["NA"], OptFor, Amplitude, Precision,
+    # the default Amplitude uses the angle to the bundle's OWN central ray (:424-434), which differs from the
+    # detector's reference axis for a manually placed / tilted detector
+    na = ReturnNumericalAperture(RayList, 1) if Amplitude is None else st["NA"]
+    s, spot, dur, amp = optimal_shift_from_scan(scan, first, st["SpotSizeSD"], na, OptFor, Amplitude, Precision,
                                                 IntensityWeighted)
     moving = Detector.copy_detector()
     moving.shiftByDistance(float(s))

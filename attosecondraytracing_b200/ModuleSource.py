@@ -162,3 +162,37 @@ def synthetic_source(SourceProperties, first_optic_support=None, device=None, fi
     if intensity:
         ApplyGaussianIntensityToRayList(b, 1 / np.e**2, group=group)
     return b
+
+
+def source_descriptor(SourceProperties, first_optic_support=None, first=0, count=None, stride=1, intensity=True):
+    """The ArtSourceDesc (include/art_b200.h) of the bundle `synthetic_source` would build: what
+    `DeviceChain.run_source` hands to the library instead of rays -- the reference's host input is this
+    description too (SourceProperties, ART/ModuleProcessing.py:58-79)."""
+    div = SourceProperties["Divergence"]
+    size = SourceProperties["SourceSize"]
+    n = int(SourceProperties["NumberRays"])
+    d = _cabi.ArtSourceDesc()
+    d.intensity = 1 if intensity else 0
+    d.intensity_fraction = 1 / np.e**2
+    d.axis = (1.0, 0.0, 0.0)
+    d.origin = (0.0, 0.0, 0.0)
+    d.first, d.stride = int(first), int(stride)
+    if div == 0:
+        if size == 0:
+            sup = first_optic_support
+            radius = 0.5 * min(sup.dimX, sup.dimY) if hasattr(sup, "dimX") else sup.radius
+        else:
+            radius = size / 2
+        d.kind, d.n_total, d.rho = 1, n, float(radius)
+        n_rays = n - 1  # PlaneWaveDisk emits NbRays - 1 rays
+    elif size != 0:
+        n_ps = min(max(30, int(250 * size)), int(n / 300))
+        per = max(300, int(n / n_ps))
+        d.kind, d.n_total, d.rho = 2, n_ps * per, float(np.tan(div))
+        d.n_point_sources, d.rays_per_source, d.source_radius = n_ps, per, size / 2
+        n_rays = n_ps * per
+    else:
+        d.kind, d.n_total, d.rho = 0, n, float(np.tan(div))
+        n_rays = n
+    d.count = _slice_count(n_rays, first, stride) if count is None else int(count)
+    return d

@@ -86,6 +86,18 @@ class ArtDetector(C.Structure):
 DETECTOR_DOUBLES = C.sizeof(ArtDetector) // 8  # 23
 
 
+class ArtSourceDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("intensity", C.c_int32), ("n_total", C.c_int64), ("first", C.c_int64),
+        ("count", C.c_int64), ("stride", C.c_int64), ("rho", C.c_double), ("axis", C.c_double * 3),
+        ("origin", C.c_double * 3), ("n_point_sources", C.c_int64), ("rays_per_source", C.c_int64),
+        ("source_radius", C.c_double), ("intensity_fraction", C.c_double),
+    ]
+
+
+E_PEER_TIMEOUT = -5  # ART_E_PEER_TIMEOUT
+
+
 HIST_FIXED_ONE = 67108864.0  # ART_HIST_FIXED_ONE
 
 
@@ -154,6 +166,9 @@ _SIGNATURES = {
     "art_run_host_sharded": (C.c_int32, [C.c_void_p, C.POINTER(ArtBundleView), C.POINTER(ArtBundleView), C.c_uint32,
                                          C.c_double, C.POINTER(ArtDetector), c_double_p, c_double_p,
                                          C.POINTER(ArtDetector), C.POINTER(C.c_uint64), C.c_int32, C.c_int32]),
+    "art_run_source_host": (C.c_int32, [C.c_void_p, C.POINTER(ArtSourceDesc), C.c_uint32, C.c_double,
+                                        C.POINTER(ArtDetector), c_double_p, c_double_p, C.POINTER(ArtDetector),
+                                        C.POINTER(C.c_uint64), C.c_int32, C.c_int32]),
     "art_trace_host": (C.c_int32, [C.c_void_p, C.POINTER(ArtBundleView), C.POINTER(ArtBundleView),
                                    C.POINTER(ArtBundleView), C.c_uint32]),
     "art_probe_fp64": (C.c_int32, [c_double_p]),
@@ -178,9 +193,10 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        sizes = (C.c_int32 * 5)()
+        sizes = (C.c_int32 * 6)()
         L.art_abi_sizes(sizes)
-        mine = [C.sizeof(t) for t in (ArtElementDesc, ArtZernikeDesc, ArtBundleView, ArtDetector, ArtGridMapDesc)]
+        mine = [C.sizeof(t) for t in (ArtElementDesc, ArtZernikeDesc, ArtBundleView, ArtDetector, ArtGridMapDesc,
+                                      ArtSourceDesc)]
         if list(sizes) != mine:
             raise RuntimeError(f"struct layout mismatch between _cabi.py {mine} and libart_b200.so {list(sizes)}")
         _lib = L

@@ -13,8 +13,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libart_b200.so")
 SOURCES = ["art_b200.cu"]
-DEPENDS = ["art_b200.cu", "art_kernels.cuh", "art_device.cuh", "art_lowering.h",
-           os.path.join("..", "..", "include", "art_b200.h")]
+
+
+def depends():
+    """Every file the library is compiled from: all of csrc/ plus the public header."""
+    import glob
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+                  glob.glob(os.path.join(CSRC, "*.h"))) + [os.path.join(HERE, "..", "include", "art_b200.h")]
+
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -30,7 +36,7 @@ def stale():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPENDS)
+    return any(os.path.getmtime(d) > t for d in depends())
 
 
 def build(force=False, verbose=False):

@@ -2,6 +2,9 @@
 // host-side lowering of scene descriptions, launch configuration and the host-buffer entry point.
 // All ray arithmetic happens in the kernels of art_kernels.cuh; there is no CPU ray path here.
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <cstdio>
 #include <cstdlib>
 #include <new>
@@ -46,7 +49,8 @@ struct HostWorkspace {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev[8] = {};
-  double* pinned = nullptr;   // results staging: moments | central | detector
+  double* pinned = nullptr;   // results staging: moments | central | detector | peer epoch, status
+  double* src_state = nullptr;  // device source state of art_run_source_host (SRC_STATE_LEN doubles)
 };
 
 struct ArtChain {
@@ -117,13 +121,14 @@ extern "C" int32_t art_version(void) { return ART_B200_VERSION; }
 extern "C" const char* art_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t art_launch_count(void) { return g_launches.load(); }
 
-extern "C" int32_t art_abi_sizes(int32_t sizes_out[5]) {
+extern "C" int32_t art_abi_sizes(int32_t sizes_out[6]) {
   if (!sizes_out) return fail(ART_E_INVALID, "sizes_out is NULL");
   sizes_out[0] = (int32_t)sizeof(ArtElementDesc);
   sizes_out[1] = (int32_t)sizeof(ArtZernikeDesc);
   sizes_out[2] = (int32_t)sizeof(ArtBundleView);
   sizes_out[3] = (int32_t)sizeof(ArtDetector);
   sizes_out[4] = (int32_t)sizeof(ArtGridMapDesc);
+  sizes_out[5] = (int32_t)sizeof(ArtSourceDesc);
   return ART_OK;
 }
 
@@ -173,6 +178,7 @@ extern "C" int32_t art_chain_destroy(ArtChain* c) {
   cudaFree(c->d_det);
   cudaFree(c->ws.cols);
   cudaFree(c->ws.alive);
+  cudaFree(c->ws.src_state);
   if (c->ws.pinned) cudaFreeHost(c->ws.pinned);
   for (auto& e : c->ws.ev)
     if (e) cudaEventDestroy(e);
@@ -448,22 +454,32 @@ extern "C" int32_t art_detector_autoplace(const double* central, double distance
   return ART_OK;
 }
 
-// reduction scratch for calls that come without a chain (stand-alone Detector objects): one
-// lazily grown buffer per device
-static double* g_scratch[64] = {};
-static size_t g_scratch_rows[64] = {};
-static int32_t global_scratch(size_t rows, double** out) {
+// reduction scratch for calls that come without a chain (stand-alone Detector objects): one lazily
+// grown buffer per (device, stream), so concurrent callers on different streams or host threads never
+// share partial rows; the table itself is guarded by a mutex.  Buffers live until the process ends.
+struct ScratchSlot {
+  double* ptr = nullptr;
+  size_t rows = 0;
+};
+static std::mutex g_scratch_mutex;
+static std::map<std::pair<int, void*>, ScratchSlot> g_scratch;
+static int32_t global_scratch(size_t rows, void* stream, double** out) {
   int dev = 0;
   ART_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return fail(ART_E_UNSUPPORTED, "device index above 63");
-  if (g_scratch_rows[dev] < rows) {
-    if (g_scratch[dev]) ART_CUDA(cudaFree(g_scratch[dev]));
-    g_scratch[dev] = nullptr;
-    g_scratch_rows[dev] = 0;
-    ART_CUDA(cudaMalloc(&g_scratch[dev], rows * PLEN_FUSED * sizeof(double)));
-    g_scratch_rows[dev] = rows;
+  std::lock_guard<std::mutex> lock(g_scratch_mutex);
+  ScratchSlot& s = g_scratch[std::make_pair(dev, stream)];
+  if (s.rows < rows) {
+    if (s.ptr) {
+      // kernels still reading the old buffer were launched on this very stream: order the free behind them
+      ART_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+      ART_CUDA(cudaFree(s.ptr));
+    }
+    s.ptr = nullptr;
+    s.rows = 0;
+    ART_CUDA(cudaMalloc(&s.ptr, rows * PLEN_FUSED * sizeof(double)));
+    s.rows = rows;
   }
-  *out = g_scratch[dev];
+  *out = s.ptr;
   return ART_OK;
 }
 
@@ -481,7 +497,7 @@ extern "C" int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bu
     ART_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     tmp.sm_count = sms;
     tmp.partial_rows = (size_t)sms * 8 + (size_t)n_variants + 8;
-    int32_t rc = global_scratch(tmp.partial_rows, &tmp.d_partials);
+    int32_t rc = global_scratch(tmp.partial_rows, stream, &tmp.d_partials);
     if (rc) return rc;
     chain = &tmp;
   }
@@ -567,7 +583,7 @@ extern "C" int32_t art_detector_scan_moments(ArtChain* chain, const ArtBundleVie
     ART_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     tmp.sm_count = sms;
     tmp.partial_rows = (size_t)sms * 8 + (size_t)n_variants + 8;
-    int32_t rc = global_scratch(tmp.partial_rows, &tmp.d_partials);
+    int32_t rc = global_scratch(tmp.partial_rows, stream, &tmp.d_partials);
     if (rc) return rc;
     chain = &tmp;
   }
@@ -603,7 +619,7 @@ extern "C" int32_t art_peer_exchange(const uint64_t* peer_bufs, int32_t rank, in
   if (!peer_bufs || !rows) return fail(ART_E_INVALID, "NULL argument");
   if (world < 1 || world > ART_PEER_MAX_RANKS || rank < 0 || rank >= world)
     return fail(ART_E_INVALID, "rank / world out of range");
-  if (kind != 0 && kind != 1) return fail(ART_E_INVALID, "kind must be 0 (central) or 1 (moments)");
+  if (kind < 0 || kind > 2) return fail(ART_E_INVALID, "kind must be 0 (central), 1 (moments) or 2 (source extents)");
   if (n_variants < 1 || n_variants > ART_PEER_MAX_VARIANTS)
     return fail(ART_E_INVALID, "n_variants must be in [1, ART_PEER_MAX_VARIANTS]");
   PeerArgs a;
@@ -697,6 +713,7 @@ extern "C" int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t fi
   rotation_from_to(ez, axis, a.rot);  // RotationRayList(RayList, ez, Axis), ART/ModuleSource.py:79,167
   for (int i = 0; i < 3; ++i) a.origin[i] = origin[i];
   a.b = to_dev(bundle);
+  a.partials = nullptr;
   long long bx = (count + TPB - 1) / TPB;
   if (bx < 1) bx = 1;
   if (bx > 148 * 16) bx = 148 * 16;
@@ -724,6 +741,7 @@ extern "C" int32_t art_source_extents(const ArtBundleView* bundle, const double 
   a.mode = 0;
   a.scale = 1.0;
   a.lnf = 0.0;
+  a.state = nullptr;
   a.partials = g_ext_partials[dev];
   cudaStream_t st = (cudaStream_t)stream;
   intensity_kernel<<<kIntensityBlocks, TPB, 0, st>>>(a);
@@ -749,6 +767,7 @@ extern "C" int32_t art_source_intensity(const ArtBundleView* bundle, const doubl
   a.mode = mode;
   a.scale = scale;
   a.lnf = -0.5 * std::log(fraction);
+  a.state = nullptr;
   a.partials = nullptr;
   intensity_kernel<<<kIntensityBlocks, TPB, 0, (cudaStream_t)stream>>>(a);
   ART_LAUNCHED();
@@ -764,19 +783,92 @@ static int32_t ensure_workspace(ArtChain* c, size_t n) {
     ART_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     ART_CUDA(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
     for (auto& e : w.ev) ART_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    ART_CUDA(cudaMallocHost(&w.pinned, sizeof(double) * (ART_MOMENTS_LEN + ART_CENTRAL_LEN) + sizeof(ArtDetector)));
+    ART_CUDA(cudaMallocHost(&w.pinned, sizeof(double) * (ART_MOMENTS_LEN + ART_CENTRAL_LEN) + sizeof(ArtDetector) +
+                                          2 * sizeof(uint64_t)));
   }
-  if (n > w.cap_n) {
+  if (n > w.cap_n || !w.cols) {
     cudaFree(w.cols);
     cudaFree(w.alive);
     w.cols = nullptr;
     w.alive = nullptr;
     w.cap_n = 0;
-    const size_t cap = (n + 1023) & ~size_t(1023);
+    const size_t cap = ((n > 0 ? n : 1) + 1023) & ~size_t(1023);  // n == 0 (an empty shard) still gets columns
     ART_CUDA(cudaMalloc(&w.cols, sizeof(double) * 15 * cap));
     ART_CUDA(cudaMalloc(&w.alive, cap));
     w.cap_n = cap;
   }
+  return ART_OK;
+}
+
+// The part of a host-level run that follows the trace: all-reduce of the central sums + Detector.autoplace
+// (or the caller's detector), detector moments of the stored final bundle, merge over the ranks, results
+// (and optionally the final bundle) back to the host.  c->d_central holds this rank's folded central sums.
+static int32_t statistics_tail(ArtChain* c, const ArtBundleView* dout_p, size_t n, bool want_inc,
+                               const ArtBundleView* out_final_host, double distance, const ArtDetector* manual_det,
+                               double* moments_host, double* central_host, ArtDetector* det_host,
+                               const uint64_t* peer_bufs, int32_t rank, int32_t world, int exchanges_before = 0) {
+  HostWorkspace& w = c->ws;
+  const size_t cap = w.cap_n;
+  auto col = [&](int j) { return w.cols + (size_t)j * cap; };
+  cudaStream_t st = w.stream;
+  const ArtBundleView& dout = *dout_p;
+  int32_t rc = ART_OK;
+  // sharded bundle: the central sums of all ranks are added (and the detector placed) inside one kernel over
+  // peer memory, likewise the moments rows below
+  if (manual_det) {
+    ART_CUDA(cudaMemcpyAsync(c->d_det, manual_det, sizeof(ArtDetector), cudaMemcpyHostToDevice, st));
+    if (peer_bufs) {
+      rc = art_peer_exchange(peer_bufs, rank, world, 0, 1, c->d_central, distance, nullptr, st);
+      if (rc) return rc;
+    }
+  } else if (peer_bufs) {
+    rc = art_peer_exchange(peer_bufs, rank, world, 0, 1, c->d_central, distance, c->d_det, st);
+    if (rc) return rc;
+  } else {
+    rc = art_detector_autoplace(c->d_central, distance, 1, c->d_det, st);
+    if (rc) return rc;
+  }
+  rc = art_detector_moments(c, &dout, 1, c->d_det, nullptr, nullptr, nullptr, c->d_moments, st);
+  if (rc) return rc;
+  if (peer_bufs) {
+    rc = art_peer_exchange(peer_bufs, rank, world, 1, 1, c->d_moments, 0.0, nullptr, st);
+    if (rc) return rc;
+  }
+
+  double* pm = w.pinned;
+  double* pc = pm + ART_MOMENTS_LEN;
+  ArtDetector* pd = reinterpret_cast<ArtDetector*>(pc + ART_CENTRAL_LEN);
+  ART_CUDA(cudaMemcpyAsync(pm, c->d_moments, sizeof(double) * ART_MOMENTS_LEN, cudaMemcpyDeviceToHost, st));
+  ART_CUDA(cudaMemcpyAsync(pc, c->d_central, sizeof(double) * ART_CENTRAL_LEN, cudaMemcpyDeviceToHost, st));
+  ART_CUDA(cudaMemcpyAsync(pd, c->d_det, sizeof(ArtDetector), cudaMemcpyDeviceToHost, st));
+  uint64_t* pw = reinterpret_cast<uint64_t*>(pd + 1);  // {epoch, status} of this rank's exchange buffer
+  pw[0] = pw[1] = 0;
+  if (peer_bufs) {
+    const double* base = reinterpret_cast<const double*>(peer_bufs[rank]);
+    const uint64_t* words = reinterpret_cast<const uint64_t*>(base + (size_t)2 * world * PEER_MAX_DOUBLES);
+    ART_CUDA(cudaMemcpyAsync(pw, words + world, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  }
+  if (out_final_host && n) {
+    double* hdst[8] = {out_final_host->px, out_final_host->py, out_final_host->pz, out_final_host->ux,
+                       out_final_host->uy, out_final_host->uz, out_final_host->path,
+                       want_inc ? out_final_host->incidence : nullptr};
+    for (int j = 0; j < 8; ++j)
+      if (hdst[j]) ART_CUDA(cudaMemcpyAsync(hdst[j], col(7 + j), sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (out_final_host->alive)
+      ART_CUDA(cudaMemcpyAsync(out_final_host->alive, w.alive, n, cudaMemcpyDeviceToHost, st));
+  }
+  ART_CUDA(cudaStreamSynchronize(st));
+  // A peer that did not arrive leaves the rows of this rank unreduced (peer_exchange_kernel): the status word
+  // then holds the epoch that timed out.  This call used the epochs pw[0] - 1 (central sums) and pw[0] (moments)
+  // and `exchanges_before` earlier ones.
+  if (peer_bufs && pw[1] != 0 && pw[1] + 1 + (uint64_t)exchanges_before >= pw[0])
+    return fail(ART_E_PEER_TIMEOUT, "peer-memory exchange timed out at epoch " + std::to_string(pw[1]) +
+                                        ": a rank did not arrive; the statistics of this call are not reduced");
+  if (moments_host)
+    for (int j = 0; j < ART_MOMENTS_LEN; ++j) moments_host[j] = pm[j];
+  if (central_host)
+    for (int j = 0; j < ART_CENTRAL_LEN; ++j) central_host[j] = pc[j];
+  if (det_host) *det_host = *pd;
   return ART_OK;
 }
 
@@ -858,50 +950,8 @@ static int32_t run_host_impl(ArtChain* c, const ArtBundleView* in_host, const Ar
   }
   fold_kernel<<<1, TPB, 0, st>>>(c->d_partials, launched_chunks * chunk_blocks, 0, c->d_central, nullptr);
   ART_LAUNCHED();
-  // sharded bundle: the central sums of all ranks are added (and the detector placed) inside one kernel over
-  // peer memory, likewise the moments rows below
-  if (manual_det) {
-    ART_CUDA(cudaMemcpyAsync(c->d_det, manual_det, sizeof(ArtDetector), cudaMemcpyHostToDevice, st));
-    if (peer_bufs) {
-      rc = art_peer_exchange(peer_bufs, rank, world, 0, 1, c->d_central, distance, nullptr, st);
-      if (rc) return rc;
-    }
-  } else if (peer_bufs) {
-    rc = art_peer_exchange(peer_bufs, rank, world, 0, 1, c->d_central, distance, c->d_det, st);
-    if (rc) return rc;
-  } else {
-    rc = art_detector_autoplace(c->d_central, distance, 1, c->d_det, st);
-    if (rc) return rc;
-  }
-  rc = art_detector_moments(c, &dout, 1, c->d_det, nullptr, nullptr, nullptr, c->d_moments, st);
-  if (rc) return rc;
-  if (peer_bufs) {
-    rc = art_peer_exchange(peer_bufs, rank, world, 1, 1, c->d_moments, 0.0, nullptr, st);
-    if (rc) return rc;
-  }
-
-  double* pm = w.pinned;
-  double* pc = pm + ART_MOMENTS_LEN;
-  ArtDetector* pd = reinterpret_cast<ArtDetector*>(pc + ART_CENTRAL_LEN);
-  ART_CUDA(cudaMemcpyAsync(pm, c->d_moments, sizeof(double) * ART_MOMENTS_LEN, cudaMemcpyDeviceToHost, st));
-  ART_CUDA(cudaMemcpyAsync(pc, c->d_central, sizeof(double) * ART_CENTRAL_LEN, cudaMemcpyDeviceToHost, st));
-  ART_CUDA(cudaMemcpyAsync(pd, c->d_det, sizeof(ArtDetector), cudaMemcpyDeviceToHost, st));
-  if (out_final_host && n) {
-    double* hdst[8] = {out_final_host->px, out_final_host->py, out_final_host->pz, out_final_host->ux,
-                       out_final_host->uy, out_final_host->uz, out_final_host->path,
-                       want_inc ? out_final_host->incidence : nullptr};
-    for (int j = 0; j < 8; ++j)
-      if (hdst[j]) ART_CUDA(cudaMemcpyAsync(hdst[j], col(7 + j), sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-    if (out_final_host->alive)
-      ART_CUDA(cudaMemcpyAsync(out_final_host->alive, w.alive, n, cudaMemcpyDeviceToHost, st));
-  }
-  ART_CUDA(cudaStreamSynchronize(st));
-  if (moments_host)
-    for (int j = 0; j < ART_MOMENTS_LEN; ++j) moments_host[j] = pm[j];
-  if (central_host)
-    for (int j = 0; j < ART_CENTRAL_LEN; ++j) central_host[j] = pc[j];
-  if (det_host) *det_host = *pd;
-  return ART_OK;
+  return statistics_tail(c, &dout, n, want_inc, out_final_host, distance, manual_det, moments_host, central_host,
+                         det_host, peer_bufs, rank, world);
 }
 
 extern "C" int32_t art_run_host(ArtChain* c, const ArtBundleView* in_host, const ArtBundleView* out_final_host,
@@ -920,6 +970,129 @@ extern "C" int32_t art_run_host_sharded(ArtChain* c, const ArtBundleView* in_hos
     return fail(ART_E_INVALID, "rank / world out of range");
   return run_host_impl(c, in_host, out_final_host, flags, distance, manual_det, moments_host, central_host, det_host,
                        peer_bufs, rank, world);
+}
+
+// -------------------------------------------------------------------------------------------------
+// descriptor-driven end-to-end entry point: the reference's real host input is SourceProperties
+// (ART/ModuleProcessing.py:58-79), not ray columns
+// -------------------------------------------------------------------------------------------------
+extern "C" int32_t art_run_source_host(ArtChain* c, const ArtSourceDesc* src, uint32_t flags, double distance,
+                                       const ArtDetector* manual_det, double* moments_host, double* central_host,
+                                       ArtDetector* det_host, const uint64_t* peer_bufs, int32_t rank, int32_t world) {
+  if (!c || !src) return fail(ART_E_INVALID, "NULL argument");
+  if (src->kind < 0 || src->kind > 2)
+    return fail(ART_E_INVALID, "kind must be 0 (point source), 1 (plane wave) or 2 (extended source)");
+  if (src->kind == 2 && (src->n_point_sources < 1 || src->rays_per_source < 1 ||
+                         src->n_point_sources * src->rays_per_source != src->n_total))
+    return fail(ART_E_INVALID, "extended source: n_total must equal n_point_sources * rays_per_source");
+  if (src->n_total < 1 || src->first < 0 || src->count < 0 || src->stride < 1 ||
+      (src->count > 0 && src->first + (src->count - 1) * src->stride >= src->n_total))
+    return fail(ART_E_INVALID, "bad index range");
+  if (peer_bufs && (world < 1 || world > ART_PEER_MAX_RANKS || rank < 0 || rank >= world))
+    return fail(ART_E_INVALID, "rank / world out of range");
+  ART_CUDA(cudaSetDevice(c->device));
+  const size_t n = (size_t)src->count;
+  int32_t rc = ensure_workspace(c, n);
+  if (rc) return rc;
+  HostWorkspace& w = c->ws;
+  const size_t cap = w.cap_n;
+  auto col = [&](int j) { return w.cols + (size_t)j * cap; };
+  cudaStream_t st = w.stream;
+  if (!w.src_state) ART_CUDA(cudaMalloc(&w.src_state, sizeof(double) * SRC_STATE_LEN));
+
+  const bool point = src->kind == 0;  // one origin for all rays: three single doubles instead of three columns
+  const bool weighted = src->intensity != 0;
+  ArtBundleView din = {};
+  din.n = (int64_t)n;
+  din.px = col(0); din.py = col(1); din.pz = col(2);
+  din.ux = col(3); din.uy = col(4); din.uz = col(5);
+  din.intensity = weighted ? col(6) : nullptr;
+  if (point) flags |= ART_TRACE_UNIFORM_POINT;
+  else flags &= ~ART_TRACE_UNIFORM_POINT;
+
+  // K0: the Vogel-spiral bundle in closed form, straight into the workspace columns, with the sums of the
+  // directions that ApplyGaussianIntensityToRayList's axis needs
+  SourceArgs a;
+  a.kind = src->kind;
+  a.n_total = src->n_total;
+  a.first = src->first;
+  a.count = src->count;
+  a.stride = src->stride;
+  a.per = src->kind == 2 ? src->rays_per_source : 1;
+  a.n_ps = src->kind == 2 ? src->n_point_sources : 1;
+  a.ps_radius = src->source_radius;
+  a.rho = src->rho;
+  const double ez[3] = {0.0, 0.0, 1.0};
+  rotation_from_to(ez, src->axis, a.rot);
+  for (int i = 0; i < 3; ++i) a.origin[i] = src->origin[i];
+  a.b = to_dev(&din);
+  a.b.inten = nullptr;
+  if (point) {
+    a.b.px = a.b.py = a.b.pz = nullptr;
+    for (int j = 0; j < 3; ++j)
+      ART_CUDA(cudaMemcpyAsync(col(j), &src->origin[j], sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  long long bx = ((long long)n + TPB - 1) / TPB;
+  if (bx < 1) bx = 1;
+  if (bx > (long long)c->sm_count * 8) bx = (long long)c->sm_count * 8;
+  a.partials = weighted ? c->d_partials : nullptr;
+  source_kernel<<<(unsigned)bx, TPB, 0, st>>>(a);
+  ART_LAUNCHED();
+  int exchanges = 0;
+  if (weighted) {
+    // axis = normalised mean direction of the WHOLE bundle; then the largest angle to it / largest |P|
+    fold_kernel<<<1, TPB, 0, st>>>(c->d_partials, (int)bx, 0, c->d_central, nullptr);
+    ART_LAUNCHED();
+    if (peer_bufs) {
+      rc = art_peer_exchange(peer_bufs, rank, world, 0, 1, c->d_central, 0.0, nullptr, st);
+      if (rc) return rc;
+      ++exchanges;
+    }
+    source_axis_kernel<<<1, 32, 0, st>>>(c->d_central, w.src_state);
+    ART_LAUNCHED();
+    IntensityArgs ia;
+    ia.b = to_dev(&din);
+    if (point) ia.b.px = ia.b.py = ia.b.pz = nullptr;  // |P| is the same for all rays; a diverging bundle uses angles
+    ia.n = (long long)n;
+    for (int i = 0; i < 3; ++i) ia.axis[i] = 0.0;
+    ia.pass = 0;
+    ia.mode = 0;
+    ia.scale = 1.0;
+    ia.lnf = 0.0;
+    ia.state = w.src_state;
+    ia.partials = c->d_partials;
+    const int iblocks = c->sm_count * 4;
+    intensity_kernel<<<iblocks, TPB, 0, st>>>(ia);
+    ART_LAUNCHED();
+    extents_fold_kernel<<<1, 32, 0, st>>>(c->d_partials, iblocks, w.src_state + 3);
+    ART_LAUNCHED();
+    if (peer_bufs) {
+      rc = art_peer_exchange(peer_bufs, rank, world, 2, 1, w.src_state + 3, 0.0, nullptr, st);
+      if (rc) return rc;
+      ++exchanges;
+    }
+    double fraction = src->intensity_fraction;
+    if (!(fraction > 0.0 && fraction < 1.0)) fraction = 0.1353352832366127;  // 1/e^2, ART/ModuleSource.py:233-238
+    ia.pass = 1;
+    ia.lnf = -0.5 * std::log(fraction);
+    ia.partials = nullptr;
+    intensity_kernel<<<iblocks, TPB, 0, st>>>(ia);
+    ART_LAUNCHED();
+  }
+
+  ArtBundleView dout = {};
+  dout.n = (int64_t)n;
+  dout.px = col(7); dout.py = col(8); dout.pz = col(9);
+  dout.ux = col(10); dout.uy = col(11); dout.uz = col(12);
+  dout.path = col(13);
+  dout.alive = w.alive;
+  ArtBundleView tout = dout;
+  dout.intensity = din.intensity;
+  rc = launch_trace(c, 0, 1, &din, &tout, nullptr, flags | ART_TRACE_NO_INCIDENCE, nullptr, nullptr, nullptr, nullptr,
+                    c->d_central, nullptr, st);
+  if (rc) return rc;
+  return statistics_tail(c, &dout, n, false, nullptr, distance, manual_det, moments_host, central_host, det_host,
+                         peer_bufs, rank, world, exchanges);
 }
 
 // RayTracingCalculation for a host caller: host columns in, the bundle after every element (and / or

@@ -1069,7 +1069,8 @@ constexpr int PEER_MAX_DOUBLES = ART_PEER_MAX_VARIANTS * ART_MOMENTS_LEN;
 struct PeerArgs {
   unsigned long long bufs[ART_PEER_MAX_RANKS];  // device address of each rank's exchange buffer
   int rank, world;
-  int kind;            // 0: central rows (all sums), optionally followed by autoplace; 1: moments rows (sum/min/max)
+  int kind;            // 0: central rows (all sums), optionally followed by autoplace; 1: moments rows (sum/min/max);
+                       // 2: source extents rows (2 doubles: max angle, max |P|; max)
   int n_variants;
   double* rows;        // in / out, n_variants x (ART_CENTRAL_LEN | ART_MOMENTS_LEN)
   double distance;     // kind 0 with det_out
@@ -1088,7 +1089,7 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
   __shared__ unsigned long long sEpoch;
   __shared__ int sFail;
   const int tid = threadIdx.x;
-  const int rlen = a.kind == 0 ? ART_CENTRAL_LEN : ART_MOMENTS_LEN;
+  const int rlen = a.kind == 0 ? ART_CENTRAL_LEN : (a.kind == 1 ? ART_MOMENTS_LEN : 2);
   const int len = a.n_variants * rlen;
   auto base = [&](int owner) { return reinterpret_cast<double*>(a.bufs[owner]); };
   auto words = [&](int owner) {
@@ -1129,7 +1130,7 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
   }
   // 3. the same reduction in rank order on every rank (ld.global.cg: the slots are written by peers)
   for (int j = tid; j < len; j += blockDim.x) {
-    const int op = a.kind == 0 ? 0 : moment_op(j % ART_MOMENTS_LEN);
+    const int op = a.kind == 0 ? 0 : (a.kind == 1 ? moment_op(j % ART_MOMENTS_LEN) : 2);
     const double* src = base(a.rank) + half + j;
     double x = __ldcg(src);
     for (int r = 1; r < a.world; ++r) x = red_any(op, x, __ldcg(src + (size_t)r * PEER_MAX_DOUBLES));
@@ -1211,9 +1212,13 @@ struct SourceArgs {
   double rot[9];
   double origin[3];
   BundleDev b;
+  double* partials;  // null, or [block][PLEN_TRACE] rows in the central-sum layout: sum of the directions
+                     // (ART_C_SUX..SUZ) and the ray count (ART_C_N) -- what FindCentralRay needs for the axis
+                     // of ApplyGaussianIntensityToRayList (ART/ModuleSource.py:244)
 };
-__global__ void source_kernel(const SourceArgs a) {
+__global__ void __launch_bounds__(TPB) source_kernel(const SourceArgs a) {
   const double golden = 3.141592653589793 * (3.0 - sqrt(5.0));
+  double su[3] = {0.0, 0.0, 0.0}, cnt = 0.0;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.count;
        j += (long long)gridDim.x * blockDim.x) {
     const long long idx = a.first + j * a.stride;
@@ -1255,9 +1260,31 @@ __global__ void source_kernel(const SourceArgs a) {
     const double un = 1.0 / sqrt(fma(ux, ux, fma(uy, uy, uz * uz)));
     if (a.b.px) { a.b.px[j] = px; a.b.py[j] = py; a.b.pz[j] = pz; }
     a.b.ux[j] = ux * un; a.b.uy[j] = uy * un; a.b.uz[j] = uz * un;
+    su[0] += ux * un; su[1] += uy * un; su[2] += uz * un;
+    cnt += 1.0;
     if (a.b.path) a.b.path[j] = 0.0;
     if (a.b.alive) a.b.alive[j] = 1;
   }
+  if (a.partials) {  // launched with TPB threads per block in that case
+    __shared__ double sRed[NWARP * PLEN_TRACE];
+    double v[PLEN_TRACE];
+#pragma unroll
+    for (int j = 0; j < PLEN_TRACE; ++j) v[j] = 0.0;
+    v[ART_C_SUX] = su[0]; v[ART_C_SUY] = su[1]; v[ART_C_SUZ] = su[2]; v[ART_C_N] = cnt;
+    block_reduce_row<PLEN_TRACE>(v, [](int) { return 0; }, sRed, a.partials + (size_t)blockIdx.x * PLEN_TRACE);
+  }
+}
+
+// Source state kept on the device between the kernels of a descriptor-driven run (art_run_source_host):
+//   [0..2] axis = FindCentralRay(bundle).vector (normalised mean direction, ART/ModuleProcessing.py:464-482)
+//   [3]    largest angle(axis, ray)   [4] largest |ray point|     (ART/ModuleSource.py:244-258)
+constexpr int SRC_STATE_LEN = 8;
+__global__ void source_axis_kernel(const double* __restrict__ central_row, double* __restrict__ state) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double N = central_row[ART_C_N];
+  double m[3] = {central_row[ART_C_SUX] / N, central_row[ART_C_SUY] / N, central_row[ART_C_SUZ] / N};
+  const double nn = sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
+  for (int i = 0; i < 3; ++i) state[i] = m[i] / nn;  // Ray.vector setter normalises, ART/ModuleOpticalRay.py:85-90
 }
 
 // ApplyGaussianIntensityToRayList, ART/ModuleSource.py:219-261.
@@ -1272,19 +1299,27 @@ struct IntensityArgs {
   double scale;    // divergence or max distance
   double lnf;      // -0.5 * ln(fraction)
   double* partials;
+  const double* state;  // null, or the device source state: axis, mode and scale are taken from it
 };
 __global__ void __launch_bounds__(TPB) intensity_kernel(const IntensityArgs a) {
   __shared__ double sRed[NWARP * 2];
   double mx[2] = {0.0, 0.0};
+  double ax0 = a.axis[0], ax1 = a.axis[1], ax2 = a.axis[2], scale = a.scale;
+  int mode = a.mode;
+  if (a.state) {
+    ax0 = a.state[0]; ax1 = a.state[1]; ax2 = a.state[2];
+    mode = a.state[3] > 1e-12 ? 0 : 1;  // a diverging bundle is weighted by angle (ART/ModuleSource.py:247-249)
+    scale = mode == 0 ? a.state[3] : a.state[4];
+  }
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < a.n; i += (long long)gridDim.x * TPB) {
-    const double ang = unit_angle(a.axis[0], a.axis[1], a.axis[2], a.b.ux[i], a.b.uy[i], a.b.uz[i]);
+    const double ang = unit_angle(ax0, ax1, ax2, a.b.ux[i], a.b.uy[i], a.b.uz[i]);
     const double px = a.b.px ? a.b.px[i] : 0.0, py = a.b.px ? a.b.py[i] : 0.0, pz = a.b.px ? a.b.pz[i] : 0.0;
     const double dist = sqrt(fma(px, px, fma(py, py, pz * pz)));
     if (a.pass == 0) {
       mx[0] = fmax(mx[0], ang);
       mx[1] = fmax(mx[1], dist);
     } else {
-      const double q = (a.mode == 0 ? tan(ang) : dist) / a.scale;
+      const double q = (mode == 0 ? tan(ang) : dist) / scale;
       a.b.inten[i] = exp(-2.0 * q * q * a.lnf);
     }
   }

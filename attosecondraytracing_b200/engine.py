@@ -286,6 +286,26 @@ class DeviceChain:
             out_host.invalidate()
         return mom, cen, det
 
+    def run_source(self, source_desc, distance, ignore_defects=True, manual_det=None, peer=None):
+        """Source DESCRIPTION in (an _cabi.ArtSourceDesc, see ModuleSource.source_descriptor), statistics out:
+        the library generates the bundle on the device, weights it, traces, autoplaces the detector and
+        reduces the moments inside one synchronous C call (art_run_source_host) -- what run_ART does for a
+        config whose source is given by SourceProperties (ARTmain.py:248-290).  Returns (moments, central,
+        det).  peer: a distributed.PeerExchange when the bundle is spread over the GPUs of the node (every
+        rank passes its own first / count / stride)."""
+        flags = _cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0
+        mom = np.empty(_cabi.MOMENTS_LEN)
+        cen = np.empty(_cabi.CENTRAL_LEN)
+        det = _cabi.ArtDetector()
+        dp = _cabi.c_double_p
+        md = C.byref(manual_det) if manual_det is not None else None
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().art_run_source_host(
+                self._handle, C.byref(source_desc), flags, float(distance), md, mom.ctypes.data_as(dp),
+                cen.ctypes.data_as(dp), C.byref(det), peer._ptrs if peer is not None else None,
+                peer.rank if peer is not None else 0, peer.world if peer is not None else 1))
+        return mom, cen, det
+
 
 # ----------------------------------------------------------------------------------------------
 # statistics from a moments row (host arithmetic on ~24 numbers)

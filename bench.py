@@ -1,16 +1,24 @@
 #!/usr/bin/env python
 """Benchmark of the ray-bundle hot path (BASELINE.json metric: ray-element interactions/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg4|cfg4def|cfg5]
+                    [--sub cfg2,cfg4,cfg4def,cfg5|none] [--impl reference]
 
 One "step" = one pass of the hot path over one synthetic bundle: trace through every element of the
-chain (fused kernel), all-reduce + autoplace of the detector, detector response + moments.  The
-default workload is BASELINE config 2 (examples/CONFIG_toroidal2f-2f.py, 10M rays per GPU).
-Scaling is weak: every rank traces its own 10M-ray slice of an N x 10M-ray bundle; the only
-collectives are the all-reduces of the central sums and of the moments.
+chain (fused kernel), all-reduce + autoplace of the detector, detector response + moments.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference
-(oracle/, all host cores) on a bounded sample of the same workload.
+The headline workload is BASELINE config 3 -- the north star's 2-toroid chain
+(examples/CONFIG_2toroidals_f-x-f.py: mask + two toroids), 12.5 M rays per GPU, i.e. BASELINE's 100 M rays
+on 8 GPUs; weak scaling: every rank traces its own round-robin share of an N x 12.5 M-ray bundle and the
+only exchanges are the central sums and the moments rows.  The other BASELINE configs are measured in the
+same run, device-timed the same way, and attached as `workloads`: cfg2 (one toroid, 10 M rays / GPU), cfg4
+(Zernike order 20, 50 M rays / GPU, both IgnoreDefects modes) and cfg5 (1024 telescope variants x 1 M rays,
+the VARIANT axis sharded over the GPUs: strong scaling).
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the UNMODIFIED reference (oracle/_ref, a
+byte-for-byte copy of ART v0.93 made by oracle/make_ref.py, driven through its own OEPlacement /
+RayTracingCalculation / Detector.autoplace / GetResultSummary) on all host cores on bounded samples of the
+same workload; that arm imports nothing from attosecondraytracing_b200.
 """
 from __future__ import annotations
 
@@ -29,6 +37,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 METRIC = "ray-element interactions/s"
 UNIT = "interactions/s"
+DEFAULT_SUBS = "cfg2,cfg4,cfg4def,cfg5"
 
 
 # ----------------------------------------------------------------------------------------------
@@ -36,23 +45,30 @@ UNIT = "interactions/s"
 # ----------------------------------------------------------------------------------------------
 def load_workload(name):
     import scenes as sc
-    w = dict(sc.WORKLOADS[name])
+    base = "cfg4" if name == "cfg4def" else name
+    w = dict(sc.WORKLOADS[base])
     w["name"] = name
+    w["defect_normals"] = name == "cfg4def"   # IgnoreDefects=False: cfg4's second mode
     w["scene_spec"] = sc.resolve(w["scene"])
+    if base == "cfg3":
+        w["rays"] = w["rays"] // 8            # 100 M rays over 8 GPUs -> 12.5 M per GPU
     return w
 
 
-def build_chain_elements(w):
-    """OpticalElement list of the workload's scene, aligned by the package's OEPlacement restatement."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from golden_util import build_optic
-    import attosecondraytracing_b200.ModuleProcessing as mp
+def workload_config(w, n):
+    """The `config` object: a function of the workload alone, so that both arms print the same one."""
     s = w["scene_spec"]
-    optics = [build_optic(o) for o in s["optics"]]
-    oes = mp.place_optical_elements(optics, s["distances"], s["incidences"], s["plane_angles"])
-    for op in s.get("post", []):
-        getattr(oes[op["element"]], op["op"])(op["value"])
-    return oes
+    cfg = {"workload": f"{w['name']}: {w['scene']} ({', '.join(o['kind'] for o in s['optics'])}), "
+                       f"{n} rays per GPU, detector autoplace at {s['detector_distance']} mm",
+           "rays_per_gpu": int(n), "elements": len(s["optics"]),
+           "l2": "inputs larger than L2 (source columns + stored final bundle of one step exceed 126 MB)",
+           "ignore_defects": not w["defect_normals"]}
+    if w.get("sweep"):
+        sw = w["sweep"]
+        cfg.update({"variants_total": sw["n"], "sweep": f"{sw['axis']} of element {sw['element']} over "
+                    f"[{sw['lo']}, {sw['hi']}] deg",
+                    "l2": "source bundle (32 MB) re-read per variant from L2 by design; per-variant outputs are 34 doubles"})
+    return cfg
 
 
 def source_properties(w, n_total):
@@ -117,8 +133,70 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU legs (oracle): the cpu_baseline object and --impl reference
+# CPU legs.  kind "reference": the literal reference from oracle/_ref in P worker processes;
+# kind "port": the numpy restatement oracle/art_oracle.py (labelled, never the headline).
 # ----------------------------------------------------------------------------------------------
+def reference_rate(w, n_total, workers, seconds, steps=1, warmup=0):
+    """Interactions/s of the unmodified reference (ref_runner.ReferencePool) on bounded samples of the
+    n_total-ray bundle: `steps` timed steps of about `seconds` each.  Returns (rate, sample, t_total, steps)."""
+    import ref_runner
+    pool = ref_runner.ReferencePool(w["scene"], n_total, workers)
+    try:
+        probe = 40 * workers
+        pool.step(probe)                                   # page-in
+        inter, wall = pool.step(probe)
+        per_ray = wall / (probe / workers)                 # seconds per ray per worker
+        sample = int(max(workers * 20, workers * seconds / per_ray))
+        for _ in range(warmup):
+            pool.step(sample)
+        inter_total, t_total = 0, 0.0
+        for _ in range(steps):
+            inter, wall = pool.step(sample)
+            inter_total += inter
+            t_total += wall
+    finally:
+        pool.close()
+    return inter_total / t_total, sample, t_total, steps
+
+
+def ref_root():
+    """Where the reference was imported from, relative to the repository when it is the travelling copy."""
+    import ref_runner
+    root = ref_runner.lr.REFERENCE_ROOT
+    return os.path.relpath(root, ROOT) if root.startswith(ROOT) else root
+
+
+def run_reference(args, w):
+    """--impl reference: the unmodified reference on all host cores; imports only oracle/."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import ref_runner
+    if not ref_runner.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref missing: run python oracle/make_ref.py "
+                          "where /root/reference exists"}), flush=True)
+        return
+    cores = os.cpu_count() or 1
+    n = int(args.rays or w["rays"])
+    n_total = n * args.gpus
+    # each step is a bounded sample: ~args.ref_seconds of work per core, so that the driver's
+    # --steps 20 --warmup 5 run ends within a few minutes
+    value, sample, t_total, steps = reference_rate(w, n_total, cores, args.ref_seconds, steps=args.steps,
+                                                   warmup=max(args.warmup - 1, 0) if args.ref_warm else 0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(w, n),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": f"{sample} rays (evenly spaced spiral indices) of the {n_total}-ray bundle per step: "
+                                   f"ART v0.93 OEPlacement + RayTracingCalculation + Detector.autoplace + "
+                                   f"GetResultSummary, unmodified ({ref_root()}), in {cores} processes"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def _oracle_elements(oes):
     """Oracle element dicts from the package's OpticalElement list (poses + optic parameters)."""
     els = []
@@ -146,157 +224,141 @@ def _oracle_elements(oes):
     return els
 
 
-def _cpu_source(sp, idx):
-    """Rows `idx` of the synthetic bundle for the CPU legs (oracle generators; the Gaussian weights are
-    normalised with the bundle axis = +x and the edge ray, which is what the full-bundle normalisation
-    amounts to for a Vogel spiral)."""
+def port_rate(w, oes, n_total, seconds):
+    """Interactions/s of the numpy oracle (the PORT) on one core, ~`seconds` of work."""
     import art_oracle as orc
-    n = sp["NumberRays"]
-    if sp["Divergence"] == 0:
-        radius = sp["SourceSize"] / 2
-        P, U, num = orc.plane_wave_disk(np.zeros(3), orc.EX, radius, n, idx)
-        inten = np.exp(-2 * (orc.norm(P) / radius) ** 2)
-    else:
-        P, U, num = orc.point_source(np.zeros(3), orc.EX, sp["Divergence"], n, idx)
-        ang = orc.angle_between(np.broadcast_to(orc.EX, U.shape), U)
-        inten = np.exp(-2 * (np.tan(ang) / sp["Divergence"]) ** 2)
-    return P, U, inten
-
-
-def _cpu_worker(args):
-    import art_oracle as orc
-    sp, els, idx, dist = args
-    P, U, inten = _cpu_source(sp, idx)
-    t0 = time.perf_counter()  # timed: the path itself (trace + detector + statistics), not the source generation
-    traced = orc.trace_chain(P, U, els, ignore_defects=True)
-    last = traced[-1]
-    if last["index"].size > 1:
-        det = orc.detector_autoplace(last["P"], last["U"], dist)
-        orc.result_summary(det, last["P"], last["U"], last["path"])
-    return orc.count_interactions(P.shape[0], traced), time.perf_counter() - t0
-
-
-def cpu_oracle_rate(w, oes, n_total, sample, workers):
-    """Interactions/s of the numpy oracle on `sample` rays of the workload split over `workers`
-    processes that run concurrently: interactions / slowest worker's compute time."""
-    import multiprocessing as mpc
     sp = source_properties(w, n_total)
     els = _oracle_elements(oes)
     n_src = n_total - 1 if sp["Divergence"] == 0 else n_total
-    idx = np.linspace(0, n_src - 1, sample).astype(np.int64)
-    chunks = [c for c in np.array_split(idx, workers) if c.size]
     dist = w["scene_spec"]["detector_distance"]
-    if workers == 1:
-        res = [_cpu_worker((sp, els, chunks[0], dist))]
-    else:
-        with mpc.get_context("fork").Pool(workers) as pool:
-            res = pool.map(_cpu_worker, [(sp, els, c, dist) for c in chunks])
-    wall = max(r[1] for r in res)
-    inter = sum(r[0] for r in res)
-    return inter / wall, inter, wall
 
+    def once(sample):
+        idx = np.linspace(0, n_src - 1, sample).astype(np.int64)
+        if sp["Divergence"] == 0:
+            P, U, _ = orc.plane_wave_disk(np.zeros(3), orc.EX, sp["SourceSize"] / 2, sp["NumberRays"], idx)
+        else:
+            P, U, _ = orc.point_source(np.zeros(3), orc.EX, sp["Divergence"], sp["NumberRays"], idx)
+        t0 = time.perf_counter()
+        traced = orc.trace_chain(P, U, els, ignore_defects=not w["defect_normals"])
+        last = traced[-1]
+        if last["index"].size > 1:
+            det = orc.detector_autoplace(last["P"], last["U"], dist)
+            orc.result_summary(det, last["P"], last["U"], last["path"])
+        return orc.count_interactions(P.shape[0], traced), time.perf_counter() - t0
 
-def auto_sample(w, oes, n_total, workers, seconds, lo=2000, hi=4_000_000):
-    """Sample size (rays) whose CPU pass takes about `seconds`, from a small probe of the same workload."""
-    probe = 4000 * workers
-    cpu_oracle_rate(w, oes, n_total, probe, workers)  # imports, page-in
-    rate, inter, wall = cpu_oracle_rate(w, oes, n_total, probe, workers)
-    per_ray = wall / (probe / workers)  # seconds per ray per worker
-    return int(min(hi, max(lo, workers * seconds / per_ray)))
-
-
-def reference_literal_rate(w):
-    """Speed of the UNMODIFIED reference on this workload's seeded subset, as measured in the build
-    container while generating the golden fixture (tests/golden/<cfg>_sub*.npz metadata; the reference
-    itself cannot travel to the GPU box)."""
-    try:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from golden_util import Golden, golden_names
-        names = [n for n in golden_names() if n.startswith(w["name"] + "_sub")]
-        g = Golden(names[0])
-        return {"value": g.spec["interactions"] / g.spec["reference_trace_seconds"], "unit": UNIT, "cores": 1,
-                "where": "build container, ART v0.93 RayTracingCalculation on fixture " + names[0]}
-    except Exception:
-        return None
-
-
-def run_reference(args, w, oes):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    cores = os.cpu_count() or 1
-    n_total = w["rays"]
-    # each step is a bounded sample of the workload: ~0.3 s of CPU work per step so that the default
-    # --steps 200 --warmup 10 run ends within a few minutes
-    sample = args.cpu_sample or auto_sample(w, oes, n_total, cores, 0.3)
-    for _ in range(max(args.warmup - 1, 0)):
-        cpu_oracle_rate(w, oes, n_total, sample, cores)
-    rates, inter_total, t_total = [], 0, 0.0
-    for _ in range(args.steps):
-        r, inter, wall = cpu_oracle_rate(w, oes, n_total, sample, cores)
-        rates.append(r)
-        inter_total += inter
-        t_total += wall
-    value = inter_total / t_total
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(w, args, n_total),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} rays of the {n_total}-ray bundle per step, numpy oracle "
-                                   f"(oracle/art_oracle.py) in {cores} processes"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line), flush=True)
-
-
-def workload_config(w, args, n_total):
-    s = w["scene_spec"]
-    return {"workload": f"{w['name']}: {w['scene']} ({', '.join(o['kind'] for o in s['optics'])}), "
-                        f"{n_total} rays per GPU, detector autoplace at {s['detector_distance']} mm",
-            "rays_per_gpu": int(n_total), "elements": len(s["optics"]),
-            "l2": "inputs larger than L2 (>= 320 MB of source columns + 650 MB of outputs per step)",
-            "ignore_defects": not getattr(args, "defect_normals", False)}
+    once(4000)
+    inter, wall = once(4000)
+    sample = int(min(4_000_000, max(2000, 4000 * seconds / wall)))
+    inter, wall = once(sample)
+    return inter / wall, sample, wall
 
 
 # ----------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="cfg2")
-    ap.add_argument("--rays", type=int, default=0, help="rays per GPU (default: the workload's)")
-    ap.add_argument("--variants", type=int, default=0, help="sweep workloads: chain variants per GPU")
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--nccl", action="store_true",
-                    help="multi-GPU: exchange the central sums / moments with NCCL instead of the peer-memory kernel")
-    ap.add_argument("--defect-normals", action="store_true",
-                    help="IgnoreDefects=False: surface defects also tilt the normals (SURVEY.md 8d, cfg4's second mode)")
-    ap.add_argument("--histograms", action="store_true",
-                    help="also bin the detector response (64x64 spot + 128 delay bins) and all-reduce the int64 bins")
-    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of as a CUDA graph")
-    args = ap.parse_args()
+# scene spec -> objects of the package
+# ----------------------------------------------------------------------------------------------
+def build_optic(spec):
+    import attosecondraytracing_b200.ModuleDefects as mdef
+    import attosecondraytracing_b200.ModuleMask as mmask
+    import attosecondraytracing_b200.ModuleMirror as mmirror
+    import attosecondraytracing_b200.ModuleSupport as msupp
+    kind, p = spec["support"][0], spec["support"][1:]
+    sup = {"round": msupp.SupportRound, "roundhole": msupp.SupportRoundHole, "rect": msupp.SupportRectangle,
+           "recthole": msupp.SupportRectangleHole, "rectrecthole": msupp.SupportRectangleRectHole}[kind](*p)
+    k = spec["kind"]
+    if k == "mask":
+        return mmask.Mask(sup)
+    if k == "plane":
+        m = mmirror.MirrorPlane(sup)
+    elif k == "spherical":
+        m = mmirror.MirrorSpherical(spec["radius_signed"], sup)
+    elif k == "cylindrical":
+        m = mmirror.MirrorCylindrical(spec["radius_signed"], sup)
+    elif k == "parabolic":
+        m = mmirror.MirrorParabolic(spec["feff"], spec["offaxisangle_deg"], sup)
+    elif k == "toroidal":
+        m = mmirror.MirrorToroidal(spec["majorradius"], spec["minorradius"], sup)
+    elif k == "ellipsoidal":
+        kw = {a: spec[a] for a in ("SemiMajorAxis", "SemiMinorAxis", "OffAxisAngle", "f_object", "f_image") if a in spec}
+        m = mmirror.MirrorEllipsoidal(sup, **kw)
+    else:
+        raise ValueError(k)
+    if spec.get("defects"):
+        dl = []
+        for d in spec["defects"]:
+            if d["kind"] != "zernike":
+                raise ValueError("bench workloads carry Zernike defects only")
+            dl.append(mdef.Zernike(sup, {(int(n), int(mm_)): c for n, mm_, c in d["coefficients"]}))
+        m = mmirror.DeformedMirror(m, dl)
+    return m
 
-    w = load_workload(args.workload)
-    if args.rays:
-        w["rays"] = args.rays
-    if args.workload == "cfg3" and not args.rays:
-        w["rays"] = w["rays"] // 8  # 100M rays over 8 GPUs -> 12.5M per GPU
-    oes = build_chain_elements(w)
-    if args.impl == "reference":
-        run_reference(args, w, oes)
-        return
 
-    run_b200(args, w, oes)
+def build_chain_elements(w):
+    """OpticalElement list of the workload's scene, aligned by the package's OEPlacement restatement."""
+    import attosecondraytracing_b200.ModuleProcessing as mp
+    s = w["scene_spec"]
+    optics = [build_optic(o) for o in s["optics"]]
+    oes = mp.place_optical_elements(optics, s["distances"], s["incidences"], s["plane_angles"])
+    for op in s.get("post", []):
+        getattr(oes[op["element"]], op["op"])(op["value"])
+    return oes
 
 
-def run_b200(args, w, oes):
-    import copy
-    import ctypes
+# ----------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def _events(n):
+    import torch
+    return [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+
+
+def _graph_or_eager(step, allow):
+    """The step as a CUDA graph (its launches replayed without host work in between) when `allow`."""
+    import torch
+    if not allow:
+        return step, False
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            captured = step()
+        graph.replay()
+        torch.cuda.synchronize()
+        return (lambda: (graph.replay(), captured)[1]), True
+    except Exception as exc:  # keep the eager step if capture is not possible
+        print(f"[bench] CUDA graph capture failed ({exc}); running eagerly", file=sys.stderr)
+        torch.cuda.synchronize()
+        return step, False
+
+
+def _roofline(ctx, kernel_name, k_ms, abytes, flops_kernel, traffic_key=None, note=None):
+    hbm_peak = ctx.hbm_peak
+    achieved = abytes / (k_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": None, "kernel": kernel_name, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": abytes,
+            "peak_source": ctx.peak_src,
+            "fp64": {"model_flops_per_launch": flops_kernel, "achieved_tflops": flops_kernel / (k_ms * 1e-3) / 1e12,
+                     "peak_tflops_measured_dfma": None if ctx.fp64_peak is None else ctx.fp64_peak / 1e12,
+                     "frac": None if ctx.fp64_peak is None else flops_kernel / (k_ms * 1e-3) / ctx.fp64_peak,
+                     "model": "SURVEY.md 8(d) canonical FLOP count of the reference's algorithm (bench_flops.py); the "
+                              "hardware pipe utilisation is in profiles/ (sm__pipe_fp64_cycles_active)"}}
+    if note:
+        roof["note"] = note
+    t = ctx.traffic.get(traffic_key) if traffic_key else None
+    if t:
+        roof["traffic"] = t.get("traffic")
+        roof["traffic_source"] = (f"profiles/{ctx.traffic_file}: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                  f"ncu --set full capture of this kernel at commit {ctx.traffic.get('head')}")
+    return roof
+
+
+def measure_bundle(ctx, name, steps, warmup, rays=0, main=False, histograms=False):
+    """One ray-sharded workload (cfg2 / cfg3 / cfg4 / cfg4def): weak scaling, rays dealt round-robin."""
     import torch
     import torch.distributed as dist
     from attosecondraytracing_b200 import _cabi, engine
@@ -304,165 +366,86 @@ def run_b200(args, w, oes):
     import attosecondraytracing_b200.ModuleSource as msrc
     from bench_flops import chain_flops  # canonical FLOP model of SURVEY.md 8(d)
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _cabi.lib()
+    w = load_workload(name)
+    n = int(rays or w["rays"])
+    oes = build_chain_elements(w)
+    rank, world, dev, lib, peer = ctx.rank, ctx.world, ctx.dev, ctx.lib, ctx.peer
     distance = w["scene_spec"]["detector_distance"]
-    sweep = w.get("sweep")
-    n = int(w["rays"])
-    ign = not args.defect_normals  # the reference's default through get_output_rays is IgnoreDefects=True
+    ign = not w["defect_normals"]  # the reference's default through get_output_rays is IgnoreDefects=True
 
-    if sweep:
-        # cfg5: every rank holds the full n-ray bundle and its share of the (weak-scaled) variant axis
-        nv_rank = int(args.variants or sweep["n"])
-        nv_total = nv_rank * world
-        vals = np.linspace(sweep["lo"], sweep["hi"], nv_total)
-        variants = []
-        for x in vals[rank * nv_rank:(rank + 1) * nv_rank]:
-            v = copy.deepcopy(oes)
-            getattr(v[sweep["element"]], "rotate_%s_by" % sweep["axis"])(float(x))
-            variants.append(v)
-        sp = source_properties(w, n)
-        src = msrc.synthetic_source(sp, device=dev)
-        count = src.n
-        chain = engine.DeviceChain(variants, device=dev)
-        bufs = (torch.empty((nv_rank, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev),
-                torch.empty((nv_rank, _cabi.CENTRAL_LEN), dtype=torch.float64, device=dev),
-                torch.empty((nv_rank, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=dev))
-        gathered = torch.empty((world, nv_rank, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev)
+    n_total = n * world                     # the bundle all ranks share (weak scaling)
+    sp = source_properties(w, n_total)
+    n_src_total = n_total - 1 if sp["Divergence"] == 0 else n_total
+    # rays are dealt round-robin over the ranks (rank, rank + world, ...): every rank sees the whole
+    # aperture, so masks that block a contiguous range of spiral indices do not unbalance the ranks
+    first, count, stride = ad.shard_strided(n_src_total, rank, world)
+    src = msrc.synthetic_source(sp, device=dev, first=first, count=count, stride=stride,
+                                group=True if world > 1 else None)
+    chain = engine.DeviceChain(oes, device=dev)
+    # buffers of one step, allocated once and reused (no allocator traffic inside the timed region)
+    out = chain.new_output(src, want_incidence=True)
+    central_b = torch.empty((1, _cabi.CENTRAL_LEN), dtype=torch.float64, device=dev)
+    det_b = torch.empty((1, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=dev)
+    mom_b = torch.empty((1, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev)
+    inten = src.col("intensity")
+    gather_b = torch.empty((world, 1, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev)
+    hist_b = torch.empty((_cabi.hist_len(64, 64, 128),), dtype=torch.int64, device=dev) if histograms else None
 
-        def step():
-            mom, central, det = chain.sweep(src, distance, ignore_defects=True, out=bufs)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, mom)  # per-variant result rows, no per-ray traffic
-            return None, central, det, mom
+    def step():
+        chain.trace(src, ignore_defects=ign, history=False, want_incidence=True, out=out, central=central_b)
+        if peer is not None:
+            peer.all_reduce_central(central_b, distance, det_b)   # sum over ranks + autoplace, one kernel
+        else:
+            ad.all_reduce_central(central_b)
+            chain.autoplace(central_b, distance, det=det_b)
+        chain.moments(out, det_b, intensity=inten, out=mom_b)
+        if peer is not None:
+            peer.all_reduce_moments(mom_b)
+        else:
+            ad.all_reduce_moments(mom_b, gather_buffer=gather_b)
+        if hist_b is not None:  # SpotDiagram / DelayGraph bins over the merged extents, exact int64 SUM
+            chain.histogram(out, det_b, mom_b, bins=(64, 64), delay_bins=128, intensity=inten, out=hist_b)
+            ad.all_reduce_histogram(hist_b)
+        return out, central_b, det_b, mom_b
 
-        entering = torch.zeros(chain.n_elements, dtype=torch.int64, device=dev)
-        n_surv = 0
-        for v0 in range(0, nv_rank, 16):
-            e, sv = chain.count_entering(src, variant_first=v0, n_variants=min(16, nv_rank - v0))
-            entering += e.sum(dim=0)
-            n_surv += int(sv.sum())
-        entering = [int(x) for x in entering.cpu()]
-        kernel_name = "trace_kernel<WANT_INC=0,WITH_DET=1> (2nd pass of art_sweep)"
-        abytes = None
-    else:
-        n_total = n * world                     # the bundle all ranks share (weak scaling)
-        sp = source_properties(w, n_total)
-        n_src_total = n_total - 1 if sp["Divergence"] == 0 else n_total
-        # rays are dealt round-robin over the ranks (rank, rank + world, ...): every rank sees the whole
-        # aperture, so masks that block a contiguous range of spiral indices do not unbalance the ranks
-        first, count, stride = ad.shard_strided(n_src_total, rank, world)
-        src = msrc.synthetic_source(sp, device=dev, first=first, count=count, stride=stride,
-                                    group=True if world > 1 else None)
-        chain = engine.DeviceChain(oes, device=dev)
-        # buffers of one step, allocated once and reused (no allocator traffic inside the timed region)
-        out = chain.new_output(src, want_incidence=True)
-        central_b = torch.empty((1, _cabi.CENTRAL_LEN), dtype=torch.float64, device=dev)
-        det_b = torch.empty((1, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=dev)
-        mom_b = torch.empty((1, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev)
-        inten = src.col("intensity")
-        gather_b = torch.empty((world, 1, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev)
-        hist_b = torch.empty((_cabi.hist_len(64, 64, 128),), dtype=torch.int64, device=dev) if args.histograms else None
-        # multi-GPU: the two exchanges run inside one kernel each over peer memory (NVLink); NCCL when
-        # symmetric memory is unavailable or --nccl asks for it
-        peer = None if (world == 1 or args.nccl) else ad.PeerExchange.create(dev)
-
-        def step():
-            chain.trace(src, ignore_defects=ign, history=False, want_incidence=True, out=out, central=central_b)
-            if peer is not None:
-                peer.all_reduce_central(central_b, distance, det_b)   # sum over ranks + autoplace
-            else:
-                ad.all_reduce_central(central_b)
-                chain.autoplace(central_b, distance, det=det_b)
-            chain.moments(out, det_b, intensity=inten, out=mom_b)
-            if peer is not None:
-                peer.all_reduce_moments(mom_b)
-            else:
-                ad.all_reduce_moments(mom_b, gather_buffer=gather_b)
-            if hist_b is not None:  # SpotDiagram / DelayGraph bins over the merged extents, exact int64 SUM
-                chain.histogram(out, det_b, mom_b, bins=(64, 64), delay_bins=128, intensity=inten, out=hist_b)
-                ad.all_reduce_histogram(hist_b)
-            return out, central_b, det_b, mom_b
-
-        e, sv = chain.count_entering(src, ignore_defects=ign)
-        entering = [int(x) for x in e[0].cpu()]
-        n_surv = int(sv[0])
-        kernel_name = "trace_kernel<WANT_INC=1,WITH_DET=0>"
-        abytes = algorithmic_bytes(count, n_surv, in_columns=len(src._names))
+    e, sv = chain.count_entering(src, ignore_defects=ign)
+    entering = [int(x) for x in e[0].cpu()]
+    n_surv = int(sv[0])
     interactions_rank = int(sum(entering))
+    abytes = algorithmic_bytes(count, n_surv, in_columns=len(src._names))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        final, central, det, mom = step()
+    for _ in range(max(warmup, 3)):
+        step()
     torch.cuda.synchronize()
+    # Multi-GPU steps with NCCL calls in them stay eager (capturing the collectives changed nothing at N=2
+    # and left the communicator unable to shut down cleanly); the peer-memory exchange has no NCCL call.
+    nccl_in_step = world > 1 and (peer is None or histograms)
+    run_step, graphed = _graph_or_eager(step, not ctx.args.no_graph and not nccl_in_step)
 
-    # the step as a CUDA graph: its kernel launches replayed without host work in between.
-    # Multi-GPU steps stay eager: capturing the two NCCL collectives in the graph was measured at N=2
-    # (0.442 vs 0.446 ms per step -- the collectives' latency, not launch overhead, is what the step waits
-    # for) and the captured communicator did not shut down cleanly, so the option was removed.
-    run_step = step
-    graphed = False
-    peer_graph = world > 1 and not sweep and peer is not None and not args.histograms  # no NCCL call in the step
-    if not args.no_graph and (world == 1 or peer_graph):
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                step()
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                captured = step()
-            graph.replay()
-            torch.cuda.synchronize()
-            run_step = lambda: (graph.replay(), captured)[1]  # noqa: E731
-            graphed = True
-        except Exception as exc:  # keep the eager step if capture is not possible
-            print(f"[bench] CUDA graph capture failed ({exc}); running eagerly", file=sys.stderr)
-            torch.cuda.synchronize()
-
-    # ---- timed region: K steps, device-timed, max over ranks --------------------------------------
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(ctx.local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.art_launch_count()
     step()  # one eager step to count this step's launches
     launches_per_step = lib.art_launch_count() - launches0
-    barrier()
+    ctx.barrier()
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         final, central, det, mom = run_step()
     ev1.record()
-    barrier()
+    ctx.barrier()
     ms_total = ev0.elapsed_time(ev1)
-    if world > 1 and not sweep and peer is not None and peer.status() != 0:
+    if peer is not None and peer.status() != 0:
         raise RuntimeError("peer-memory exchange timed out (a rank did not arrive)")
 
-    # ---- the dominant kernel alone, CUDA events on the launching stream ----------------------------
-    ksteps = max(3, min(args.steps, 50))
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ksteps)]
+    # the dominant kernel alone, CUDA events on the launching stream.  want_central=False only skips the
+    # separate fold launch: trace_kernel itself always reduces the central sums, so this IS the step's K1.
+    kev = _events(max(3, min(steps, 50)))
     torch.cuda.synchronize()
-    if sweep:
-        # second pass of art_sweep = fused trace + detector over all variants of this rank
-        for e0, e1 in kev:
-            e0.record()
-            chain.trace_detect(src, bufs[2], ignore_defects=True)
-            e1.record()
-    else:
-        for e0, e1 in kev:
-            e0.record()
-            chain.trace(src, ignore_defects=ign, history=False, want_incidence=True, want_central=False, out=out)
-            e1.record()
+    for e0, e1 in kev:
+        e0.record()
+        chain.trace(src, ignore_defects=ign, history=False, want_incidence=True, want_central=False, out=out)
+        e1.record()
     torch.cuda.synchronize()
     k_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in kev]))
     clocks = sampler.summary()
@@ -474,125 +457,343 @@ def run_b200(args, w, oes):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms_total, k_ms = (float(x) for x in tms.cpu())
     interactions_all = float(tot.cpu()[0])
-    value = interactions_all * args.steps / (ms_total * 1e-3)
+    s = engine.summary_from_moments(mom.cpu().numpy()[0], central.cpu().numpy()[0])
+    flops_kernel = chain_flops(oes, entering, n_surv, True) - n_surv * 60.0  # the detector is another kernel
+    res = {
+        "config": workload_config(w, n), "value": interactions_all * steps / (ms_total * 1e-3), "unit": UNIT,
+        "scaling": "weak", "steps": steps, "ms_per_step": ms_total / steps,
+        "roofline": _roofline(ctx, "trace_kernel<WANT_INC=1,WITH_DET=0>", k_ms, abytes, flops_kernel, traffic_key=name),
+        "gpu_launches": int(launches_per_step) * steps, "cuda_graph": graphed, "clocks": clocks,
+        "interactions_per_step": interactions_all, "survivors_rank0": n_surv,
+        "result": {k: s[k] for k in ("SpotSizeSD", "DurationSD", "ETransmission") if k in s},
+    }
+    if histograms:
+        res["histograms"] = "64x64 spot + 128 delay bins per step, int64 all-reduce"
 
-    # ---- end to end through the host-buffer C-ABI call (H2D + D2H inside the timed region) ---------
-    e2e = None
-    if not sweep:
+    if main:
+        # ---- end to end, the reference's real host input: the source DESCRIPTION (SourceProperties) in,
+        #      statistics out, through one C-ABI call; the bundle is generated on the device inside the call
+        desc = msrc.source_descriptor(sp, first=first, count=count, stride=stride)
+        import ctypes
+        for _ in range(2):
+            m_s, c_s, d_s = chain.run_source(desc, distance, ignore_defects=ign, peer=peer)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(3, min(steps, 20))
+        for _ in range(e2e_steps):
+            m_s, c_s, d_s = chain.run_source(desc, distance, ignore_defects=ign, peer=peer)
+        t_src = ctx.max_over_ranks(time.perf_counter() - t0)
+        s_src = engine.summary_from_moments(m_s, c_s)
+        same = all(abs(s_src[k] - s[k]) <= 1e-9 * max(1.0, abs(s[k])) for k in ("SpotSizeSD", "DurationSD", "ETransmission"))
+        res["e2e"] = {"value": interactions_all * e2e_steps / t_src, "unit": UNIT,
+                      "h2d_bytes_per_step": ctypes.sizeof(desc) + 24,
+                      "d2h_bytes_per_step": 8 * (_cabi.MOMENTS_LEN + _cabi.CENTRAL_LEN + _cabi.DETECTOR_DOUBLES) + 16,
+                      "steps": e2e_steps, "ms_per_step": 1e3 * t_src / e2e_steps,
+                      "statistics_equal_device_step": bool(same),
+                      "api": "art_run_source_host (ctypes): SourceProperties descriptor in; bundle generated + weighted "
+                             "on the device (K0), trace, autoplace, moments; moments/central/detector out"
+                             + ("" if peer is None else "; ranks combined over peer memory inside the call")}
+        # ---- the same with HOST ray columns (a caller that already holds rays): PCIe-bound
         host = src.to("cpu").pin_memory()
         h2d = 8 * len(src._names) * count + (24 if src.origin is not None else 0)
-        d2h = 8 * (_cabi.MOMENTS_LEN + _cabi.CENTRAL_LEN) + 8 * _cabi.DETECTOR_DOUBLES
         for _ in range(2):
             chain.run_host(host, distance, ignore_defects=ign, peer=peer)
-        barrier()
+        ctx.barrier()
         t0 = time.perf_counter()
-        e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(e2e_steps):
-            mom_h, cen_h, det_h = chain.run_host(host, distance, ignore_defects=ign, peer=peer)
-        torch.cuda.synchronize()
-        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        hc_steps = max(3, min(steps, 10))
+        for _ in range(hc_steps):
+            chain.run_host(host, distance, ignore_defects=ign, peer=peer)
+        t_hc = ctx.max_over_ranks(time.perf_counter() - t0)
+        res["e2e_host_columns"] = {
+            "value": interactions_all * hc_steps / t_hc, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": 8 * (_cabi.MOMENTS_LEN + _cabi.CENTRAL_LEN + _cabi.DETECTOR_DOUBLES),
+            "steps": hc_steps, "ms_per_step": 1e3 * t_hc / hc_steps,
+            "h2d_gbs_per_gpu": h2d * hc_steps / t_hc / 1e9,
+            "api": "art_run_host" + ("" if peer is None else "_sharded") + " (ctypes): pinned host ray columns in "
+                   "(8 PCIe chunks overlapped with the trace), moments/central/detector out"}
+        del host
+    ctx.oes_main = oes if main else getattr(ctx, "oes_main", None)
+    chain.close()
+    del src, out, chain
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_sweep(ctx, name, steps, warmup, rays=0, variants=0):
+    """cfg5: 1024 misaligned variants of the telescope x 10^6 rays.  STRONG scaling: the variant axis is
+    sharded (1024 / N variants per rank, every rank holds the whole source bundle); the per-variant result
+    rows are all-gathered, there is no per-ray traffic."""
+    import copy
+    import torch
+    import torch.distributed as dist
+    from attosecondraytracing_b200 import _cabi, engine
+    import attosecondraytracing_b200.ModuleSource as msrc
+    from bench_flops import chain_flops
+
+    w = load_workload(name)
+    sweep = w["sweep"]
+    n = int(rays or w["rays"])
+    oes = build_chain_elements(w)
+    rank, world, dev, lib = ctx.rank, ctx.world, ctx.dev, ctx.lib
+    distance = w["scene_spec"]["detector_distance"]
+    nv_total = int(variants or sweep["n"])
+    nv_rank = nv_total // world
+    if nv_rank * world != nv_total:
+        raise ValueError("the number of variants must be divisible by the number of GPUs")
+    vals = np.linspace(sweep["lo"], sweep["hi"], nv_total)
+    variants_ = []
+    for x in vals[rank * nv_rank:(rank + 1) * nv_rank]:
+        v = copy.deepcopy(oes)
+        getattr(v[sweep["element"]], "rotate_%s_by" % sweep["axis"])(float(x))
+        variants_.append(v)
+    sp = source_properties(w, n)
+    src = msrc.synthetic_source(sp, device=dev)
+    count = src.n
+    chain = engine.DeviceChain(variants_, device=dev)
+    bufs = (torch.empty((nv_rank, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev),
+            torch.empty((nv_rank, _cabi.CENTRAL_LEN), dtype=torch.float64, device=dev),
+            torch.empty((nv_rank, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=dev))
+    gathered = torch.empty((world, nv_rank, _cabi.MOMENTS_LEN), dtype=torch.float64, device=dev)
+
+    def step():
+        mom, central, det = chain.sweep(src, distance, ignore_defects=True, out=bufs)
         if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e = {"value": interactions_all * e2e_steps / float(t_e2e.cpu()[0]), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-               "api": "art_run_host (ctypes, pinned host columns in, moments/central/detector out)" if peer is None else
-                      "art_run_host_sharded (ctypes, pinned host columns of this rank's shard in, whole-bundle "
-                      "moments/central/detector out; ranks combined over peer memory inside the call)"}
-    else:
-        # the sweep's per-step host traffic is the pose table in (built once) and the result rows out
-        host = src.to("cpu").pin_memory()
-        h2d = 8 * len(src._names) * count + (24 if src.origin is not None else 0)
-        d2h = 8 * nv_rank * (_cabi.MOMENTS_LEN + _cabi.CENTRAL_LEN)
-        dsrc = engine.RayBundle(count, device=dev, columns=host._names)
-        dsrc.origin = src.origin
-        barrier()
-        t0 = time.perf_counter()
-        e2e_steps = max(2, min(args.steps, 5))
-        for _ in range(e2e_steps):
-            dsrc._storage.copy_(host._storage, non_blocking=True)
-            m_, c_, d_ = chain.sweep(dsrc, distance, ignore_defects=True, out=bufs)
-            rows = torch.cat([m_, c_], dim=1).cpu()
-        torch.cuda.synchronize()
-        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(gathered, mom)  # per-variant result rows, no per-ray traffic
+        return mom, central, det
+
+    entering = torch.zeros(chain.n_elements, dtype=torch.int64, device=dev)
+    n_surv = 0
+    for v0 in range(0, nv_rank, 16):
+        e, sv = chain.count_entering(src, variant_first=v0, n_variants=min(16, nv_rank - v0))
+        entering += e.sum(dim=0)
+        n_surv += int(sv.sum())
+    entering = [int(x) for x in entering.cpu()]
+    interactions_rank = int(sum(entering))
+
+    for _ in range(max(warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    run_step, graphed = _graph_or_eager(step, not ctx.args.no_graph and world == 1)
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.art_launch_count()
+    step()
+    launches_per_step = lib.art_launch_count() - launches0
+    ctx.barrier()
+    ev0.record()
+    for _ in range(steps):
+        mom, central, det = run_step()
+    ev1.record()
+    ctx.barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    # second pass of art_sweep alone = fused trace + detector over all variants of this rank
+    kev = _events(max(3, min(steps, 10)))
+    torch.cuda.synchronize()
+    for e0, e1 in kev:
+        e0.record()
+        chain.trace_detect(src, bufs[2], ignore_defects=True)
+        e1.record()
+    torch.cuda.synchronize()
+    k_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in kev]))
+    clocks = sampler.summary()
+    tms = torch.tensor([ms_total, k_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(interactions_rank)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total, k_ms = (float(x) for x in tms.cpu())
+    interactions_all = float(tot.cpu()[0])
+
+    # end to end: the host moves the bundle in (pinned) and the per-variant result rows out every step
+    host = src.to("cpu").pin_memory()
+    h2d = 8 * len(src._names) * count + (24 if src.origin is not None else 0)
+    d2h = 8 * nv_rank * (_cabi.MOMENTS_LEN + _cabi.CENTRAL_LEN)
+    dsrc = engine.RayBundle(count, device=dev, columns=host._names)
+    dsrc.origin = src.origin
+    ctx.barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(steps, 3))
+    for _ in range(e2e_steps):
+        dsrc._storage.copy_(host._storage, non_blocking=True)
+        m_, c_, d_ = chain.sweep(dsrc, distance, ignore_defects=True, out=bufs)
+        rows = torch.cat([m_, c_], dim=1).cpu()  # noqa: F841
+    torch.cuda.synchronize()
+    t_e2e = ctx.max_over_ranks(time.perf_counter() - t0)
+
+    # two traces per variant (central pass + detector pass); per-ray outputs are never stored
+    flops = 2.0 * nv_rank * chain_flops(oes, [e_ / nv_rank for e_ in entering], n_surv / nv_rank, True)
+    abytes = 8 * len(src._names) * count * nv_rank  # the source bundle re-read per variant (L2-resident)
+    s = engine.summary_from_moments(mom.cpu().numpy()[0], central.cpu().numpy()[0])
+    cfg = workload_config(w, n)
+    cfg["variants_per_gpu"] = nv_rank
+    res = {
+        "config": cfg, "value": interactions_all * steps / (ms_total * 1e-3), "unit": UNIT, "scaling": "strong",
+        "steps": steps, "ms_per_step": ms_total / steps,
+        "roofline": _roofline(ctx, "trace_kernel<WANT_INC=0,WITH_DET=1> (2nd pass of art_sweep)", k_ms, abytes, flops / 2.0,
+                              note="FP64-bound path: the source bundle stays in L2; the binding ceiling is the fp64 entry"),
+        "e2e": {"value": interactions_all * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "api": "DeviceChain.sweep (art_sweep): pinned host bundle in, per-variant result rows out"},
+        "gpu_launches": int(launches_per_step) * steps, "cuda_graph": graphed, "clocks": clocks,
+        "interactions_per_step": interactions_all,
+        "result_variant0_rank0": {k: s[k] for k in ("SpotSizeSD", "DurationSD", "ETransmission") if k in s},
+    }
+    chain.close()
+    del src, dsrc, host, chain
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # CPU baseline first (rank 0, N = 1 only), BEFORE this process touches CUDA: the worker pool forks
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1 and rank == 0:
+        w = load_workload(args.workload)
+        n_cpu = int(args.rays or w["rays"])
+        try:
+            import ref_runner
+            if not ref_runner.available():
+                raise RuntimeError("oracle/_ref missing")
+            cores = os.cpu_count() or 1
+            rate, sample, wall, _ = reference_rate(w, n_cpu, cores, args.cpu_seconds)
+            cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
+                            "sample": f"{sample} rays (evenly spaced spiral indices) of the same {n_cpu}-ray bundle: "
+                                      f"ART v0.93 OEPlacement + RayTracingCalculation + Detector.autoplace + "
+                                      f"GetResultSummary, unmodified ({ref_root()}), in {cores} processes, {wall:.1f} s"}
+        except Exception as exc:
+            cpu_baseline = {"unavailable": f"literal reference could not run here: {exc}"}
+
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from attosecondraytracing_b200 import _cabi
+    from attosecondraytracing_b200 import distributed as ad
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = Ctx()
+    ctx.args, ctx.rank, ctx.world, ctx.local, ctx.dev = args, rank, world, local, dev
+    ctx.lib = _cabi.lib()
+    # multi-GPU: the two exchanges run inside one kernel each over peer memory (NVLink); NCCL when
+    # symmetric memory is unavailable or --nccl asks for it
+    ctx.peer = None if (world == 1 or args.nccl) else ad.PeerExchange.create(dev)
+
+    def barrier():
         if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e = {"value": interactions_all * e2e_steps / float(t_e2e.cpu()[0]), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-               "api": "DeviceChain.sweep (art_sweep): pinned host bundle in, per-variant result rows out"}
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        torch.cuda.synchronize()
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.cpu()[0])
+
+    ctx.barrier, ctx.max_over_ranks = barrier, max_over_ranks
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    ctx.hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    ctx.peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    fp64 = ctypes.c_double()
+    ctx.fp64_peak = fp64.value if ctx.lib.art_probe_fp64(fp64) == 0 else None
+    ctx.traffic, ctx.traffic_file = {}, "r02_traffic.json"
+    try:
+        ctx.traffic = json.load(open(os.path.join(ROOT, "profiles", ctx.traffic_file)))
+    except Exception:
+        pass
+
+    def measure(name, steps, warmup, main=False):
+        if load_workload(name).get("sweep"):
+            return measure_sweep(ctx, name, max(2, min(steps, 5)) if not main else steps, warmup,
+                                 rays=args.rays if main else 0, variants=args.variants)
+        return measure_bundle(ctx, name, steps, warmup, rays=args.rays if main else 0, main=main,
+                              histograms=args.histograms and main)
+
+    main_res = measure(args.workload, args.steps, args.warmup, main=True)
+    subs = {}
+    names = [] if args.sub in ("none", "") else [s for s in args.sub.split(",") if s and s != args.workload]
+    for name in names:
+        try:
+            subs[name] = measure(name, max(3, min(args.steps, 10)), 3)
+        except Exception as exc:  # a sub-workload must not take the headline down with it
+            subs[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        fp64 = ctypes.c_double()
-        fl = fp64.value if lib.art_probe_fp64(fp64) == 0 else None
-        if sweep:
-            # two traces per variant (central pass + detector pass); per-ray outputs are never stored
-            flops = 2.0 * nv_rank * chain_flops(oes, [e_ / nv_rank for e_ in entering], n_surv / nv_rank, True)
-            flops_kernel = flops / 2.0
-            abytes = 8 * len(src._names) * count * nv_rank  # the source bundle re-read per variant (L2-resident)
-            roof = {"bound": "hbm", "achieved": abytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": abytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                    "note": "FP64-bound path: the source bundle stays in L2; the binding ceiling is the fp64 entry"}
-        else:
-            flops_kernel = chain_flops(oes, entering, n_surv, True) - n_surv * 60.0  # detector is another kernel
-            achieved = abytes / (k_ms * 1e-3) / 1e9
-            traffic = None
-            try:  # DRAM bytes of this kernel from the committed ncu --set full capture of the same command
-                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-                if w["name"] in tj and not args.rays:
-                    traffic = tj[w["name"]]["traffic"]
-            except Exception:
-                pass
-            roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": traffic}
-        roof.update({"kernel": kernel_name, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": abytes,
-                     "peak_source": peak_src,
-                     "fp64": {"model_flops_per_launch": flops_kernel,
-                              "achieved_tflops": flops_kernel / (k_ms * 1e-3) / 1e12,
-                              "peak_tflops_measured_dfma": None if fl is None else fl / 1e12,
-                              "frac": None if fl is None else flops_kernel / (k_ms * 1e-3) / fl}})
-        s = engine.summary_from_moments(mom.cpu().numpy()[0], central.cpu().numpy()[0])
-        cfg = workload_config(w, args, n)
-        if args.histograms and not sweep:
-            cfg["histograms"] = "64x64 spot + 128 delay bins per step, int64 all-reduce"
-        if world > 1 and not sweep:
-            cfg["exchange"] = ("central sums and moments exchanged inside one kernel each over peer memory (NVLink)"
-                               if peer is not None else "NCCL all-reduce + all-gather")
-        if sweep:
-            cfg.update({"variants_per_gpu": nv_rank, "sweep": f"{sweep['axis']} of element {sweep['element']} over "
-                        f"[{sweep['lo']}, {sweep['hi']}] deg", "l2": "source bundle (56 MB) re-read per variant from L2 "
-                        "by design; per-variant outputs are 34 doubles"})
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "roofline": roof, "e2e": e2e, "gpu_launches": int(launches_per_step) * args.steps, "cuda_graph": graphed,
-            "clocks": clocks, "interactions_per_step": interactions_all, "survivors_rank0": int(n_surv),
-            "result": {k: s[k] for k in ("SpotSizeSD", "DurationSD", "ETransmission") if k in s},
+            "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+            "scaling": main_res["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": main_res["config"], "roofline": main_res["roofline"], "e2e": main_res.get("e2e"),
+            "gpu_launches": main_res["gpu_launches"], "cuda_graph": main_res["cuda_graph"],
+            "clocks": main_res["clocks"], "interactions_per_step": main_res["interactions_per_step"],
         }
-        if not args.no_cpu_baseline and world == 1:
-            n_cpu = n if sweep else n * world
-            sample = args.cpu_sample or auto_sample(w, oes, n_cpu, 1, 15.0)  # ~15 s on one core
-            rate, inter, wall = cpu_oracle_rate(w, oes, n_cpu, sample, 1)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"{sample} rays of the same {n_cpu}-ray bundle, numpy oracle "
-                                              f"(oracle/art_oracle.py), {wall:.1f} s",
-                                    "reference_literal": reference_literal_rate(w)}
+        for k in ("e2e_host_columns", "survivors_rank0", "result", "result_variant0_rank0", "histograms"):
+            if k in main_res:
+                line[k] = main_res[k]
+        if world > 1:
+            line["multi_gpu"] = ("central sums and moments exchanged inside one kernel each over peer memory (NVLink)"
+                                 if ctx.peer is not None else "NCCL all-reduce + all-gather")
+        if subs:
+            line["workloads"] = subs
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+            if not args.no_port_baseline and getattr(ctx, "oes_main", None) is not None:
+                try:
+                    w = load_workload(args.workload)
+                    n_cpu = int(args.rays or w["rays"])
+                    rate, sample, wall = port_rate(w, ctx.oes_main, n_cpu, 4.0)
+                    line["cpu_baseline_port"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                                                 "sample": f"{sample} rays of the same bundle, numpy restatement "
+                                                           f"(oracle/art_oracle.py) on one core, {wall:.1f} s; NOT the "
+                                                           "reference -- for orientation only"}
+                except Exception as exc:
+                    line["cpu_baseline_port"] = {"unavailable": str(exc)}
         print(json.dumps(line), flush=True)
-    chain.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def C_double():
-    import ctypes
-    return ctypes.c_double()
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg3", "cfg4", "cfg4def", "cfg5"])
+    ap.add_argument("--sub", default=DEFAULT_SUBS,
+                    help="comma list of further workloads measured in the same run and attached as `workloads` (or none)")
+    ap.add_argument("--rays", type=int, default=0, help="rays per GPU of the main workload (default: the workload's)")
+    ap.add_argument("--variants", type=int, default=0, help="sweep workloads: total chain variants (default 1024)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work per core of the cpu_baseline sample")
+    ap.add_argument("--ref-seconds", type=float, default=2.0, help="--impl reference: CPU work per core and step")
+    ap.add_argument("--ref-warm", action="store_true", help="--impl reference: also run the warm-up steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-port-baseline", action="store_true")
+    ap.add_argument("--nccl", action="store_true",
+                    help="multi-GPU: exchange the central sums / moments with NCCL instead of the peer-memory kernel")
+    ap.add_argument("--histograms", action="store_true",
+                    help="also bin the detector response (64x64 spot + 128 delay bins) and all-reduce the int64 bins")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of as a CUDA graph")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference(args, load_workload(args.workload))
+        return
+    run_b200(args)
 
 
 if __name__ == "__main__":

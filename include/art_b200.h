@@ -30,6 +30,7 @@ extern "C" {
 #define ART_E_CUDA (-2)     /* CUDA runtime error (message holds cudaGetErrorString) */
 #define ART_E_NOMEM (-3)
 #define ART_E_UNSUPPORTED (-4)
+#define ART_E_PEER_TIMEOUT (-5) /* multi-GPU: a rank did not arrive at a peer-memory exchange */
 
 /* limits */
 #define ART_MAX_ELEMENTS 16 /* elements per chain (longer chains: chain the calls) */
@@ -187,9 +188,9 @@ int32_t art_version(void);
 const char* art_last_error(void);
 
 /* sizeof(ArtElementDesc), sizeof(ArtZernikeDesc), sizeof(ArtBundleView), sizeof(ArtDetector),
- * sizeof(ArtGridMapDesc) as this library was compiled -- lets a binding in another language verify its
+ * sizeof(ArtGridMapDesc), sizeof(ArtSourceDesc) as this library was compiled -- lets a binding in another language verify its
  * struct layouts. */
-int32_t art_abi_sizes(int32_t sizes_out[5]);
+int32_t art_abi_sizes(int32_t sizes_out[6]);
 
 /* CUDA device count (plumbing for the host; no reference counterpart). */
 int32_t art_device_count(int32_t* count);
@@ -311,6 +312,8 @@ int32_t art_moments_merge(const double* rows, int32_t n_ranks, int32_t n_variant
  *           the same kernel (replaces art_detector_autoplace).
  *   kind 1  rows = n_variants x ART_MOMENTS_LEN, merged as art_moments_merge does (replaces the all-gather
  *           + art_moments_merge after art_detector_moments).
+ *   kind 2  rows = n_variants x 2 (largest angle to the axis, largest |P| of a source bundle), maximum over
+ *           the ranks (the normalisation of ApplyGaussianIntensityToRayList for a sharded source).
  * rows are reduced in place; every rank ends up with bit-identical rows.  The call sequence must be the same
  * on all ranks.  No host synchronisation, CUDA-graph capturable (the epoch is kept in the buffer).  A peer
  * that does not arrive within ~10 s leaves rows unreduced and sets the buffer's status word
@@ -399,12 +402,49 @@ int32_t art_run_host(ArtChain* chain, const ArtBundleView* in_host, const ArtBun
  * art_run_host for ONE SHARD of a bundle that is spread over the GPUs of a node (one process / thread per
  * GPU, every rank calling with its own shard): the central sums and the moments rows of all ranks are
  * combined inside the call over peer memory (art_peer_exchange; peer_bufs / rank / world as there), so every
- * rank places the identical detector and returns the statistics of the WHOLE bundle.
+ * rank places the identical detector and returns the statistics of the WHOLE bundle.  An empty shard (n = 0)
+ * still takes part in both exchanges.  Returns ART_E_PEER_TIMEOUT when a rank did not arrive at one of this
+ * call's exchanges (the outputs are then not written).
  */
 int32_t art_run_host_sharded(ArtChain* chain, const ArtBundleView* in_host, const ArtBundleView* out_final_host,
                              uint32_t flags, double distance, const ArtDetector* manual_det,
                              double* moments_host, double* central_host, ArtDetector* det_host,
                              const uint64_t* peer_bufs, int32_t rank, int32_t world);
+
+/*
+ * The source bundle as the reference's host hands it over: a DESCRIPTION, not rays.  OEPlacement
+ * (ART/ModuleProcessing.py:58-79) turns SourceProperties {Divergence, SourceSize, NumberRays, Wavelength}
+ * into PointSource / PlaneWaveDisk / ExtendedSource (+ ApplyGaussianIntensityToRayList); this struct
+ * carries the arguments of those generators (art_source_generate / art_source_intensity have the details).
+ */
+typedef struct ArtSourceDesc {
+  int32_t kind;               /* 0 PointSource, 1 PlaneWaveDisk, 2 ExtendedSource                     */
+  int32_t intensity;          /* 0: every ray has intensity 1; 1: ApplyGaussianIntensityToRayList     */
+  int64_t n_total;            /* rays of the WHOLE bundle (PlaneWaveDisk: NbRays; it emits NbRays-1)  */
+  int64_t first, count, stride; /* this call's share: rays first, first+stride, ... (count of them)  */
+  double rho;                 /* tan(Divergence) (kinds 0, 2) or the disk radius (kind 1)             */
+  double axis[3];             /* direction of the bundle                                              */
+  double origin[3];           /* S / Centre                                                           */
+  int64_t n_point_sources;    /* kind 2 only                                                          */
+  int64_t rays_per_source;    /* kind 2 only                                                          */
+  double source_radius;       /* kind 2 only                                                          */
+  double intensity_fraction;  /* relative intensity at the edge; outside (0,1): 1/e^2                 */
+} ArtSourceDesc;
+
+/*
+ * End to end from the source DESCRIPTION: generates this call's share of the synthetic bundle on the device
+ * (K0, closed form), weights it, traces variant 0, autoplaces the detector at `distance` (or uses
+ * *manual_det), reduces the moments and copies moments / central sums / detector back.  The host moves a
+ * ~150-byte descriptor in and ~450 bytes out; no ray ever crosses PCIe.  Synchronises; uses the chain's
+ * internal workspace like art_run_host.  This is what ARTmain.py:248-290 run_ART does for a config whose
+ * source is given by SourceProperties.
+ * peer_bufs non-NULL: the bundle is spread over `world` GPUs (every rank passes its own first/count/stride
+ * of the same n_total-ray bundle); the axis and extent of the intensity profile, the central sums and the
+ * moments are combined over peer memory inside the call as in art_run_host_sharded.
+ */
+int32_t art_run_source_host(ArtChain* chain, const ArtSourceDesc* source, uint32_t flags, double distance,
+                            const ArtDetector* manual_det, double* moments_host, double* central_host,
+                            ArtDetector* det_host, const uint64_t* peer_bufs, int32_t rank, int32_t world);
 
 /*
  * ART/ModuleProcessing.py:250 RayTracingCalculation for a caller that holds HOST arrays (the

@@ -50,7 +50,7 @@ def load(path):
     L.art_chain_destroy.argtypes = [C.c_void_p]
     L.art_trace_host.argtypes = [C.c_void_p, C.POINTER(ArtBundleView), C.POINTER(ArtBundleView),
                                  C.POINTER(ArtBundleView), C.c_uint32]
-    sizes = (C.c_int32 * 5)()
+    sizes = (C.c_int32 * 6)()
     L.art_abi_sizes(sizes)
     assert list(sizes)[:3] == [C.sizeof(ArtElementDesc), C.sizeof(ArtZernikeDesc), C.sizeof(ArtBundleView)], "ABI mismatch"
     _lib = L

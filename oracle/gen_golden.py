@@ -35,60 +35,12 @@ EXTRA_ARRAYS = {}  # arrays of gridded defects collected by derived_optic for th
 
 
 def ref():
-    global REF
-    if REF is None:
-        REF = lr.load()
-    return REF
+    import ref_runner
+    return ref_runner.ref()
 
 
-# ------------------------------------------------------------------------------------------
-def build_support(spec):
-    ms = ref().msupp
-    kind, p = spec[0], spec[1:]
-    return {
-        "round": ms.SupportRound, "roundhole": ms.SupportRoundHole, "rect": ms.SupportRectangle,
-        "recthole": ms.SupportRectangleHole, "rectrecthole": ms.SupportRectangleRectHole,
-    }[kind](*p)
-
-
-def build_optic(spec):
-    R = ref()
-    mm = R.mmirror
-    sup = build_support(spec["support"])
-    k = spec["kind"]
-    if k == "mask":
-        return R.mmask.Mask(sup)
-    if k == "plane":
-        m = mm.MirrorPlane(sup)
-    elif k == "spherical":
-        m = mm.MirrorSpherical(spec["radius_signed"], sup)
-    elif k == "cylindrical":
-        m = mm.MirrorCylindrical(spec["radius_signed"], sup)
-    elif k == "parabolic":
-        m = mm.MirrorParabolic(spec["feff"], spec["offaxisangle_deg"], sup)
-    elif k == "toroidal":
-        m = mm.MirrorToroidal(spec["majorradius"], spec["minorradius"], sup)
-    elif k == "ellipsoidal":
-        kw = {a: spec[a] for a in ("SemiMajorAxis", "SemiMinorAxis", "OffAxisAngle", "f_object", "f_image")
-              if a in spec}
-        m = mm.MirrorEllipsoidal(sup, **kw)
-    else:
-        raise ValueError(k)
-    if spec.get("defects"):
-        dl = []
-        for d in spec["defects"]:
-            if d["kind"] == "zernike":
-                coeffs = {(int(n), int(mm_)): c for n, mm_, c in d["coefficients"]}
-                dl.append(R.mdef.Zernike(sup, coeffs))
-            elif d["kind"] == "measuredmap":
-                dl.append(R.mdef.MeasuredMap(sup, sc.measured_map(d["nx"], d["ny"], d["amplitude"])))
-            elif d["kind"] == "fourier":
-                np.random.seed(d["seed"])  # the reference draws its phases from the global numpy RNG
-                dl.append(R.mdef.Fourrier(sup, d["rms"], slope=d["slope"], smallest=d["smallest"]))
-            else:
-                raise ValueError(d["kind"])
-        m = mm.DeformedMirror(m, dl)
-    return m
+# scene spec -> reference objects: shared with bench.py's CPU legs
+from ref_runner import build_chain, build_optic, build_support  # noqa: E402,F401
 
 
 def derived_optic(spec, obj):
@@ -129,17 +81,6 @@ def derived_optic(spec, obj):
                                      "x0": float(X[0]), "x1": float(X[-1]), "y0": float(Y[0]), "y1": float(Y[-1])})
     d["centre"] = [float(v) for v in obj.get_centre()]
     return d
-
-
-def build_chain(scene):
-    R = ref()
-    optics = [build_optic(s) for s in scene["optics"]]
-    with lr.quiet():
-        chain = R.mp.OEPlacement(dict(scene["source"]), optics, list(scene["distances"]),
-                                 list(scene["incidences"]), list(scene["plane_angles"]), scene["name"])
-    for op in scene.get("post", []):
-        getattr(chain.optical_elements[op["element"]], op["op"])(op["value"])
-    return chain
 
 
 def bundle_arrays(rays):
@@ -218,35 +159,13 @@ def save(name, data):
 
 # ------------------------------------------------------------------------------------------
 def subset_source_rays(scene, n_full, idx):
-    """Reference Ray objects for rays `idx` of the n_full-ray synthetic bundle.
-
-    Built with the reference's own constructors / rotation (ART/ModuleSource.py:23-81,135-169),
-    only the Vogel-spiral row is evaluated per index instead of for all n_full rays; intensities
-    take their normalisation from the full bundle (oracle.source_for)."""
-    R = ref()
+    """Reference Ray objects for rays `idx` of the n_full-ray synthetic bundle (ref_runner.subset_source_rays);
+    intensities take their normalisation from the full bundle (oracle.source_for)."""
+    import ref_runner
     sp = dict(scene["source"])
     sp["NumberRays"] = n_full
-    first = scene["optics"][0]["support"]
-    _, _, num, inten = orc.source_for(sp, first_support=None, k=idx)
-    ez = np.array([0, 0, 1])
-    axis = np.array([1, 0, 0])
-    rays = []
-    if sp["Divergence"] == 0:
-        radius = sp["SourceSize"] / 2
-        xy = orc.spiral_vogel(n_full, radius, idx)
-        for (x, y), k in zip(xy, idx):
-            rays.append(R.mray.Ray(np.array([x, y, 0]), np.array([0, 0, 1]), Number=int(k),
-                                   Wavelength=sp["Wavelength"]))
-    else:
-        xy = orc.spiral_vogel(n_full, 1 * np.tan(sp["Divergence"]), idx)
-        for (x, y), k in zip(xy, idx):
-            rays.append(R.mray.Ray(np.array([0, 0, 0]), np.array([x, y, 1]), Number=int(k),
-                                   Wavelength=sp["Wavelength"]))
-    rays = R.mgeo.RotationRayList(rays, ez, axis)
-    rays = R.mgeo.TranslationRayList(rays, np.array([0, 0, 0]))
-    for r, i in zip(rays, inten):
-        r.intensity = np.float64(i)
-    return rays
+    _, _, _, inten = orc.source_for(sp, first_support=None, k=idx)
+    return ref_runner.subset_source_rays(scene, n_full, idx, intensities=inten)
 
 
 def gen_subsets(which):

@@ -9,7 +9,8 @@ and colorcet are not installed.  The hot path needs none of the plotting stack a
   * the plotting modules resolve to empty stub modules.
 
 Nothing under attosecondraytracing_b200/, bench.py's GPU arm or the `-m gpu` tests imports
-this module; /root/reference does not exist on the GPU box.
+this module; /root/reference does not exist on the GPU box -- there bench.py's CPU legs import the
+byte-for-byte copy oracle/make_ref.py left in oracle/_ref.
 """
 import contextlib
 import importlib
@@ -18,8 +19,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("ART_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# where the reference package `ART` is imported from: $ART_REFERENCE_ROOT, else the tree itself in the build
+# container, else the travelling byte-for-byte copy that oracle/make_ref.py leaves in oracle/_ref (GPU box)
+_TRAVEL = os.path.join(os.path.dirname(_HERE), "_ref")
+
+
+def _default_root():
+    env = os.environ.get("ART_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/ART"):
+        return "/root/reference"
+    return _TRAVEL
+
+
+REFERENCE_ROOT = _default_root()
 
 
 class _Dummy:
@@ -63,8 +78,12 @@ def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "ART"))
 
 
-def load():
-    """Return a namespace with the reference's hot-path modules (mp, mgeo, mmirror, ...)."""
+def load(root=None):
+    """Return a namespace with the reference's hot-path modules (mp, mgeo, mmirror, ...), imported from
+    `root` (default: REFERENCE_ROOT).  One root per process: `ART.*` lands in sys.modules."""
+    global REFERENCE_ROOT
+    if root is not None:
+        REFERENCE_ROOT = root
     if not available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
     for name in _STUBS:

@@ -7,7 +7,7 @@
 #include "art_b200.h"
 
 int main(void) {
-  int32_t sizes[5];
+  int32_t sizes[6];
   double rot[9];
   const double n[3] = {0.0, 0.0, 1.0}, m[3] = {1.0, 0.0, 0.0};
   const double centre[3] = {0.0, 0.0, 10.0}, normal[3] = {0.0, 0.0, -2.0}, ref[3] = {0.0, 0.0, 0.0};
@@ -17,7 +17,7 @@ int main(void) {
   if (art_abi_sizes(sizes) != ART_OK) return 2;
   if (sizes[0] != (int32_t)sizeof(ArtElementDesc) || sizes[1] != (int32_t)sizeof(ArtZernikeDesc) ||
       sizes[2] != (int32_t)sizeof(ArtBundleView) || sizes[3] != (int32_t)sizeof(ArtDetector) ||
-      sizes[4] != (int32_t)sizeof(ArtGridMapDesc))
+      sizes[4] != (int32_t)sizeof(ArtGridMapDesc) || sizes[5] != (int32_t)sizeof(ArtSourceDesc))
     return 3;
   if (art_element_rotation(n, m, rot) != ART_OK) return 4;
   for (i = 0; i < 9; ++i) bad += fabs(rot[i] - ((i % 4 == 0) ? 1.0 : 0.0)) > 1e-15;

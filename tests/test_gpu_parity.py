@@ -132,6 +132,38 @@ def test_host_buffer_entry_point(name):
     chain.close()
 
 
+@pytest.mark.parametrize("name", ["cfg3_2tor", "cfg1_par", "cfg2_tor2f", "cfg5_tele", "cfg4_zern_def"])
+def test_source_descriptor_entry_point(name):
+    """art_run_source_host: the reference's real host input -- SourceProperties -- in, statistics out.  The
+    fixtures' statistics come from the reference's own OEPlacement source (PointSource / PlaneWaveDisk +
+    ApplyGaussianIntensityToRayList, ART/ModuleProcessing.py:58-79), so this pins the device generator, the
+    device-side intensity normalisation and the whole path in one call; an empty share must not fail either."""
+    eng = _engine()
+    import attosecondraytracing_b200.ModuleSource as msrc
+    g = Golden(name)
+    chain = eng.DeviceChain(golden_optical_elements(g))
+    desc = msrc.source_descriptor(dict(g.spec["source"]))
+    assert desc.count == g["src_P"].shape[0]
+    mom, cen, det = chain.run_source(desc, g.spec["detector_distance"], ignore_defects=g.ignore_defects)
+    s = eng.summary_from_moments(mom, cen)
+    assert s["n_rays"] == g.out(g.n_elements - 1)["num"].size
+    assert abs(s["SpotSizeSD"] - g["SpotSizeSD"]) <= 1e-9
+    assert abs(s["DurationSD"] - g["DurationSD"]) <= DELAY_TOL_FS
+    assert abs(s["SpotSizeSD_w"] - g["SpotSizeSD_w"]) <= 1e-9
+    assert abs(s["DurationSD_w"] - g["DurationSD_w"]) <= DELAY_TOL_FS
+    assert abs(s["ETransmission"] - g["ETransmission"]) <= 1e-9
+    assert np.max(np.abs(np.array(det.centre[:]) - g["det_centre"])) <= point_tol(name)
+    # a strided share of the same bundle agrees with the host-column path on the same rays
+    desc2 = msrc.source_descriptor(dict(g.spec["source"]), first=1, stride=3)
+    m2, c2, _ = chain.run_source(desc2, g.spec["detector_distance"], ignore_defects=g.ignore_defects)
+    assert c2[7] == np.sum((g.out(g.n_elements - 1)["num"] - 1) % 3 == 0)
+    empty = msrc.source_descriptor(dict(g.spec["source"]), first=0, count=0)
+    m0, c0, _ = chain.run_source(empty, g.spec["detector_distance"], ignore_defects=g.ignore_defects,
+                                 manual_det=det)
+    assert m0[0] == 0 and c0[7] == 0
+    chain.close()
+
+
 def test_edge_cases_empty_ragged_and_all_blocked():
     """n = 0, n = 1, odd n (ragged 128-bit tail), and a bundle that loses every ray."""
     eng = _engine()

@@ -28,10 +28,11 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"libart_b200.so does not export {name}"
     assert declared == set(_cabi.EXPORTED_SYMBOLS), declared ^ set(_cabi.EXPORTED_SYMBOLS)
     assert lib.art_version() == 100
-    sizes = (C.c_int32 * 5)()
+    sizes = (C.c_int32 * 6)()
     assert lib.art_abi_sizes(sizes) == 0
     assert list(sizes) == [C.sizeof(t) for t in (_cabi.ArtElementDesc, _cabi.ArtZernikeDesc, _cabi.ArtBundleView,
-                                                  _cabi.ArtDetector, _cabi.ArtGridMapDesc)] == [200, 40, 88, 184, 64]
+                                                  _cabi.ArtDetector, _cabi.ArtGridMapDesc,
+                                                  _cabi.ArtSourceDesc)] == [200, 40, 88, 184, 64, 128]
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
