@@ -342,7 +342,7 @@ def optic_intersection(optic, P, U):
 # --------------------------------------------------------------------------------------
 # Zernike defects (ART/ModuleDefects.py:149-177, ART/recursive_zernike_generator.py:4-254)
 # --------------------------------------------------------------------------------------
-def zernike_gradient(x, y, max_order):
+def zernike_gradient(x, y, max_order, dtype=np.float64):
     """Andersen's Cartesian recurrences as the reference evaluates them, vectorised over rays.
 
     ART/recursive_zernike_generator.py:36-253.  Returns three dicts keyed (n, m), m = 0..n:
@@ -350,8 +350,8 @@ def zernike_gradient(x, y, max_order):
     """
     if max_order < 2:  # :37-38
         max_order = 2
-    x = np.asarray(x, dtype=np.float64)
-    y = np.asarray(y, dtype=np.float64)
+    x = np.asarray(x, dtype=dtype)  # dtype: np.longdouble for the extended-precision arbiter (art_oracle_ld.py)
+    y = np.asarray(y, dtype=dtype)
     one = np.ones_like(x)
     zero = np.zeros_like(x)
     Z = {(0, 0): one, (1, 0): y, (1, 1): x}  # :52-54
@@ -533,6 +533,69 @@ def trace_chain(P, U, elements, ignore_defects=True, numbers=None):
             "index": index.copy(), "number": np.asarray(numbers)[index], "P": P.copy(), "U": U.copy(),
             "path": path.copy(), "incidence": incidence,
         })
+    return out
+
+
+def support_edge_distance(support, x, y):
+    """Distance (mm) from (x, y) to the nearest edge LINE / CIRCLE of the support (same parameters as
+    support_include).  Used only to REPORT rays whose survival may legitimately differ between two
+    evaluations because they sit within rounding noise of an aperture edge ("bit-exact
+    survival"); the survival rule itself is support_include."""
+    kind, p = support[0], support[1:]
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+
+    def circle(R, cx=0.0, cy=0.0):
+        return np.abs(np.hypot(x - cx, y - cy) - abs(R))
+
+    def rect(X, Y, cx=0.0, cy=0.0):
+        return np.minimum(np.abs(np.abs(x - cx) - abs(X / 2)), np.abs(np.abs(y - cy) - abs(Y / 2)))
+
+    if kind == "round":
+        return circle(p[0])
+    if kind == "roundhole":
+        return np.minimum(circle(p[0]), circle(p[1], p[2], p[3]))
+    if kind == "rect":
+        return rect(p[0], p[1])
+    if kind == "recthole":
+        return np.minimum(rect(p[0], p[1]), circle(p[2], p[3], p[4]))
+    if kind == "rectrecthole":
+        return np.minimum(rect(p[0], p[1]), rect(p[2], p[3], p[4], p[5]))
+    raise ValueError(f"unknown support kind {kind!r}")
+
+
+def edge_margins(P, U, elements, ignore_defects=True):
+    """For every source ray and element: how far (mm) the ray's hit point on that element's surface lies
+    from the nearest aperture edge, NaN once the ray is lost for another reason (no intersection with the
+    unbounded surface).  The rays are traced with every support opened wide, so a ray that the true support
+    blocks still gets its margin at the blocking element; callers read the column of the element at which two
+    evaluations disagree.  Returns an (N, K) array."""
+    P = np.asarray(P, dtype=np.float64)
+    n = P.shape[0]
+    out = np.full((n, len(elements)), np.nan)
+    wide = []
+    for el in elements:
+        optic = dict(el["optic"])
+        optic["support"] = ("rect", 1e30, 1e30)
+        if optic["kind"] == "mask":
+            optic["kind"] = "plane"   # the plane hit itself; a mask only inverts the support test
+        w = dict(el)
+        w["optic"] = optic
+        wide.append(w)
+    prev_P, prev_U, prev_idx = P, normalize(np.asarray(U, dtype=np.float64)), np.arange(n)
+    for k, el in enumerate(elements):
+        step = trace_chain(prev_P, prev_U, [wide[k]], ignore_defects=ignore_defects)[0]
+        idx = prev_idx[step["index"]]
+        R = element_frame_matrix(el["normal"], el["majoraxis"])
+        C = optic_centre(el["optic"])
+        q = (step["P"] - np.asarray(el["position"], dtype=np.float64)) @ R.T + C   # hit point, element frame
+        sup = el["optic"]["support"]
+        off = C if el["optic"]["kind"] in ("parabolic", "ellipsoidal") else np.zeros(3)
+        out[idx, k] = support_edge_distance(sup, q[:, 0] - off[0], q[:, 1] - off[1])
+        if el["optic"]["kind"] == "mask":
+            prev_P, prev_U = step["P"], prev_U[step["index"]]   # a mask does not deflect
+        else:
+            prev_P, prev_U = step["P"], step["U"]
+        prev_idx = idx
     return out
 
 

@@ -169,12 +169,15 @@ def subset_source_rays(scene, n_full, idx):
 
 
 def gen_subsets(which):
+    # M = 10^4 seeded indices per full-size bundle (SURVEY.md 8(d) "parity check at scale");
+    # of the three cfg5 sweep variants the middle one carries 10^4 rays, the end points 1000 each (fixture size)
     todo = {
-        "cfg2_sub": ("cfg2", 2000, [True]),
-        "cfg3_sub": ("cfg3", 2000, [True]),
-        "cfg4_sub": ("cfg4", 1500, [True, False]),
-        "cfg5_sub": ("cfg5", 1000, [True]),
+        "cfg2_sub": ("cfg2", 10000, [True]),
+        "cfg3_sub": ("cfg3", 10000, [True]),
+        "cfg4_sub": ("cfg4", 10000, [True, False]),
+        "cfg5_sub": ("cfg5", 10000, [True]),
     }
+    small_variant_rays = 1000
     for name, (wl, m, modes) in todo.items():
         if which and name not in which:
             continue
@@ -182,7 +185,6 @@ def gen_subsets(which):
         scene = sc.resolve(w["scene"])
         n_full = w["rays"]
         n_src = n_full - 1 if scene["source"]["Divergence"] == 0 else n_full  # PlaneWaveDisk off-by-one
-        idx = np.sort(np.random.default_rng(1234).choice(n_src, m, replace=False))
         variants = [None]
         if "sweep" in w:
             sw = w["sweep"]
@@ -201,6 +203,8 @@ def gen_subsets(which):
                     extra["variant_index"] = var[0]
                 if len(modes) > 1:
                     tag += "_ign" if ign else "_def"
+                m_here = small_variant_rays if (var is not None and var[0] != 300) else m
+                idx = np.sort(np.random.default_rng(1234).choice(n_src, m_here, replace=False))
                 rays = subset_source_rays(scn, n_full, idx)
                 data, counts, dt = run_scene(scn, ignore_defects=ign, source_rays=rays, extra=extra)
                 p = save(tag, data)

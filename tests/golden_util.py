@@ -150,9 +150,46 @@ def golden_optical_elements(g):
     return out
 
 
+EDGE_EPS_MM = 1e-9   # rays closer than this to an aperture edge may legitimately flip between two evaluations
+EDGE_REPORT = []     # (fixture, element, ray number, margin in mm) of every excused ray, for the test log
+
+
+def survivors_agree(name, k, ref_num, number):
+    """Ray numbering / survival is compared BIT-EXACT.  When the two survivor sets differ, the disputed rays
+    are looked up: a ray whose hit point on element <= k lies within EDGE_EPS_MM of an aperture edge is
+    REPORTED (EDGE_REPORT, printed) and excused -- the `<=` of the support tests is taken on freshly computed
+    coordinates, so two correct evaluations can disagree there; any other disputed ray
+    fails the test.  Returns the numbers both sides keep."""
+    ref_num, number = np.asarray(ref_num), np.asarray(number)
+    if np.array_equal(number, ref_num):
+        return ref_num
+    disputed = np.setxor1d(ref_num, number)
+    try:
+        g = Golden(name)
+    except Exception:
+        raise AssertionError(f"{name}: survivors differ after element {k}: rays {disputed[:10]}")
+    import art_oracle as orc
+    pos = {int(nn): i for i, nn in enumerate(g["src_num"])}
+    rows = np.array([pos[int(d)] for d in disputed])
+    margins = orc.edge_margins(g["src_P"][rows], g["src_U"][rows], g.oracle_elements()[: k + 1],
+                               ignore_defects=g.ignore_defects)
+    worst = np.nanmin(margins, axis=1)
+    bad = [(int(d), float(m)) for d, m in zip(disputed, worst) if not m <= EDGE_EPS_MM]
+    assert not bad, f"{name}: survivors differ after element {k} away from any aperture edge: {bad[:10]}"
+    for d, m in zip(disputed, worst):
+        EDGE_REPORT.append((name, k, int(d), float(m)))
+        print(f"[edge report] {name}: ray {int(d)} is {m:.2e} mm from an aperture edge (element <= {k}); survival "
+              "differs between the two evaluations and is excused")
+    return np.intersect1d(ref_num, number)
+
+
 def compare_bundle(name, k, ref, number, P, U, path, inc, check_inc=True):
     """The parity bars of the north star for the bundle after element k; returns the max deviations."""
-    assert np.array_equal(number, ref["num"]), f"{name}: survivors differ after element {k}"
+    common = survivors_agree(name, k, ref["num"], number)
+    if common.size != ref["num"].size or common.size != np.asarray(number).size:
+        keep_r, keep_g = np.isin(ref["num"], common), np.isin(number, common)
+        ref = {key: np.asarray(v)[keep_r] for key, v in ref.items()}
+        P, U, path, inc = P[keep_g], U[keep_g], path[keep_g], inc[keep_g]
     if ref["num"].size == 0:
         return {}
     tol = point_tol(name)
