@@ -90,21 +90,27 @@ class GridDefect(Defect):
 
 
 class MeasuredMap(GridDefect):
-    """MeasuredMap(Support, Map): a measured height map (mm) covering twice the support's circumscribed
-    rectangle (X in [-rect_x, rect_x], ART/ModuleDefects.py:34-47).  The reference computes the slopes with
-    `np.gradient(Map, rect / Map.shape)`, which raises TypeError under numpy >= 2, and pairs an
-    (nx, ny) grid with the transposed map, which only fits square maps.  Implemented here with one
-    self-consistent convention -- Map[ix, iy], one sample spacing per axis -- since no reference output
-    exists to pin it."""
+    """MeasuredMap(Support, Map): a measured height map (mm), ART/ModuleDefects.py:34-61.
+
+    The reference's semantics, kept literally: the map spans X in [-rect_x, rect_x], Y in [-rect_y, rect_y] with
+    rect = Support._CircumRect(); slopes are `np.gradient(Map, rect_x / n0, rect_y / n1)` (the reference writes
+    `np.gradient(Map, rect / Map.shape)`, which numpy rejects; one spacing per axis is the evident intent -- the
+    compatibility patch of oracle/make_ref.py); the interpolators pair the grid (X[n0], Y[n1]) with the
+    TRANSPOSED arrays (:45-47), so the value at (X[i], Y[j]) is Map[j, i] -- which, as in the reference, only fits
+    square maps.  Pinned by tests/golden/par_measured_*.npz (oracle/gen_golden_gridmap.py)."""
 
     def __init__(self, Support, Map):
         self.deformation = np.asarray(Map, dtype=np.float64)
+        if self.deformation.ndim != 2 or self.deformation.shape[0] != self.deformation.shape[1]:
+            raise ValueError("MeasuredMap needs a square 2-D map (the reference pairs an (n0, n1) grid with the "
+                             "transposed map, ART/ModuleDefects.py:45-47)")
         self.Support = Support
         rect = Support._CircumRect()
         spacing = rect / self.deformation.shape
         self.DerivX, self.DerivY = np.gradient(self.deformation, spacing[0], spacing[1])
         self.rms = np.std(self.deformation)
-        self._set_grid(self.deformation, self.DerivX, self.DerivY, -rect[0], rect[0], -rect[1], rect[1])
+        self._set_grid(np.transpose(self.deformation), np.transpose(self.DerivX), np.transpose(self.DerivY),
+                       -rect[0], rect[0], -rect[1], rect[1])
 
 
 class Fourrier(GridDefect):

@@ -76,9 +76,9 @@ struct ArtChain {
 #ifndef ART_GRID_PER_SM
 #define ART_GRID_PER_SM 2  // blocks per SM of the grid-stride kernels = the resident count: a persistent grid (measured 8 -> 2: cfg2 step 0.414 -> 0.397 ms, fewer block prologues and partial rows)
 #endif
-static int blocks_per_variant(const ArtChain* c, long long n, int n_variants, int per_thread = RPT) {
+static int blocks_per_variant(const ArtChain* c, long long n, int n_variants, int per_thread = RPT, int tpb = TPB) {
   const long long npairs = (n + per_thread - 1) / per_thread;
-  long long maxb = (npairs + TPB - 1) / TPB;
+  long long maxb = (npairs + tpb - 1) / tpb;
   if (maxb < 1) maxb = 1;
   // one variant: a persistent grid; several variants share the SMs block by block, so keep enough blocks
   // for the last wave to be full (1024 variants x 1 block left the tail at 46 %: 87.7 -> 92.7 ms on cfg5)
@@ -230,6 +230,8 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
           return fail(ART_E_INVALID, "variants must share surface / support kinds and defects");
       }
     }
+  for (int v = 0; v < n_variants; ++v)  // hand-over maps between consecutive elements of each variant
+    for (int k = 0; k + 1 < n_elements; ++k) link_elements(h[(size_t)v * n_elements + k], h[(size_t)v * n_elements + k + 1]);
   std::vector<double> ztab;
   std::vector<int> zoff;
   for (int i = 0; i < n_defects; ++i) {
@@ -271,9 +273,9 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
   if (c->smem_bytes > 200 * 1024) return bail(ART_E_UNSUPPORTED, "Zernike tables exceed 200 KB of shared memory");
   {
     // dynamic shared memory: tables | moment slots (fused detector) | cp.async input stages (plain trace)
-    const size_t fused = c->smem_bytes + SMEM_MOMENTS_BYTES;
-    const size_t plain = c->smem_bytes + STAGE_BYTES;
 #define ART_ALLOW(DEFS, SURF)                                                      \
+  fused = c->smem_bytes + smem_moments_bytes(trace_block_threads(DEFS, SURF));     \
+  plain = c->smem_bytes + stage_bytes(trace_block_threads(DEFS, SURF));            \
   CK(allow_smem(trace_kernel<true, false, DEFS, SURF, false>, plain));             \
   CK(allow_smem(trace_kernel<false, false, DEFS, SURF, false>, plain));            \
   CK(allow_smem(trace_kernel<true, true, DEFS, SURF, false>, fused));              \
@@ -282,6 +284,7 @@ extern "C" int32_t art_chain_create(const ArtElementDesc* elements, int32_t n_el
   CK(allow_smem(trace_kernel<false, false, DEFS, SURF, true>, plain));             \
   CK(allow_smem(trace_kernel<true, true, DEFS, SURF, true>, fused));               \
   CK(allow_smem(trace_kernel<false, true, DEFS, SURF, true>, fused));
+    size_t fused = 0, plain = 0;
     ART_ALLOW(true, SURFS_ANY)
     ART_ALLOW(false, SURFS_ANY)
     ART_ALLOW(false, SURFS_TOROID)
@@ -330,7 +333,7 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
                             const ArtDetector* det, double* x_out, double* y_out, double* l_out,
                             double* central_out, double* moments_out, cudaStream_t st, bool keep_l2 = false,
                             double place_distance = 0.0, ArtDetector* place_det = nullptr, int chunk_blocks = 0,
-                            int chunk_row0 = 0) {
+                            int chunk_row0 = 0, const double* wstate = nullptr, double wcoef = 0.0) {
   // chunk_blocks > 0: this launch is one chunk of a pipelined trace -- it uses exactly chunk_blocks
   // blocks, writes its partial rows at chunk_row0 and leaves the fold to the caller
   if (!c) return fail(ART_E_INVALID, "chain is NULL");
@@ -385,7 +388,9 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
   a.y_out = y_out;
   a.l_out = l_out;
 
-  const int bpv = chunk_blocks > 0 ? chunk_blocks : blocks_per_variant(c, in->n, n_variants, ART_RPT);
+  const int surfs_class = c->has_defects ? SURFS_ANY : c->surfs;
+  const int bt = trace_block_threads(c->has_defects, surfs_class);  // threads per block of this chain's kernels
+  const int bpv = chunk_blocks > 0 ? chunk_blocks : blocks_per_variant(c, in->n, n_variants, ART_RPT, bt);
   if ((size_t)bpv * n_variants + chunk_row0 > c->partial_rows)
     return fail(ART_E_INVALID, "internal: partial buffer too small");
   if (chunk_blocks > 0) a.partials = c->d_partials + (size_t)chunk_row0 * PLEN_TRACE;
@@ -394,14 +399,17 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
   a.stage_smem_offset = (int)c->smem_bytes;
   a.keep_l2 = keep_l2 ? 1 : 0;
   a.uniform_point = uniform_point ? 1 : 0;
-  const size_t sm = c->smem_bytes + (det ? (size_t)SMEM_MOMENTS_BYTES : (size_t)STAGE_BYTES);
+  a.wstate = wstate;
+  a.wcoef = wcoef;
+  if (wstate && !in->intensity) return fail(ART_E_INVALID, "internal: computed weights need an intensity column");
+  const size_t sm = c->smem_bytes + (det ? (size_t)smem_moments_bytes(bt) : (size_t)stage_bytes(bt));
   // Zernike chains run the general kernel; defect-free chains one specialised for their surface class
 #define ART_TRACE_LAUNCH2(INC, DET, UPT)                                                                      \
   do {                                                                                                       \
-    if (c->has_defects) trace_kernel<INC, DET, true, SURFS_ANY, UPT><<<grid, TPB, sm, st>>>(a);              \
-    else if (c->surfs == SURFS_TOROID) trace_kernel<INC, DET, false, SURFS_TOROID, UPT><<<grid, TPB, sm, st>>>(a);   \
-    else if (c->surfs == SURFS_QUADRIC) trace_kernel<INC, DET, false, SURFS_QUADRIC, UPT><<<grid, TPB, sm, st>>>(a); \
-    else trace_kernel<INC, DET, false, SURFS_ANY, UPT><<<grid, TPB, sm, st>>>(a);                            \
+    if (c->has_defects) trace_kernel<INC, DET, true, SURFS_ANY, UPT><<<grid, bt, sm, st>>>(a);              \
+    else if (c->surfs == SURFS_TOROID) trace_kernel<INC, DET, false, SURFS_TOROID, UPT><<<grid, bt, sm, st>>>(a);   \
+    else if (c->surfs == SURFS_QUADRIC) trace_kernel<INC, DET, false, SURFS_QUADRIC, UPT><<<grid, bt, sm, st>>>(a); \
+    else trace_kernel<INC, DET, false, SURFS_ANY, UPT><<<grid, bt, sm, st>>>(a);                            \
   } while (0)
 #define ART_TRACE_LAUNCH(INC, DET)                       \
   do {                                                   \
@@ -516,6 +524,38 @@ extern "C" int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bu
   if ((size_t)bpv * n_variants > chain->partial_rows)
     return fail(ART_E_INVALID, "n_variants exceeds the chain's variant count");
   cudaStream_t st = (cudaStream_t)stream;
+  // Bulk-copy kernel (copy engine + mbarrier ring) whenever the rows of every variant keep the 16-byte alignment
+  // the engine needs and there is at least one full tile; the LDGSTS kernel otherwise (ART_B200_DET_LEGACY=1
+  // forces it, for A/B measurements).
+  static const bool legacy = std::getenv("ART_B200_DET_LEGACY") != nullptr;
+  const bool rows_aligned = n_variants == 1 || a.n % 16 == 0;
+  const bool flags_aligned = !a.b.alive || aligned16(a.b.alive);
+  if (!legacy && rows_aligned && flags_aligned && a.n >= DB_TILE) {
+    static std::mutex attr_mutex;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    ART_CUDA(cudaGetDevice(&dev));
+    {
+      std::lock_guard<std::mutex> lock(attr_mutex);
+      if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        ART_CUDA(cudaFuncSetAttribute(detector_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES));
+        attr_done[dev] = true;
+      }
+    }
+    // one resident block per SM (ART_DB_MINB): a persistent grid over the tiles
+    const long long tiles = a.n / DB_TILE;
+    const long long target = (long long)chain->sm_count * ART_DB_MINB * (n_variants > 1 ? 4 : 1);
+    long long bulk_bpv = (target + n_variants - 1) / n_variants;
+    if (bulk_bpv > tiles) bulk_bpv = tiles;
+    if (bulk_bpv < 1) bulk_bpv = 1;
+    if ((size_t)bulk_bpv * n_variants > chain->partial_rows)
+      return fail(ART_E_INVALID, "n_variants exceeds the chain's variant count");
+    detector_bulk_kernel<<<dim3((unsigned)bulk_bpv, n_variants), DB_THREADS, DB_SMEM_BYTES, st>>>(a);
+    ART_LAUNCHED();
+    fold_kernel<<<n_variants, TPB, 0, st>>>(chain->d_partials, (int)bulk_bpv, 2, nullptr, moments_out);
+    ART_LAUNCHED();
+    return ART_OK;
+  }
   detector_kernel<<<dim3(bpv, n_variants), TPB, DET_STAGE_BYTES, st>>>(a);
   ART_LAUNCHED();
   fold_kernel<<<n_variants, TPB, 0, st>>>(chain->d_partials, bpv, 2, nullptr, moments_out);
@@ -1039,6 +1079,7 @@ extern "C" int32_t art_run_source_host(ArtChain* c, const ArtSourceDesc* src, ui
   source_kernel<<<(unsigned)bx, TPB, 0, st>>>(a);
   ART_LAUNCHED();
   int exchanges = 0;
+  double fraction = 0.0;
   if (weighted) {
     // axis = normalised mean direction of the WHOLE bundle; then the largest angle to it / largest |P|
     fold_kernel<<<1, TPB, 0, st>>>(c->d_partials, (int)bx, 0, c->d_central, nullptr);
@@ -1050,34 +1091,22 @@ extern "C" int32_t art_run_source_host(ArtChain* c, const ArtSourceDesc* src, ui
     }
     source_axis_kernel<<<1, 32, 0, st>>>(c->d_central, w.src_state);
     ART_LAUNCHED();
-    IntensityArgs ia;
-    ia.b = to_dev(&din);
-    if (point) ia.b.px = ia.b.py = ia.b.pz = nullptr;  // |P| is the same for all rays; a diverging bundle uses angles
-    ia.n = (long long)n;
-    for (int i = 0; i < 3; ++i) ia.axis[i] = 0.0;
-    ia.pass = 0;
-    ia.mode = 0;
-    ia.scale = 1.0;
-    ia.lnf = 0.0;
-    ia.state = w.src_state;
-    ia.partials = c->d_partials;
-    const int iblocks = c->sm_count * 4;
-    intensity_kernel<<<iblocks, TPB, 0, st>>>(ia);
+    ExtentArgs ea;
+    ea.src = a;
+    ea.state = w.src_state;
+    ea.partials = c->d_partials;
+    const int iblocks = c->sm_count * 2;
+    source_extents_kernel<<<iblocks, TPB, 0, st>>>(ea);
     ART_LAUNCHED();
-    extents_fold_kernel<<<1, 32, 0, st>>>(c->d_partials, iblocks, w.src_state + 3);
+    source_extents_fold<<<1, 32, 0, st>>>(c->d_partials, iblocks, w.src_state);
     ART_LAUNCHED();
     if (peer_bufs) {
       rc = art_peer_exchange(peer_bufs, rank, world, 2, 1, w.src_state + 3, 0.0, nullptr, st);
       if (rc) return rc;
       ++exchanges;
     }
-    double fraction = src->intensity_fraction;
+    fraction = src->intensity_fraction;
     if (!(fraction > 0.0 && fraction < 1.0)) fraction = 0.1353352832366127;  // 1/e^2, ART/ModuleSource.py:233-238
-    ia.pass = 1;
-    ia.lnf = -0.5 * std::log(fraction);
-    ia.partials = nullptr;
-    intensity_kernel<<<iblocks, TPB, 0, st>>>(ia);
-    ART_LAUNCHED();
   }
 
   ArtBundleView dout = {};
@@ -1088,8 +1117,11 @@ extern "C" int32_t art_run_source_host(ArtChain* c, const ArtSourceDesc* src, ui
   dout.alive = w.alive;
   ArtBundleView tout = dout;
   dout.intensity = din.intensity;
+  // the Gaussian weights are computed inside the trace kernel from the device source state (and left in the
+  // intensity column for the detector kernel)
   rc = launch_trace(c, 0, 1, &din, &tout, nullptr, flags | ART_TRACE_NO_INCIDENCE, nullptr, nullptr, nullptr, nullptr,
-                    c->d_central, nullptr, st);
+                    c->d_central, nullptr, st, false, 0.0, nullptr, 0, 0, weighted ? w.src_state : nullptr,
+                    weighted ? std::log(fraction) : 0.0);
   if (rc) return rc;
   return statistics_tail(c, &dout, n, false, nullptr, distance, manual_det, moments_host, central_host, det_host,
                          peer_bufs, rank, world, exchanges);

@@ -30,6 +30,8 @@ struct __align__(16) ElemDev {
   double sp[6];    // surface parameters, pre-digested (see lower_element)
   double ap[6];    // support parameters, pre-digested
   double soff[2];  // (x,y) subtracted before the support test (parabola / ellipsoid: centre)
+  double nrot[9];  // this element's frame -> the NEXT element's frame: p' = nrot h + noff, u' = nrot u
+  double noff[3];  // (link_elements, art_lowering.h; unused for the last element of a chain)
   int32_t surface;
   int32_t support;
   int32_t n_defects;

@@ -50,6 +50,10 @@ struct TraceArgs {
   int stage_smem_offset;    // byte offset of the cp.async input stages in dynamic smem (plain trace)
   int keep_l2;              // final-bundle stores with the default cache policy (re-read from L2 next)
   int uniform_point;        // in.px/py/pz point to one double each (ART_TRACE_UNIFORM_POINT)
+  const double* wstate;     // null, or the device source state (axis, largest angle, largest |P|): the Gaussian
+                            // intensity of every source ray is then COMPUTED here (ApplyGaussianIntensityToRayList,
+                            // ART/ModuleSource.py:219-261) and written to in.inten instead of being read from it
+  double wcoef;             // ln(IntensityFraction)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -103,8 +107,8 @@ __device__ __forceinline__ double red_any(int op, double a, double b) {
   return op == 0 ? a + b : (op == 1 ? fmin(a, b) : fmax(a, b));
 }
 
-template <int NV, typename V, typename OPF>
-__device__ __forceinline__ void block_reduce_row(const V& v, OPF opf, double* smem /* NWARP*NV */,
+template <int NV, int BT = TPB, typename V, typename OPF>
+__device__ __forceinline__ void block_reduce_row(const V& v, OPF opf, double* smem /* (BT/32)*NV */,
                                                  double* __restrict__ out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -116,10 +120,10 @@ __device__ __forceinline__ void block_reduce_row(const V& v, OPF opf, double* sm
     if (lane == 0) smem[warp * NV + j] = x;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < NV; j += TPB) {
+  for (int j = threadIdx.x; j < NV; j += BT) {
     const int op = opf(j);
     double x = smem[j];
-    for (int w = 1; w < NWARP; ++w) x = red_any(op, x, smem[w * NV + j]);
+    for (int w = 1; w < BT / 32; ++w) x = red_any(op, x, smem[w * NV + j]);
     out[j] = x;
   }
 }
@@ -153,14 +157,15 @@ __device__ __forceinline__ DetHit detector_ray(const ArtDetector& D, const Ray& 
   return h;
 }
 
-// Per-thread moment accumulators living in shared memory (slot j of thread t at base[j * TPB + t]):
+// Per-thread moment accumulators living in shared memory (slot j of thread t at base[j * BT + t], BT threads per block):
 // 24 doubles per thread would otherwise cost 48 registers for the whole kernel lifetime.
+template <int BT>
 struct SmemMoments {
   volatile double* base;  // &slots[0][threadIdx.x]; volatile keeps the compiler from promoting the slots back
                           // into registers across the ray loop
-  __device__ __forceinline__ volatile double& operator[](int j) const { return base[j * TPB]; }
+  __device__ __forceinline__ volatile double& operator[](int j) const { return base[j * BT]; }
 };
-constexpr int SMEM_MOMENTS_BYTES = ART_MOMENTS_LEN * TPB * (int)sizeof(double);
+constexpr int smem_moments_bytes(int bt) { return ART_MOMENTS_LEN * bt * (int)sizeof(double); }
 
 template <class ACC>
 __device__ __forceinline__ void moments_init(ACC& m) {
@@ -249,7 +254,7 @@ __device__ __forceinline__ void moments_finish(ACC& m) {
 // the source columns is hidden behind the FP64 work without costing registers.  Slots are private
 // to the issuing thread: cp.async.wait_group is the only synchronisation needed.
 constexpr int STAGE_COLS = 8;  // px py pz ux uy uz intensity path
-constexpr int STAGE_BYTES = 2 * STAGE_COLS * TPB * 16;
+constexpr int stage_bytes(int bt) { return 2 * STAGE_COLS * bt * 16; }
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
@@ -327,8 +332,29 @@ __device__ __forceinline__ void store_bundle(const BundleDev& O, long long at, b
   }
 }
 
+// Threads per block of a trace kernel instantiation, by what the chain contains (two blocks per SM are resident;
+// the register budget per thread follows: 65536 / (2 BT)).  Measured on B200 (profiles/r02_summary.md): the
+// lock-step pair of the defect-free chains fits 128 registers without spilling, the Zernike recurrences need ~168.
+#ifndef ART_BT_QUADRIC
+#define ART_BT_QUADRIC 256
+#endif
+#ifndef ART_BT_TOROID
+#define ART_BT_TOROID 256
+#endif
+#ifndef ART_BT_ANY
+#define ART_BT_ANY 256
+#endif
+#ifndef ART_BT_DEF
+#define ART_BT_DEF 192
+#endif
+__host__ __device__ constexpr int trace_block_threads(bool has_def, int surfs) {
+  return has_def ? ART_BT_DEF : (surfs == SURFS_TOROID ? ART_BT_TOROID : (surfs == SURFS_QUADRIC ? ART_BT_QUADRIC : ART_BT_ANY));
+}
+
 template <bool WANT_INC, bool WITH_DET, bool HAS_DEF, int SURFS, bool UPT>
-__global__ void __launch_bounds__(TPB, HAS_DEF ? ART_MINB_DEF : ART_MINB) trace_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(trace_block_threads(HAS_DEF, SURFS), HAS_DEF ? ART_MINB_DEF : ART_MINB)
+    trace_kernel(const TraceArgs a) {
+  constexpr int BT = trace_block_threads(HAS_DEF, SURFS);
   constexpr int N = ART_RPT;
   // two rays in lock-step (lane pack D2).  With 256-thread blocks (128 registers) the Zernike evaluation did
   // not fit two lanes; with 192-thread blocks it does (cfg4 trace 0.177 -> 0.150 ms per 2e6 rays)
@@ -343,10 +369,10 @@ __global__ void __launch_bounds__(TPB, HAS_DEF ? ART_MINB_DEF : ART_MINB) trace_
   double* sZ = reinterpret_cast<double*>(smem_raw + sizeof(ElemDev) * ART_MAX_ELEMENTS);
   int* sZoff = reinterpret_cast<int*>(sZ + a.ztab_len);
   constexpr int PLEN = WITH_DET ? PLEN_FUSED : PLEN_TRACE;
-  __shared__ double sRed[NWARP * PLEN];
+  __shared__ double sRed[(BT / 32) * PLEN];
   __shared__ ArtDetector sDet;
 #if ART_SMEM_ACC
-  __shared__ double sAcc[ART_CENTRAL_LEN][TPB];
+  __shared__ double sAcc[ART_CENTRAL_LEN][BT];
 #define ART_ACC(j) sAcc[j][threadIdx.x]
 #else
   double c[ART_CENTRAL_LEN];
@@ -358,13 +384,13 @@ __global__ void __launch_bounds__(TPB, HAS_DEF ? ART_MINB_DEF : ART_MINB) trace_
     const double* src = reinterpret_cast<const double*>(a.elems + (size_t)(a.variant_first + v) * a.n_elements);
     double* dst = reinterpret_cast<double*>(sE);
     const int nd = a.n_elements * (int)(sizeof(ElemDev) / sizeof(double));
-    for (int i = threadIdx.x; i < nd; i += TPB) dst[i] = src[i];
-    for (int i = threadIdx.x; i < a.ztab_len; i += TPB) sZ[i] = a.ztab[i];
-    for (int i = threadIdx.x; i < a.n_defects; i += TPB) sZoff[i] = a.zoff[i];
+    for (int i = threadIdx.x; i < nd; i += BT) dst[i] = src[i];
+    for (int i = threadIdx.x; i < a.ztab_len; i += BT) sZ[i] = a.ztab[i];
+    for (int i = threadIdx.x; i < a.n_defects; i += BT) sZoff[i] = a.zoff[i];
     if (WITH_DET) {
       const double* ds = reinterpret_cast<const double*>(a.det + v);
       double* dd = reinterpret_cast<double*>(&sDet);
-      for (int i = threadIdx.x; i < (int)(sizeof(ArtDetector) / sizeof(double)); i += TPB) dd[i] = ds[i];
+      for (int i = threadIdx.x; i < (int)(sizeof(ArtDetector) / sizeof(double)); i += BT) dd[i] = ds[i];
     }
   }
 #pragma unroll
@@ -383,6 +409,21 @@ __global__ void __launch_bounds__(TPB, HAS_DEF ? ART_MINB_DEF : ART_MINB) trace_
     __syncthreads();
   }
   const double* const eorg0 = (UPT && ART_UPT_HOIST) ? sOrg : nullptr;
+  // Gaussian source weights computed in registers: I = exp(ln(f) (tan(angle(axis, u)) / D)^2) for a diverging
+  // bundle (D = largest angle > 1e-12), else exp(ln(f) (|P| / max |P|)^2).  tan^2 = |axis x u|^2 / (axis.u)^2
+  // needs neither the angle nor a square root.
+  __shared__ double sW[5];  // axis, ln(f) / scale^2, mode
+  if (a.wstate) {
+    if (threadIdx.x == 0) {
+      const bool by_angle = a.wstate[3] > 1e-12;
+      const double scale = by_angle ? a.wstate[3] : a.wstate[4];
+      sW[0] = a.wstate[0]; sW[1] = a.wstate[1]; sW[2] = a.wstate[2];
+      sW[3] = a.wcoef / (scale * scale);
+      sW[4] = by_angle ? 0.0 : 1.0;
+    }
+    __syncthreads();
+  }
+  const bool load_w = a.in.inten != nullptr && a.wstate == nullptr;
 
   const bool ignore_defects = (a.flags & ART_TRACE_IGNORE_DEFECTS) != 0;
   const long long n = a.n;
@@ -392,24 +433,24 @@ __global__ void __launch_bounds__(TPB, HAS_DEF ? ART_MINB_DEF : ART_MINB) trace_
   const int last = a.n_elements - 1;
 
   // fused detector: per-thread moment slots behind the tables in dynamic shared memory
-  SmemMoments m;
+  SmemMoments<BT> m;
   m.base = reinterpret_cast<double*>(smem_raw + a.moments_smem_offset) + threadIdx.x;
   if constexpr (WITH_DET) moments_init(m);
 
   double2* const sStage = reinterpret_cast<double2*>(smem_raw + a.stage_smem_offset) + threadIdx.x;
   auto stage_issue = [&](int stage, long long it) {
     const long long ii = it * 2;
-    double2* b = sStage + stage * STAGE_COLS * TPB;
+    double2* b = sStage + stage * STAGE_COLS * BT;
     if (!UPT) {
-      cp_async16(b + 0 * TPB, a.in.px + ii); cp_async16(b + 1 * TPB, a.in.py + ii); cp_async16(b + 2 * TPB, a.in.pz + ii);
+      cp_async16(b + 0 * BT, a.in.px + ii); cp_async16(b + 1 * BT, a.in.py + ii); cp_async16(b + 2 * BT, a.in.pz + ii);
     }
-    cp_async16(b + 3 * TPB, a.in.ux + ii); cp_async16(b + 4 * TPB, a.in.uy + ii); cp_async16(b + 5 * TPB, a.in.uz + ii);
-    if (a.in.inten) cp_async16(b + 6 * TPB, a.in.inten + ii);
-    if (a.in.path) cp_async16(b + 7 * TPB, a.in.path + ii);
+    cp_async16(b + 3 * BT, a.in.ux + ii); cp_async16(b + 4 * BT, a.in.uy + ii); cp_async16(b + 5 * BT, a.in.uz + ii);
+    if (load_w) cp_async16(b + 6 * BT, a.in.inten + ii);
+    if (a.in.path) cp_async16(b + 7 * BT, a.in.path + ii);
     cp_async_commit();
   };
-  const long long stride = (long long)gridDim.x * TPB;
-  long long item = (long long)blockIdx.x * TPB + threadIdx.x;
+  const long long stride = (long long)gridDim.x * BT;
+  long long item = (long long)blockIdx.x * BT + threadIdx.x;
   int stage = 0;
   bool staged = STAGE && item < nitems && (item * 2 + 1 < n);
   if (staged) stage_issue(0, item);
@@ -424,20 +465,20 @@ __global__ void __launch_bounds__(TPB, HAS_DEF ? ART_MINB_DEF : ART_MINB) trace_
     if (staged) {
       if (staged_next) cp_async_wait<1>();
       else cp_async_wait<0>();
-      const double2* b = sStage + stage * STAGE_COLS * TPB;
+      const double2* b = sStage + stage * STAGE_COLS * BT;
       double2 v;
       if (UPT) {  // point source: one origin for all rays (re-read per pair: an L1 hit, no live registers)
         r[0].px = r[N - 1].px = a.in.px[0]; r[0].py = r[N - 1].py = a.in.py[0]; r[0].pz = r[N - 1].pz = a.in.pz[0];
       } else {
-        v = b[0 * TPB]; r[0].px = v.x; r[N - 1].px = v.y;
-        v = b[1 * TPB]; r[0].py = v.x; r[N - 1].py = v.y;
-        v = b[2 * TPB]; r[0].pz = v.x; r[N - 1].pz = v.y;
+        v = b[0 * BT]; r[0].px = v.x; r[N - 1].px = v.y;
+        v = b[1 * BT]; r[0].py = v.x; r[N - 1].py = v.y;
+        v = b[2 * BT]; r[0].pz = v.x; r[N - 1].pz = v.y;
       }
-      v = b[3 * TPB]; r[0].ux = v.x; r[N - 1].ux = v.y;
-      v = b[4 * TPB]; r[0].uy = v.x; r[N - 1].uy = v.y;
-      v = b[5 * TPB]; r[0].uz = v.x; r[N - 1].uz = v.y;
-      if (a.in.inten) { v = b[6 * TPB]; w[0] = v.x; w[N - 1] = v.y; } else { w[0] = w[N - 1] = 1.0; }
-      if (a.in.path) { v = b[7 * TPB]; r[0].path = v.x; r[N - 1].path = v.y; } else { r[0].path = r[N - 1].path = 0.0; }
+      v = b[3 * BT]; r[0].ux = v.x; r[N - 1].ux = v.y;
+      v = b[4 * BT]; r[0].uy = v.x; r[N - 1].uy = v.y;
+      v = b[5 * BT]; r[0].uz = v.x; r[N - 1].uz = v.y;
+      if (load_w) { v = b[6 * BT]; w[0] = v.x; w[N - 1] = v.y; } else { w[0] = w[N - 1] = 1.0; }
+      if (a.in.path) { v = b[7 * BT]; r[0].path = v.x; r[N - 1].path = v.y; } else { r[0].path = r[N - 1].path = 0.0; }
     } else {
       double t[N];
 #define ART_LD(colp, field)                      \
@@ -457,7 +498,7 @@ __global__ void __launch_bounds__(TPB, HAS_DEF ? ART_MINB_DEF : ART_MINB) trace_
         for (int q = 0; q < N; ++q) r[q].path = 0.0;
       }
 #undef ART_LD
-      if (a.in.inten) {
+      if (load_w) {
         load_rays<N>(a.in.inten, i, two, w);
       } else {
 #pragma unroll
@@ -470,6 +511,26 @@ __global__ void __launch_bounds__(TPB, HAS_DEF ? ART_MINB_DEF : ART_MINB) trace_
       if (a.in.alive && r[q].alive) r[q].alive = a.in.alive[i + q] != 0;
       r[q].inc = ART_NAN;
     }
+    if (a.wstate) {
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        double q2;
+        if (sW[4] == 0.0) {
+          const double cx = fma(sW[1], r[q].uz, -(sW[2] * r[q].uy)), cy = fma(sW[2], r[q].ux, -(sW[0] * r[q].uz)),
+                       cz = fma(sW[0], r[q].uy, -(sW[1] * r[q].ux));
+          const double dt = fma(sW[0], r[q].ux, fma(sW[1], r[q].uy, sW[2] * r[q].uz));
+          q2 = fdiv(fma(cx, cx, fma(cy, cy, cz * cz)), dt * dt);
+        } else {
+          q2 = fma(r[q].px, r[q].px, fma(r[q].py, r[q].py, r[q].pz * r[q].pz));
+        }
+        w[q] = exp(q2 * sW[3]);
+      }
+      if (N == 2 && two) {
+        *reinterpret_cast<double2*>(a.in.inten + i) = make_double2(w[0], w[N - 1]);
+      } else {
+        a.in.inten[i] = w[0];
+      }
+    }
     {
       double win = 0.0;
 #pragma unroll
@@ -478,14 +539,24 @@ __global__ void __launch_bounds__(TPB, HAS_DEF ? ART_MINB_DEF : ART_MINB) trace_
       ART_ACC(ART_C_SW_IN) += win;
     }
 
+    // Between elements the rays are handed over straight in the next element's frame (apply_element); the
+    // lab-frame bundle after an inner element is materialised only when the caller wants the history.
     if constexpr (PACK) {
       RayT<D2> pr = pack_rays(r[0], r[N - 1]);
       for (int k = 0; k < a.n_elements; ++k) {
         const bool inc_here = WANT_INC && (k == last || a.has_hist);
-        if (any(pr.alive)) apply_element<WANT_INC, HAS_DEF, SURFS, D2>(sE[k], pr, sZ, sZoff, ignore_defects, inc_here, a.maps,
-                                                                         k == 0 ? eorg0 : nullptr);
+        const bool inner = k != last;
+        if (any(pr.alive))
+          apply_element<WANT_INC, HAS_DEF, SURFS, D2>(sE[k], pr, sZ, sZoff, ignore_defects, inc_here, a.maps,
+                                                      k == 0 ? eorg0 : nullptr, k != 0, inner);
         if (a.has_hist) {
-          unpack_rays(pr, r[0], r[N - 1]);
+          if (inner) {
+            RayT<D2> lab;
+            frame_to_lab(sE[k + 1], pr, lab);
+            unpack_rays(lab, r[0], r[N - 1]);
+          } else {
+            unpack_rays(pr, r[0], r[N - 1]);
+          }
           store_bundle<N>(a.hist[k], row + i, out_vec, two, r, WANT_INC);
         }
       }
@@ -493,13 +564,37 @@ __global__ void __launch_bounds__(TPB, HAS_DEF ? ART_MINB_DEF : ART_MINB) trace_
     } else {
       for (int k = 0; k < a.n_elements; ++k) {
         const bool inc_here = WANT_INC && (k == last || a.has_hist);
+        const bool inner = k != last;
 #pragma unroll
         for (int q = 0; q < N; ++q)
           if (r[q].alive)
             apply_element<WANT_INC, HAS_DEF, SURFS, double>(sE[k], r[q], sZ, sZoff, ignore_defects, inc_here, a.maps,
-                                                            k == 0 ? eorg0 : nullptr);
-        if (a.has_hist) store_bundle<N>(a.hist[k], row + i, out_vec, two, r, WANT_INC);
+                                                            k == 0 ? eorg0 : nullptr, k != 0, inner);
+        if (a.has_hist) {
+          if (inner) {
+            Ray lab[N];
+#pragma unroll
+            for (int q = 0; q < N; ++q) frame_to_lab(sE[k + 1], r[q], lab[q]);
+            store_bundle<N>(a.hist[k], row + i, out_vec, two, lab, WANT_INC);
+          } else {
+            store_bundle<N>(a.hist[k], row + i, out_vec, two, r, WANT_INC);
+          }
+        }
       }
+    }
+    // both rays of the pair lost on the way (a mask blocks a whole range of spiral indices): nothing to store
+    // but the flags, nothing to add to the central sums
+    if (!r[0].alive && !r[N - 1].alive) {
+      if (a.has_out && a.out.alive) {
+        if (N == 2 && two && out_vec) {
+          *reinterpret_cast<uchar2*>(a.out.alive + row + i) = make_uchar2(0, 0);
+        } else {
+          a.out.alive[row + i] = 0;
+          if (N == 2 && two) a.out.alive[row + i + 1] = 0;
+        }
+      }
+      staged = staged_next;
+      continue;
     }
     if (a.has_out) store_bundle<N>(a.out, row + i, out_vec, two, r, WANT_INC, a.keep_l2 != 0);
 
@@ -538,12 +633,12 @@ __global__ void __launch_bounds__(TPB, HAS_DEF ? ART_MINB_DEF : ART_MINB) trace_
     double all[PLEN_TRACE];
 #pragma unroll
     for (int j = 0; j < ART_CENTRAL_LEN; ++j) all[j] = ART_ACC(j);
-    block_reduce_row<PLEN_TRACE>(all, [](int) { return 0; }, sRed, prow);
+    block_reduce_row<PLEN_TRACE, BT>(all, [](int) { return 0; }, sRed, prow);
   }
   if constexpr (WITH_DET) {
     __syncthreads();  // sRed is reused
     moments_finish(m);
-    block_reduce_row<ART_MOMENTS_LEN>(m, [](int j) { return moment_op(j); }, sRed, prow + ART_CENTRAL_LEN);
+    block_reduce_row<ART_MOMENTS_LEN, BT>(m, [](int j) { return moment_op(j); }, sRed, prow + ART_CENTRAL_LEN);
   }
 #undef ART_ACC
 }
@@ -706,6 +801,239 @@ __global__ void __launch_bounds__(TPB, ART_DET_MINB) detector_kernel(const DetAr
   moments_finish(m);
   block_reduce_row<PLEN_DET>(m, [](int j) { return moment_op(j); }, sRed,
                              a.partials + ((size_t)v * gridDim.x + blockIdx.x) * PLEN_DET);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 on bulk asynchronous copies (sm_90+ TMA engine, 1-D form: cp.async.bulk + mbarrier transaction counts).
+//
+// The stored bundle is a set of dense FP64 columns, so a block does not need 256 threads each issuing eight
+// 16-byte LDGSTS per ray pair: ONE lane of a producer warp asks the copy engine for the next tile of every
+// column (DB_TILE rays = 4 KB per column, eight columns) and the bytes land in a shared-memory stage whose
+// mbarrier counts them in.  DB_STAGES stages form a ring: `full[s]` (the tile has landed) is waited on by the
+// eight consumer warps, `empty[s]` (all consumer warps are done with the stage) by the producer.
+// The alive flags (1 B / ray) are read by the producer warp itself, a group of tiles ahead; a tile without
+// survivors (a mask blocks a contiguous range of spiral indices) is stepped over without touching a barrier or
+// the copy engine, so dead rays cost 1 B each, as in the LDGSTS kernel; the flags of a live tile are put into
+// its stage for the consumers.
+// Each stage carries the index of the tile it holds; a stage with tile -1 ends the consumers' loop.
+// The ragged tail (n mod DB_TILE rays) is evaluated with plain loads by the last block.
+// ---------------------------------------------------------------------------------------------
+#ifndef ART_DB_WARPS
+#define ART_DB_WARPS 8      // consumer warps per block (one block per SM: the 24 moment accumulators stay in registers)
+#endif
+#ifndef ART_DB_STAGES
+#define ART_DB_STAGES 6     // 6 x 32.5 KB stages in flight per SM
+#endif
+#ifndef ART_DB_MINB
+#define ART_DB_MINB 1
+#endif
+constexpr int DB_STAGES = ART_DB_STAGES;
+constexpr int DB_CONSUMER_WARPS = ART_DB_WARPS;
+#ifndef ART_DB_PAIRS
+#define ART_DB_PAIRS 1      // ray pairs per consumer thread and tile (instruction-level parallelism of the FP64 chains)
+#endif
+constexpr int DB_PAIRS = ART_DB_PAIRS;
+constexpr int DB_TILE = 64 * DB_CONSUMER_WARPS * DB_PAIRS;   // rays per tile
+constexpr int DB_THREADS = 32 * (DB_CONSUMER_WARPS + 1);
+constexpr int DB_COL_BYTES = DB_TILE * 8;
+constexpr int DB_STAGE_BYTES = STAGE_COLS * DB_COL_BYTES + DB_TILE;   // 8 columns + flags
+constexpr int DB_SMEM_BYTES = DB_STAGES * DB_STAGE_BYTES;
+#ifndef ART_DB_GROUP
+#define ART_DB_GROUP 4      // tiles whose alive flags the producer warp reads ahead in one go
+#endif
+constexpr int DB_GROUP = ART_DB_GROUP;
+static_assert(DB_STAGE_BYTES % 16 == 0 && DB_TILE % 16 == 0, "stages and flag rows stay 16-byte aligned");
+static_assert(DB_SMEM_BYTES <= 220 * 1024, "stage ring exceeds the shared memory of an SM");
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait (a lost arrival must not hang the device): false after ~2^22 probes.
+__device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity) {
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    unsigned ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(DB_THREADS, ART_DB_MINB) detector_bulk_kernel(const DetArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double sRed[(DB_THREADS / 32) * PLEN_DET];
+  __shared__ ArtDetector sDet;
+  __shared__ __align__(8) unsigned long long sFull[DB_STAGES], sEmpty[DB_STAGES];
+  __shared__ long long sTile[DB_STAGES];        // which tile a stage holds; -1 = no more tiles
+  const int v = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n = a.n, row = (long long)v * n;   // row is a multiple of 16 (checked by the host)
+  const long long ntiles = n / DB_TILE;
+  // tiles of this block: blockIdx.x, blockIdx.x + gridDim.x, ...  (K of them)
+  const long long K = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  {
+    const double* ds = reinterpret_cast<const double*>(a.det + v);
+    double* dd = reinterpret_cast<double*>(&sDet);
+    for (int i = threadIdx.x; i < (int)(sizeof(ArtDetector) / sizeof(double)); i += DB_THREADS) dd[i] = ds[i];
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < DB_STAGES; ++s) {
+        mbar_init(smem_addr(&sFull[s]), 1);                     // the producer's (expect_tx) arrival
+        mbar_init(smem_addr(&sEmpty[s]), DB_CONSUMER_WARPS);    // one arrival per consumer warp
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  double m[ART_MOMENTS_LEN];
+  moments_init(m);
+
+  if (warp == 0) {
+    // ---- producer warp ------------------------------------------------------------------------------
+    // The warp reads the alive flags of its tiles itself (DB_TILE bytes per tile, FV 16-byte vectors per lane),
+    // DB_GROUP tiles at a time and one group AHEAD of the group it is handing to the copy engine, so the flag
+    // loads of a long run of dead tiles overlap instead of costing one DRAM latency each.
+    constexpr int FV = (DB_TILE / 16 + 31) / 32;   // 16-byte flag vectors per lane and tile
+    constexpr int G = DB_GROUP;
+    struct Flags { uint4 v[FV]; };
+    auto load_flags = [&](long long k) -> Flags {
+      Flags f;
+#pragma unroll
+      for (int q = 0; q < FV; ++q) {
+        f.v[q] = make_uint4(0u, 0u, 0u, 0u);
+        const int chunk = q * 32 + lane;
+        if (k < K && chunk < DB_TILE / 16) {
+          const long long tile = blockIdx.x + k * gridDim.x;
+          f.v[q] = a.b.alive ? *reinterpret_cast<const uint4*>(a.b.alive + row + tile * DB_TILE + chunk * 16)
+                             : make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+        }
+      }
+      return f;
+    };
+    const unsigned tx = (unsigned)DB_COL_BYTES * (6u + (a.b.path ? 1u : 0u) + (a.b.inten ? 1u : 0u));
+    Flags cur[G], nxt[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) nxt[g] = load_flags(g);
+    int stage = 0;
+    unsigned phase = 0;
+    bool ok = true;
+    for (long long k0 = 0; k0 < K && ok; k0 += G) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) cur[g] = nxt[g];
+#pragma unroll
+      for (int g = 0; g < G; ++g) nxt[g] = load_flags(k0 + G + g);   // in flight while this group is issued
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const long long k = k0 + g;
+        unsigned live = 0u;
+#pragma unroll
+        for (int q = 0; q < FV; ++q) live |= cur[g].v[q].x | cur[g].v[q].y | cur[g].v[q].z | cur[g].v[q].w;
+        const bool any_alive = __any_sync(0xffffffffu, live != 0u);   // (k >= K: no flags were loaded)
+        if (!any_alive || !ok) continue;                              // a dead tile costs nothing further
+        ok = mbar_wait(smem_addr(&sEmpty[stage]), phase ^ 1u);
+        if (!ok) continue;
+        const long long tile = blockIdx.x + k * gridDim.x;
+        unsigned char* st = smem_raw + (size_t)stage * DB_STAGE_BYTES;
+#pragma unroll
+        for (int q = 0; q < FV; ++q) {
+          const int chunk = q * 32 + lane;
+          if (chunk < DB_TILE / 16) *reinterpret_cast<uint4*>(st + STAGE_COLS * DB_COL_BYTES + chunk * 16) = cur[g].v[q];
+        }
+        __syncwarp();
+        if (lane == 0) {
+          sTile[stage] = tile;
+          const unsigned bar = smem_addr(&sFull[stage]);
+          mbar_arrive_expect_tx(bar, tx);
+          const long long at = row + tile * DB_TILE;
+          const unsigned dst = smem_addr(st);
+          bulk_copy_g2s(dst + 0 * DB_COL_BYTES, a.b.px + at, DB_COL_BYTES, bar);
+          bulk_copy_g2s(dst + 1 * DB_COL_BYTES, a.b.py + at, DB_COL_BYTES, bar);
+          bulk_copy_g2s(dst + 2 * DB_COL_BYTES, a.b.pz + at, DB_COL_BYTES, bar);
+          bulk_copy_g2s(dst + 3 * DB_COL_BYTES, a.b.ux + at, DB_COL_BYTES, bar);
+          bulk_copy_g2s(dst + 4 * DB_COL_BYTES, a.b.uy + at, DB_COL_BYTES, bar);
+          bulk_copy_g2s(dst + 5 * DB_COL_BYTES, a.b.uz + at, DB_COL_BYTES, bar);
+          if (a.b.path) bulk_copy_g2s(dst + 6 * DB_COL_BYTES, a.b.path + at, DB_COL_BYTES, bar);
+          if (a.b.inten) bulk_copy_g2s(dst + 7 * DB_COL_BYTES, a.b.inten + tile * DB_TILE, DB_COL_BYTES, bar);
+        }
+        if (++stage == DB_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    // end marker: the consumers leave their loop on a stage whose tile is -1
+    if (ok && mbar_wait(smem_addr(&sEmpty[stage]), phase ^ 1u) && lane == 0) {
+      sTile[stage] = -1;
+      mbar_arrive(smem_addr(&sFull[stage]));
+    }
+  } else {
+    // ---- consumer warps: thread c owns DB_PAIRS pairs of adjacent rays of every tile ---------------------
+    const int c = threadIdx.x - 32;
+    int stage = 0;
+    unsigned phase = 0;
+    for (;;) {
+      if (!mbar_wait(smem_addr(&sFull[stage]), phase)) break;
+      const long long tile = sTile[stage];
+      if (tile < 0) break;
+      const unsigned char* st = smem_raw + (size_t)stage * DB_STAGE_BYTES;
+      // pair p of this thread: rays 2 (c + p NT), 2 (c + p NT) + 1 of the tile (conflict-free 16-byte reads)
+      constexpr int NT = 32 * DB_CONSUMER_WARPS;
+#pragma unroll
+      for (int p = 0; p < DB_PAIRS; ++p) {
+        const int pi = c + p * NT;   // pair index within the tile
+        const uchar2 fl = *reinterpret_cast<const uchar2*>(st + STAGE_COLS * DB_COL_BYTES + 2 * pi);
+        if (fl.x | fl.y) {
+          const double2* cols = reinterpret_cast<const double2*>(st) + pi;   // column j at cols[j * DB_TILE / 2]
+          Ray r[RPT];
+          double w[RPT];
+          const bool al[RPT] = {fl.x != 0, fl.y != 0};
+          double2 t;
+          t = cols[0 * (DB_TILE / 2)]; r[0].px = t.x; r[1].px = t.y;
+          t = cols[1 * (DB_TILE / 2)]; r[0].py = t.x; r[1].py = t.y;
+          t = cols[2 * (DB_TILE / 2)]; r[0].pz = t.x; r[1].pz = t.y;
+          t = cols[3 * (DB_TILE / 2)]; r[0].ux = t.x; r[1].ux = t.y;
+          t = cols[4 * (DB_TILE / 2)]; r[0].uy = t.x; r[1].uy = t.y;
+          t = cols[5 * (DB_TILE / 2)]; r[0].uz = t.x; r[1].uz = t.y;
+          if (a.b.path) { t = cols[6 * (DB_TILE / 2)]; r[0].path = t.x; r[1].path = t.y; } else { r[0].path = r[1].path = 0.0; }
+          if (a.b.inten) { t = cols[7 * (DB_TILE / 2)]; w[0] = t.x; w[1] = t.y; } else { w[0] = w[1] = 1.0; }
+          detector_pair(a, sDet, row + tile * DB_TILE + 2 * pi, r, w, al, m);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_addr(&sEmpty[stage]));
+      if (++stage == DB_STAGES) { stage = 0; phase ^= 1u; }
+    }
+    // ragged tail: plain loads, last block of the variant
+    if (blockIdx.x == gridDim.x - 1) {
+      for (long long i = ntiles * DB_TILE + c; i < n; i += 32 * DB_CONSUMER_WARPS) {
+        const long long at = row + i;
+        if (a.b.alive && !a.b.alive[at]) continue;
+        Ray r[RPT];
+        double w[RPT] = {a.b.inten ? a.b.inten[i] : 1.0, 0.0};
+        r[0].px = a.b.px[at]; r[0].py = a.b.py[at]; r[0].pz = a.b.pz[at];
+        r[0].ux = a.b.ux[at]; r[0].uy = a.b.uy[at]; r[0].uz = a.b.uz[at];
+        r[0].path = a.b.path ? a.b.path[at] : 0.0;
+        r[1] = r[0];
+        const bool al[RPT] = {true, false};
+        detector_pair(a, sDet, at, r, w, al, m);
+      }
+    }
+  }
+  moments_finish(m);
+  block_reduce_row<PLEN_DET, DB_THREADS>(m, [](int j) { return moment_op(j); }, sRed,
+                                         a.partials + ((size_t)v * gridDim.x + blockIdx.x) * PLEN_DET);
 }
 
 // Scan sums for FindOptimalDistance (ART/ModuleProcessing.py:317-460), layout ART_S_* of the header.
@@ -1216,27 +1544,55 @@ struct SourceArgs {
                      // (ART_C_SUX..SUZ) and the ray count (ART_C_N) -- what FindCentralRay needs for the axis
                      // of ApplyGaussianIntensityToRayList (ART/ModuleSource.py:244)
 };
+// sin and cos of a Vogel angle x = golden * k (0 <= x < 2^28 pi/2, i.e. k < 1.7e8) without the slow path
+// the library takes above 1e5 (Payne-Hanek, local memory): three-constant Cody-Waite reduction
+// pi/2 = C1 + C2 + C3 with 25-bit C1, C2 (n C1 and n C2 are exact for the quadrant count n < 2^28) followed by the
+// fdlibm kernel polynomials on [-pi/4, pi/4].  Largest deviation from libm over k < 4e8: 2.2e-16 (1 ulp of 1),
+// checked on the host with the same arithmetic.
+__device__ __forceinline__ void vogel_sincos(double x, double& sn, double& cs) {
+  const double n = rint(x * 0.63661977236758138);
+  double r = fma(-n, 0x1.921fb50000000p+0, x);
+  r = fma(-n, 0x1.110b460000000p-26, r);
+  r = fma(-n, 0x1.1a62633145c07p-54, r);
+  const double z = r * r;
+  const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08),
+                                             2.75573137070700676789e-06), -1.98412698298579493134e-04),
+                               8.33333333332248946124e-03), -1.66666666666666324348e-01);
+  const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09),
+                                             -2.75573143513906633035e-07), 2.48015872894767294178e-05),
+                               -1.38888888888741095749e-03), 4.16666666666666019037e-02);
+  const double s0 = fma(r * z, ps, r);
+  const double c0 = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const long long q = (long long)n;
+  const double a = (q & 1) ? c0 : s0, b = (q & 1) ? s0 : c0;
+  sn = (q & 2) ? -a : a;
+  cs = ((q + 1) & 2) ? -b : b;
+}
+
 __global__ void __launch_bounds__(TPB) source_kernel(const SourceArgs a) {
   const double golden = 3.141592653589793 * (3.0 - sqrt(5.0));
   double su[3] = {0.0, 0.0, 0.0}, cnt = 0.0;
+  const bool fast = a.n_total < (1LL << 27);  // beyond that the reduction above is not exact: library sincos
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.count;
        j += (long long)gridDim.x * blockDim.x) {
     const long long idx = a.first + j * a.stride;
     // the Vogel point that shapes the direction (kinds 0, 2) or the position (kind 1)
     const double k = (double)(a.kind == 2 ? idx % a.per : idx);
     const double kn = (double)(a.kind == 2 ? a.per : a.n_total);
-    const double rad = sqrt(k / kn) * a.rho;
+    const double rad = fsqrt(fdiv(k, kn)) * a.rho;
     double s, c;
-    sincos(golden * k, &s, &c);
+    if (fast) vogel_sincos(golden * k, s, c);
+    else sincos(golden * k, &s, &c);
     const double x = c * rad, y = s * rad;
     double px, py, pz, ux, uy, uz;
     if (a.kind == 2) {
       const double ks = (double)(idx / a.per);
-      const double rs = sqrt(ks / (double)a.n_ps) * a.ps_radius;
+      const double rs = fsqrt(fdiv(ks, (double)a.n_ps)) * a.ps_radius;
       double ss, cs;
-      sincos(golden * ks, &ss, &cs);
+      if (fast) vogel_sincos(golden * ks, ss, cs);
+      else sincos(golden * ks, &ss, &cs);
       const double xs = cs * rs, ys = ss * rs;
-      const double inv = 1.0 / sqrt(fma(x, x, fma(y, y, 1.0)));
+      const double inv = frsqrt(fma(x, x, fma(y, y, 1.0)));
       const double vx = x * inv, vy = y * inv, vz = inv;
       ux = a.rot[0] * vx + a.rot[1] * vy + a.rot[2] * vz;
       uy = a.rot[3] * vx + a.rot[4] * vy + a.rot[5] * vz;
@@ -1245,7 +1601,7 @@ __global__ void __launch_bounds__(TPB) source_kernel(const SourceArgs a) {
       py = a.rot[3] * xs + a.rot[4] * ys + a.origin[1];
       pz = a.rot[6] * xs + a.rot[7] * ys + a.origin[2];
     } else if (a.kind == 0) {
-      const double inv = 1.0 / sqrt(fma(x, x, fma(y, y, 1.0)));
+      const double inv = frsqrt(fma(x, x, fma(y, y, 1.0)));
       const double vx = x * inv, vy = y * inv, vz = inv;
       ux = a.rot[0] * vx + a.rot[1] * vy + a.rot[2] * vz;
       uy = a.rot[3] * vx + a.rot[4] * vy + a.rot[5] * vz;
@@ -1257,10 +1613,11 @@ __global__ void __launch_bounds__(TPB) source_kernel(const SourceArgs a) {
       pz = a.rot[6] * x + a.rot[7] * y + a.origin[2];
       ux = a.rot[2]; uy = a.rot[5]; uz = a.rot[8];
     }
-    const double un = 1.0 / sqrt(fma(ux, ux, fma(uy, uy, uz * uz)));
+    const double un = frsqrt(fma(ux, ux, fma(uy, uy, uz * uz)));
+    ux *= un; uy *= un; uz *= un;
     if (a.b.px) { a.b.px[j] = px; a.b.py[j] = py; a.b.pz[j] = pz; }
-    a.b.ux[j] = ux * un; a.b.uy[j] = uy * un; a.b.uz[j] = uz * un;
-    su[0] += ux * un; su[1] += uy * un; su[2] += uz * un;
+    a.b.ux[j] = ux; a.b.uy[j] = uy; a.b.uz[j] = uz;
+    su[0] += ux; su[1] += uy; su[2] += uz;
     cnt += 1.0;
     if (a.b.path) a.b.path[j] = 0.0;
     if (a.b.alive) a.b.alive[j] = 1;
@@ -1285,6 +1642,73 @@ __global__ void source_axis_kernel(const double* __restrict__ central_row, doubl
   double m[3] = {central_row[ART_C_SUX] / N, central_row[ART_C_SUY] / N, central_row[ART_C_SUZ] / N};
   const double nn = sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
   for (int i = 0; i < 3; ++i) state[i] = m[i] / nn;  // Ray.vector setter normalises, ART/ModuleOpticalRay.py:85-90
+}
+
+// Extent of a generated bundle for ApplyGaussianIntensityToRayList (ART/ModuleSource.py:244-258): the largest
+// angle between the axis and a ray, the largest |P|.  Both grow monotonically along a Vogel spiral, so only the
+// OUTER RING can hold the maximum: with d = angle(axis, cone axis) (the mean direction is tilted by ~rho/N
+// against the exact axis), ray k can be the widest only if theta_k >= theta_(N-1) - 2 d; the kernel derives the
+// first such k from the device state itself (a tilted axis simply widens the ring) and scans from there --
+// a few thousand rays instead of the whole bundle.  Kinds whose extremes are not at the end of the index
+// range (extended source, plane wave about a shifted origin) scan everything.
+// Partials: [block][2] = {max |u - axis|^2, max |P|^2}; source_extents_fold turns them into angle / distance.
+struct ExtentArgs {
+  SourceArgs src;        // the generator's arguments (index range, kind, rot)
+  const double* state;   // [0..2] axis
+  double* partials;
+};
+__global__ void __launch_bounds__(TPB) source_extents_kernel(const ExtentArgs a) {
+  __shared__ double sRed[NWARP * 2];
+  const SourceArgs& g = a.src;
+  const double ax = a.state[0], ay = a.state[1], az = a.state[2];
+  long long j0 = 0;
+  const bool origin0 = g.origin[0] == 0.0 && g.origin[1] == 0.0 && g.origin[2] == 0.0;
+  if (g.kind == 0 || (g.kind == 1 && origin0)) {
+    double kmin;
+    if (g.kind == 0) {
+      const double cone[3] = {g.rot[2], g.rot[5], g.rot[8]};
+      const double axis[3] = {ax, ay, az};
+      const double d = kahan_angle(axis, cone);
+      const double nn = (double)g.n_total;
+      const double th = atan(g.rho * sqrt((nn - 1.0) / nn)) - 2.0 * d - 1e-9;
+      const double q = th > 0.0 ? tan(th) / g.rho : 0.0;
+      kmin = nn * q * q - 4.0;
+    } else {
+      kmin = (double)g.n_total - 4096.0;  // |P_k| = radius sqrt(k / N): the last rays
+    }
+    if (!(kmin > 0.0)) kmin = 0.0;       // also catches NaN (a degenerate axis): scan everything
+    const long long k0 = (long long)kmin;
+    j0 = k0 <= g.first ? 0 : (k0 - g.first) / g.stride;
+  }
+  double mx[2] = {0.0, 0.0};
+  for (long long j = j0 + (long long)blockIdx.x * TPB + threadIdx.x; j < g.count; j += (long long)gridDim.x * TPB) {
+    const double dx = g.b.ux[j] - ax, dy = g.b.uy[j] - ay, dz = g.b.uz[j] - az;
+    const double m = fma(dx, dx, fma(dy, dy, dz * dz));
+    mx[0] = m > mx[0] ? m : mx[0];
+    if (g.b.px) {
+      const double px = g.b.px[j], py = g.b.py[j], pz = g.b.pz[j];
+      const double p2 = fma(px, px, fma(py, py, pz * pz));
+      mx[1] = p2 > mx[1] ? p2 : mx[1];
+    }
+  }
+  block_reduce_row<2>(mx, [](int) { return 2; }, sRed, a.partials + (size_t)blockIdx.x * 2);
+}
+// state[3] = largest Kahan angle 2 atan2(|u - a|, |u + a|) with |u + a|^2 = 4 - |u - a|^2 (unit vectors),
+// state[4] = largest |P|
+__global__ void source_extents_fold(const double* __restrict__ partials, int nblocks, double* __restrict__ state) {
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 32) {
+    a = fmax(a, partials[2 * i]);
+    b = fmax(b, partials[2 * i + 1]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+    b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+  }
+  if (threadIdx.x == 0) {
+    state[3] = 2.0 * atan2(sqrt(a), sqrt(4.0 - a));
+    state[4] = sqrt(b);
+  }
 }
 
 // ApplyGaussianIntensityToRayList, ART/ModuleSource.py:219-261.

@@ -110,6 +110,29 @@ inline std::string lower_element(const ArtElementDesc& d, ElemDev& e) {
   return std::string();
 }
 
+// Hand-over map between consecutive elements: a point h / direction o in element `e`'s frame arrive in
+// `next`'s frame as  M h + b  /  M o  with  M = R_next R^T,  b = R_next (pos - pos_next - R^T ctr) + ctr_next
+// -- the composition of ART/ModuleProcessing.py:306-309 (element -> lab) and :289-295 of the next loop trip
+// (lab -> next element), evaluated once per element pair in extended precision.
+inline void link_elements(ElemDev& e, const ElemDev& next) {
+  long double t[3];
+  for (int i = 0; i < 3; ++i) {
+    long double rc = 0;  // (R^T ctr)[i]
+    for (int j = 0; j < 3; ++j) rc += (long double)e.rot[3 * j + i] * e.ctr[j];
+    t[i] = (long double)e.pos[i] - next.pos[i] - rc;
+  }
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      long double m = 0;
+      for (int q = 0; q < 3; ++q) m += (long double)next.rot[3 * i + q] * e.rot[3 * j + q];
+      e.nrot[3 * i + j] = (double)m;
+    }
+    long double b = next.ctr[i];
+    for (int q = 0; q < 3; ++q) b += (long double)next.rot[3 * i + q] * t[q];
+    e.noff[i] = (double)b;
+  }
+}
+
 inline std::string lower_gridmap(const ArtGridMapDesc& g, MapDev& m) {
   if (g.nx < 2 || g.ny < 2) return "a grid map needs at least 2 x 2 points";
   if (!(g.x1 > g.x0) || !(g.y1 > g.y0)) return "grid extents must be increasing";

@@ -168,12 +168,25 @@ def measured_map(nx, ny, amplitude):
 
 SCENES.update({
     # gridded defects: ModuleDefects.Fourrier (+ a Zernike term) on the cfg4 geometry.
-    # (ModuleDefects.MeasuredMap cannot be run: its np.gradient call raises TypeError under numpy >= 2.)
     "par_fourier": {
         "source": {"Divergence": 0, "SourceSize": 100, "Wavelength": 800e-6, "NumberRays": 800},
         "optics": [{"kind": "parabolic", "feff": 25.4, "offaxisangle_deg": 0, "support": ["rect", 40, 40],
                     "defects": [{"kind": "fourier", "rms": 1e-4, "slope": -2, "smallest": 1.0, "seed": 3},
                                 {"kind": "zernike", "coefficients": [[2, 1, 5e-5], [3, 0, -4e-5]]}]}],
+        "distances": [15], "incidences": [0], "plane_angles": [0], "post": [], "detector_distance": 25.4,
+    },
+})
+
+
+SCENES.update({
+    # ModuleDefects.MeasuredMap on the same geometry: a deterministic synthetic height map.  The stock reference
+    # cannot construct it under numpy >= 2; pinned through the documented compatibility patch (oracle/make_ref.py,
+    # oracle/gen_golden_gridmap.py).  Square: the reference hands (X[nx], Y[ny]) grids but TRANSPOSED (ny, nx) value
+    # arrays to its interpolators (ART/ModuleDefects.py:45-47), which only fits for nx == ny
+    "par_measured": {
+        "source": {"Divergence": 0, "SourceSize": 100, "Wavelength": 800e-6, "NumberRays": 800},
+        "optics": [{"kind": "parabolic", "feff": 25.4, "offaxisangle_deg": 0, "support": ["rect", 40, 40],
+                    "defects": [{"kind": "measuredmap", "nx": 53, "ny": 53, "amplitude": 2e-4}]}],
         "distances": [15], "incidences": [0], "plane_angles": [0], "post": [], "detector_distance": 25.4,
     },
 })

@@ -133,6 +133,9 @@ def build_optic(spec, fixture=None, derived=None):
                                           dd["x0"], dd["x1"], dd["y0"], dd["y1"]))
             elif d["kind"] == "fourier":
                 dl.append(mdef.Fourrier(sup, d["rms"], slope=d["slope"], smallest=d["smallest"], seed=d["seed"]))
+            elif d["kind"] == "measuredmap":
+                import scenes as sc
+                dl.append(mdef.MeasuredMap(sup, sc.measured_map(d["nx"], d["ny"], d["amplitude"])))
             else:
                 raise ValueError(d["kind"])
         m = mmirror.DeformedMirror(m, dl)

@@ -28,6 +28,7 @@ extern "C" int hc_trace(const ArtElementDesc* els, int n_el, const ArtZernikeDes
       return -1;
     }
   }
+  for (int k = 0; k + 1 < n_el; ++k) link_elements(E[k], E[k + 1]);
   std::vector<double> ztab;
   std::vector<int> zoff;
   for (int i = 0; i < n_def; ++i) {
@@ -56,13 +57,20 @@ extern "C" int hc_trace(const ArtElementDesc* els, int n_el, const ArtZernikeDes
     r.path = 0.0;
     r.inc = ART_NAN;
     r.alive = true;
+    // the trace kernel's element loop: inner elements hand the ray over in the next element's frame and
+    // the lab-frame bundle of the history is recovered with frame_to_lab
     for (int k = 0; k < n_el; ++k) {
-      if (r.alive) apply_element<true, true, SURFS_ANY, double>(E[k], r, ztab.data(), zoff.data(), ign, true, maps.data());
+      const bool inner = k + 1 < n_el;
+      if (r.alive)
+        apply_element<true, true, SURFS_ANY, double>(E[k], r, ztab.data(), zoff.data(), ign, true, maps.data(), nullptr,
+                                                     k != 0, inner);
+      Ray w = r;
+      if (inner) frame_to_lab(E[k + 1], r, w);
       const long long o = (long long)k * n + i;
-      oalive[o] = r.alive;
-      opx[o] = r.px; opy[o] = r.py; opz[o] = r.pz;
-      oux[o] = r.ux; ouy[o] = r.uy; ouz[o] = r.uz;
-      opath[o] = r.path; oinc[o] = r.inc;
+      oalive[o] = w.alive;
+      opx[o] = w.px; opy[o] = w.py; opz[o] = w.pz;
+      oux[o] = w.ux; ouy[o] = w.uy; ouz[o] = w.uz;
+      opath[o] = w.path; oinc[o] = w.inc;
     }
   }
   return 0;

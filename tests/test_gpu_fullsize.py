@@ -1,7 +1,7 @@
 """Full-size checks on the GPU (BASELINE.json sizes): the rows of the full 10^6..10^8-ray bundles at
 the seeded subset indices against what the reference produced for exactly those rays
 (tests/golden/*_sub*.npz), plus size-independent properties of the path: permutation and sharding
-invariance, chaining two partial chains == one chain, merged shard moments == full moments, and
+invariance, chaining two partial chains == one chain (to rounding), merged shard moments == full moments, and
 the known answers of the geometry (parabola focus, ellipsoid focus-to-focus path 2a, plane mirror)."""
 import numpy as np
 import pytest
@@ -147,9 +147,13 @@ def test_permutation_sharding_and_chaining_invariance_10M():
     o2, c2 = rest.trace(o1[0], history=False)
     assert torch.equal(o2[0].alive, full.alive)
     lv = full.alive.bool()
+    # one call hands the rays from element to element through ONE composed affine map (apply_element), the split
+    # chain goes through the lab frame in between: equal to rounding (1e-13 mm per step, amplified ~100x by two
+    # reflections at 80 degrees grazing incidence), not bit for bit
     for c in cols:
-        assert torch.equal(o2[0].col(c)[lv], full.col(c)[lv]), c
-    assert torch.equal(c2[0, :8], central[0, :8])  # the stored intermediate bundle carries no intensities
+        assert float((o2[0].col(c)[lv] - full.col(c)[lv]).abs().max()) <= 1e-10, c
+    assert float((c2[0, :8] - central[0, :8]).abs().max()) <= 1e-10 * float(central[0, 7])  # sums of N such rows
+    assert c2[0, 7] == central[0, 7]  # the stored intermediate bundle carries no intensities
     for ch in (chain, first_el, rest):
         ch.close()
 

@@ -255,19 +255,35 @@ def test_fourier_defect_generator_reproduces_reference_maps():
         assert np.max(np.abs(f.get_normal(p) - orc.gridmap_normal(od, p[None, :])[0])) <= 1e-14
 
 
-def test_measured_map_slopes():
+def test_measured_map_follows_the_reference_conventions():
+    """ModuleDefects.MeasuredMap keeps the reference's layout (ART/ModuleDefects.py:34-61): slopes by np.gradient
+    with one spacing per axis, interpolation grids paired with the TRANSPOSED arrays (square maps only).  The
+    numbers themselves are pinned by tests/golden/par_measured_*.npz (the reference run through the documented
+    numpy-2 compatibility patch)."""
     import attosecondraytracing_b200.ModuleDefects as mdef
     import attosecondraytracing_b200.ModuleSupport as msupp
     sup = msupp.SupportRectangle(40, 20)
     i = np.arange(50)[:, None]
-    j = np.arange(30)[None, :]
-    Map = 1e-4 * (0.02 * i + 0.05 * j)  # a tilted plane: constant slopes
+    j = np.arange(50)[None, :]
+    Map = 1e-4 * (0.02 * i + 0.05 * j)  # a tilted plane: constant slopes along both array axes
     m = mdef.MeasuredMap(sup, Map)
-    assert np.allclose(m.DerivX, 1e-4 * 0.02 / (40 / 50)) and np.allclose(m.DerivY, 1e-4 * 0.05 / (20 / 30))
-    assert m._extent == (-40.0, 40.0, -20.0, 20.0) and m._h.shape == (50, 30)
-    p = np.array([1.0, 2.0, 0.0])
-    n = m.get_normal(p)
+    assert np.allclose(m.DerivX, 1e-4 * 0.02 / (40 / 50)) and np.allclose(m.DerivY, 1e-4 * 0.05 / (20 / 50))
+    assert m._extent == (-40.0, 40.0, -20.0, 20.0) and m._h.shape == (50, 50)
+    assert np.array_equal(m._h, Map.T)           # value at (X[a], Y[b]) is Map[b, a]
+    n = m.get_normal(np.array([1.0, 2.0, 0.0]))
     assert abs(n[0] / n[2] - 1e-4 * 0.02 / (40 / 50)) < 1e-15
+    with pytest.raises(ValueError, match="square"):
+        mdef.MeasuredMap(sup, np.zeros((50, 30)))
+    # the fixture's arrays are what this class builds from the same map
+    import scenes as sc
+    g = Golden("par_measured_def")
+    d = g.spec["optics"][0]["defects"][0]
+    mm = mdef.MeasuredMap(msupp.SupportRectangle(40, 40), sc.measured_map(d["nx"], d["ny"], d["amplitude"]))
+    dd = g.spec["derived_optics"][0]["defects"][0]
+    assert np.array_equal(mm._h, g[dd["arrays"] + "_h"])
+    assert np.max(np.abs(mm._dx - g[dd["arrays"] + "_dx"])) <= 1e-18
+    assert np.max(np.abs(mm._dy - g[dd["arrays"] + "_dy"])) <= 1e-18
+    assert mm._extent == (dd["x0"], dd["x1"], dd["y0"], dd["y1"])
 
 
 def test_save_and_load_compressed_round_trip(tmp_path, capsys):

@@ -54,20 +54,61 @@ def worker():
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         res[f"{wl}_det_ms"] = round(float(np.median(ts)), 4)
+        if wl == "cfg3":  # descriptor-driven end-to-end call (K0 + trace + detector), wall clock
+            import time
+            desc = msrc.source_descriptor(sp)
+            for _ in range(3):
+                chain.run_source(desc, w["scene_spec"]["detector_distance"])
+            t0 = time.perf_counter()
+            for _ in range(10):
+                chain.run_source(desc, w["scene_spec"]["detector_distance"])
+            res["cfg3_run_source_ms"] = round((time.perf_counter() - t0) * 100, 4)
         chain.close()
         del src, outs
         torch.cuda.empty_cache()
+    # cfg5: the batched sweep (64 variants x 10^6 rays), both passes
+    import copy
+    w = bench.load_workload("cfg5")
+    oes = bench.build_chain_elements(w)
+    sw = w["sweep"]
+    variants = []
+    for x in np.linspace(sw["lo"], sw["hi"], 64):
+        v = copy.deepcopy(oes)
+        getattr(v[sw["element"]], "rotate_%s_by" % sw["axis"])(float(x))
+        variants.append(v)
+    src = msrc.synthetic_source(bench.source_properties(w, 1_000_000), device="cuda")
+    chain = engine.DeviceChain(variants)
+    for _ in range(2):
+        chain.sweep(src, w["scene_spec"]["detector_distance"])
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        chain.sweep(src, w["scene_spec"]["detector_distance"])
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    res["cfg5_sweep64_ms"] = round(float(np.median(ts)), 4)
+    chain.close()
     print("RESULT " + json.dumps(res), flush=True)
 
 
 def main():
     libs = sorted(glob.glob(os.path.join(ROOT, "build", "variants", "*.so")))
     libs.append(os.path.join(ROOT, "attosecondraytracing_b200", "libart_b200.so"))
-    for lib in libs:
-        env = dict(os.environ, ART_B200_LIB=lib)
-        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=env, capture_output=True, text=True)
-        line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
-        print(os.path.basename(lib), line[0][7:] if line else "FAILED " + out.stderr[-400:], flush=True)
+    runs = [(lib, {}) for lib in libs]
+    runs.append((libs[-1], {"ART_B200_DET_LEGACY": "1"}))  # A/B: the LDGSTS detector kernel instead of the bulk-copy one
+    for lib, extra in runs:
+        env = dict(os.environ, ART_B200_LIB=lib, **extra)
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=env, capture_output=True,
+                                 text=True, timeout=300)
+            line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
+            msg = line[0][7:] if line else "FAILED " + out.stderr[-400:]
+        except subprocess.TimeoutExpired:
+            msg = "TIMEOUT"
+        print(os.path.basename(lib), " ".join(f"{k}={v}" for k, v in extra.items()), msg, flush=True)
 
 
 if __name__ == "__main__":
