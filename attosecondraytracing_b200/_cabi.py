@@ -103,11 +103,12 @@ HIST_FIXED_ONE = 67108864.0  # ART_HIST_FIXED_ONE
 
 PEER_MAX_RANKS = 16       # ART_PEER_MAX_RANKS
 PEER_MAX_VARIANTS = 64    # ART_PEER_MAX_VARIANTS
+PEER_STATS = 4            # ART_PEER_STATS
 
 
 def peer_buffer_bytes(world):
     """ART_PEER_BUFFER_BYTES of the header."""
-    return 8 * (2 * world * PEER_MAX_VARIANTS * MOMENTS_LEN + world + 2)
+    return 8 * (2 * world * PEER_MAX_VARIANTS * MOMENTS_LEN + world + 2 + PEER_STATS)
 
 
 def hist_len(nx, ny, nt):
@@ -149,6 +150,8 @@ _SIGNATURES = {
     "art_peer_exchange": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_double, C.c_void_p, C.c_void_p]),
     "art_peer_status": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_void_p]),
+    "art_peer_stats": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_int32,
+                                   C.c_void_p]),
     "art_moments_merge": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "art_sweep": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(ArtBundleView), C.c_uint32, C.c_double,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -49,8 +49,13 @@ struct HostWorkspace {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev[8] = {};
-  double* pinned = nullptr;   // results staging: moments | central | detector | peer epoch, status
+  double* pinned = nullptr;   // staging: moments | central | detector | peer epoch, status | caller's detector (in)
   double* src_state = nullptr;  // device source state of art_run_source_host (SRC_STATE_LEN doubles)
+  // art_run_source_host replays its launch sequence as a CUDA graph once the same call has been seen twice
+  cudaGraphExec_t src_graph = nullptr;
+  std::string src_key;        // the arguments the cached graph was captured for
+  std::string src_last_key;   // arguments of the previous call
+  int src_exchanges = 0;      // peer exchanges inside the cached graph
 };
 
 struct ArtChain {
@@ -179,6 +184,7 @@ extern "C" int32_t art_chain_destroy(ArtChain* c) {
   cudaFree(c->ws.cols);
   cudaFree(c->ws.alive);
   cudaFree(c->ws.src_state);
+  if (c->ws.src_graph) cudaGraphExecDestroy(c->ws.src_graph);
   if (c->ws.pinned) cudaFreeHost(c->ws.pinned);
   for (auto& e : c->ws.ev)
     if (e) cudaEventDestroy(e);
@@ -689,6 +695,18 @@ extern "C" int32_t art_peer_status(const uint64_t* peer_bufs, int32_t rank, int3
   return ART_OK;
 }
 
+extern "C" int32_t art_peer_stats(const uint64_t* peer_bufs, int32_t rank, int32_t world, uint64_t* stats_out,
+                                  int32_t reset, void* stream) {
+  if (!peer_bufs || !stats_out || world < 1 || rank < 0 || rank >= world) return fail(ART_E_INVALID, "bad argument");
+  double* base = reinterpret_cast<double*>(peer_bufs[rank]);
+  uint64_t* words = reinterpret_cast<uint64_t*>(base + (size_t)2 * world * PEER_MAX_DOUBLES);
+  cudaStream_t st = (cudaStream_t)stream;
+  ART_CUDA(cudaMemcpyAsync(stats_out, words + world + 2, ART_PEER_STATS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  if (reset) ART_CUDA(cudaMemsetAsync(words + world + 2, 0, ART_PEER_STATS * sizeof(uint64_t), st));
+  ART_CUDA(cudaStreamSynchronize(st));
+  return ART_OK;
+}
+
 // The sweep traces every ray twice (pass 1: central sums, fold + autoplace; pass 2: fused trace +
 // detector) and stores nothing per ray.  The alternative -- trace once, keep each variant's final
 // bundle (57 B/ray) in L2 and run the detector kernel on it -- was built and measured slower on B200
@@ -754,6 +772,8 @@ extern "C" int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t fi
   for (int i = 0; i < 3; ++i) a.origin[i] = origin[i];
   a.b = to_dev(bundle);
   a.partials = nullptr;
+  a.origin_out = nullptr;
+  a.origin_stride = 0;
   long long bx = (count + TPB - 1) / TPB;
   if (bx < 1) bx = 1;
   if (bx > 148 * 16) bx = 148 * 16;
@@ -823,7 +843,7 @@ static int32_t ensure_workspace(ArtChain* c, size_t n) {
     ART_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     ART_CUDA(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
     for (auto& e : w.ev) ART_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    ART_CUDA(cudaMallocHost(&w.pinned, sizeof(double) * (ART_MOMENTS_LEN + ART_CENTRAL_LEN) + sizeof(ArtDetector) +
+    ART_CUDA(cudaMallocHost(&w.pinned, sizeof(double) * (ART_MOMENTS_LEN + ART_CENTRAL_LEN) + 2 * sizeof(ArtDetector) +
                                           2 * sizeof(uint64_t)));
   }
   if (n > w.cap_n || !w.cols) {
@@ -840,13 +860,22 @@ static int32_t ensure_workspace(ArtChain* c, size_t n) {
   return ART_OK;
 }
 
-// The part of a host-level run that follows the trace: all-reduce of the central sums + Detector.autoplace
-// (or the caller's detector), detector moments of the stored final bundle, merge over the ranks, results
-// (and optionally the final bundle) back to the host.  c->d_central holds this rank's folded central sums.
-static int32_t statistics_tail(ArtChain* c, const ArtBundleView* dout_p, size_t n, bool want_inc,
-                               const ArtBundleView* out_final_host, double distance, const ArtDetector* manual_det,
-                               double* moments_host, double* central_host, ArtDetector* det_host,
-                               const uint64_t* peer_bufs, int32_t rank, int32_t world, int exchanges_before = 0) {
+// The part of a host-level run that follows the trace, in two halves so that the first can be captured in a
+// CUDA graph: statistics_enqueue issues the all-reduce of the central sums + Detector.autoplace (or takes the
+// caller's detector from the pinned staging area), the detector moments of the stored final bundle, the merge
+// over the ranks and the copies of the results (and optionally of the final bundle) to the host;
+// statistics_finish waits for the stream, checks the peer exchanges and hands the results out.
+// c->d_central holds this rank's folded central sums on entry.
+static ArtDetector* pinned_det_in(HostWorkspace& w) {
+  double* pc = w.pinned + ART_MOMENTS_LEN;
+  ArtDetector* pd = reinterpret_cast<ArtDetector*>(pc + ART_CENTRAL_LEN);
+  uint64_t* pw = reinterpret_cast<uint64_t*>(pd + 1);
+  return reinterpret_cast<ArtDetector*>(pw + 2);
+}
+
+static int32_t statistics_enqueue(ArtChain* c, const ArtBundleView* dout_p, size_t n, bool want_inc,
+                                  const ArtBundleView* out_final_host, double distance, bool manual_det,
+                                  const uint64_t* peer_bufs, int32_t rank, int32_t world) {
   HostWorkspace& w = c->ws;
   const size_t cap = w.cap_n;
   auto col = [&](int j) { return w.cols + (size_t)j * cap; };
@@ -856,7 +885,7 @@ static int32_t statistics_tail(ArtChain* c, const ArtBundleView* dout_p, size_t 
   // sharded bundle: the central sums of all ranks are added (and the detector placed) inside one kernel over
   // peer memory, likewise the moments rows below
   if (manual_det) {
-    ART_CUDA(cudaMemcpyAsync(c->d_det, manual_det, sizeof(ArtDetector), cudaMemcpyHostToDevice, st));
+    ART_CUDA(cudaMemcpyAsync(c->d_det, pinned_det_in(w), sizeof(ArtDetector), cudaMemcpyHostToDevice, st));
     if (peer_bufs) {
       rc = art_peer_exchange(peer_bufs, rank, world, 0, 1, c->d_central, distance, nullptr, st);
       if (rc) return rc;
@@ -874,16 +903,14 @@ static int32_t statistics_tail(ArtChain* c, const ArtBundleView* dout_p, size_t 
     rc = art_peer_exchange(peer_bufs, rank, world, 1, 1, c->d_moments, 0.0, nullptr, st);
     if (rc) return rc;
   }
-
   double* pm = w.pinned;
   double* pc = pm + ART_MOMENTS_LEN;
   ArtDetector* pd = reinterpret_cast<ArtDetector*>(pc + ART_CENTRAL_LEN);
   ART_CUDA(cudaMemcpyAsync(pm, c->d_moments, sizeof(double) * ART_MOMENTS_LEN, cudaMemcpyDeviceToHost, st));
   ART_CUDA(cudaMemcpyAsync(pc, c->d_central, sizeof(double) * ART_CENTRAL_LEN, cudaMemcpyDeviceToHost, st));
   ART_CUDA(cudaMemcpyAsync(pd, c->d_det, sizeof(ArtDetector), cudaMemcpyDeviceToHost, st));
-  uint64_t* pw = reinterpret_cast<uint64_t*>(pd + 1);  // {epoch, status} of this rank's exchange buffer
-  pw[0] = pw[1] = 0;
   if (peer_bufs) {
+    uint64_t* pw = reinterpret_cast<uint64_t*>(pd + 1);  // {epoch, status} of this rank's exchange buffer
     const double* base = reinterpret_cast<const double*>(peer_bufs[rank]);
     const uint64_t* words = reinterpret_cast<const uint64_t*>(base + (size_t)2 * world * PEER_MAX_DOUBLES);
     ART_CUDA(cudaMemcpyAsync(pw, words + world, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -897,11 +924,21 @@ static int32_t statistics_tail(ArtChain* c, const ArtBundleView* dout_p, size_t 
     if (out_final_host->alive)
       ART_CUDA(cudaMemcpyAsync(out_final_host->alive, w.alive, n, cudaMemcpyDeviceToHost, st));
   }
-  ART_CUDA(cudaStreamSynchronize(st));
+  return ART_OK;
+}
+
+static int32_t statistics_finish(ArtChain* c, double* moments_host, double* central_host, ArtDetector* det_host,
+                                 bool peers, int exchanges_before) {
+  HostWorkspace& w = c->ws;
+  double* pm = w.pinned;
+  double* pc = pm + ART_MOMENTS_LEN;
+  ArtDetector* pd = reinterpret_cast<ArtDetector*>(pc + ART_CENTRAL_LEN);
+  uint64_t* pw = reinterpret_cast<uint64_t*>(pd + 1);
+  ART_CUDA(cudaStreamSynchronize(w.stream));
   // A peer that did not arrive leaves the rows of this rank unreduced (peer_exchange_kernel): the status word
   // then holds the epoch that timed out.  This call used the epochs pw[0] - 1 (central sums) and pw[0] (moments)
   // and `exchanges_before` earlier ones.
-  if (peer_bufs && pw[1] != 0 && pw[1] + 1 + (uint64_t)exchanges_before >= pw[0])
+  if (peers && pw[1] != 0 && pw[1] + 1 + (uint64_t)exchanges_before >= pw[0])
     return fail(ART_E_PEER_TIMEOUT, "peer-memory exchange timed out at epoch " + std::to_string(pw[1]) +
                                         ": a rank did not arrive; the statistics of this call are not reduced");
   if (moments_host)
@@ -910,6 +947,17 @@ static int32_t statistics_tail(ArtChain* c, const ArtBundleView* dout_p, size_t 
     for (int j = 0; j < ART_CENTRAL_LEN; ++j) central_host[j] = pc[j];
   if (det_host) *det_host = *pd;
   return ART_OK;
+}
+
+static int32_t statistics_tail(ArtChain* c, const ArtBundleView* dout_p, size_t n, bool want_inc,
+                               const ArtBundleView* out_final_host, double distance, const ArtDetector* manual_det,
+                               double* moments_host, double* central_host, ArtDetector* det_host,
+                               const uint64_t* peer_bufs, int32_t rank, int32_t world, int exchanges_before = 0) {
+  if (manual_det) *pinned_det_in(c->ws) = *manual_det;
+  int32_t rc = statistics_enqueue(c, dout_p, n, want_inc, out_final_host, distance, manual_det != nullptr, peer_bufs,
+                                  rank, world);
+  if (rc) return rc;
+  return statistics_finish(c, moments_host, central_host, det_host, peer_bufs != nullptr, exchanges_before);
 }
 
 static int32_t run_host_impl(ArtChain* c, const ArtBundleView* in_host, const ArtBundleView* out_final_host,
@@ -1016,29 +1064,17 @@ extern "C" int32_t art_run_host_sharded(ArtChain* c, const ArtBundleView* in_hos
 // descriptor-driven end-to-end entry point: the reference's real host input is SourceProperties
 // (ART/ModuleProcessing.py:58-79), not ray columns
 // -------------------------------------------------------------------------------------------------
-extern "C" int32_t art_run_source_host(ArtChain* c, const ArtSourceDesc* src, uint32_t flags, double distance,
-                                       const ArtDetector* manual_det, double* moments_host, double* central_host,
-                                       ArtDetector* det_host, const uint64_t* peer_bufs, int32_t rank, int32_t world) {
-  if (!c || !src) return fail(ART_E_INVALID, "NULL argument");
-  if (src->kind < 0 || src->kind > 2)
-    return fail(ART_E_INVALID, "kind must be 0 (point source), 1 (plane wave) or 2 (extended source)");
-  if (src->kind == 2 && (src->n_point_sources < 1 || src->rays_per_source < 1 ||
-                         src->n_point_sources * src->rays_per_source != src->n_total))
-    return fail(ART_E_INVALID, "extended source: n_total must equal n_point_sources * rays_per_source");
-  if (src->n_total < 1 || src->first < 0 || src->count < 0 || src->stride < 1 ||
-      (src->count > 0 && src->first + (src->count - 1) * src->stride >= src->n_total))
-    return fail(ART_E_INVALID, "bad index range");
-  if (peer_bufs && (world < 1 || world > ART_PEER_MAX_RANKS || rank < 0 || rank >= world))
-    return fail(ART_E_INVALID, "rank / world out of range");
-  ART_CUDA(cudaSetDevice(c->device));
-  const size_t n = (size_t)src->count;
-  int32_t rc = ensure_workspace(c, n);
-  if (rc) return rc;
+// the launch sequence of art_run_source_host on the workspace stream (no synchronisation, no pageable copies:
+// capturable in a CUDA graph); *exchanges_out = peer exchanges issued before the statistics tail
+static int32_t run_source_enqueue(ArtChain* c, const ArtSourceDesc* src, uint32_t flags, double distance,
+                                  bool manual_det, const uint64_t* peer_bufs, int32_t rank, int32_t world,
+                                  int* exchanges_out) {
   HostWorkspace& w = c->ws;
+  const size_t n = (size_t)src->count;
   const size_t cap = w.cap_n;
   auto col = [&](int j) { return w.cols + (size_t)j * cap; };
   cudaStream_t st = w.stream;
-  if (!w.src_state) ART_CUDA(cudaMalloc(&w.src_state, sizeof(double) * SRC_STATE_LEN));
+  int32_t rc = ART_OK;
 
   const bool point = src->kind == 0;  // one origin for all rays: three single doubles instead of three columns
   const bool weighted = src->intensity != 0;
@@ -1067,10 +1103,11 @@ extern "C" int32_t art_run_source_host(ArtChain* c, const ArtSourceDesc* src, ui
   for (int i = 0; i < 3; ++i) a.origin[i] = src->origin[i];
   a.b = to_dev(&din);
   a.b.inten = nullptr;
+  a.origin_out = nullptr;
   if (point) {
     a.b.px = a.b.py = a.b.pz = nullptr;
-    for (int j = 0; j < 3; ++j)
-      ART_CUDA(cudaMemcpyAsync(col(j), &src->origin[j], sizeof(double), cudaMemcpyHostToDevice, st));
+    a.origin_out = col(0);  // the one origin of a point source: written by the generator into col(0..2)[0]
+    a.origin_stride = (long long)cap;
   }
   long long bx = ((long long)n + TPB - 1) / TPB;
   if (bx < 1) bx = 1;
@@ -1123,8 +1160,77 @@ extern "C" int32_t art_run_source_host(ArtChain* c, const ArtSourceDesc* src, ui
                     c->d_central, nullptr, st, false, 0.0, nullptr, 0, 0, weighted ? w.src_state : nullptr,
                     weighted ? std::log(fraction) : 0.0);
   if (rc) return rc;
-  return statistics_tail(c, &dout, n, false, nullptr, distance, manual_det, moments_host, central_host, det_host,
-                         peer_bufs, rank, world, exchanges);
+  *exchanges_out = exchanges;
+  return statistics_enqueue(c, &dout, n, false, nullptr, distance, manual_det, peer_bufs, rank, world);
+}
+
+extern "C" int32_t art_run_source_host(ArtChain* c, const ArtSourceDesc* src, uint32_t flags, double distance,
+                                       const ArtDetector* manual_det, double* moments_host, double* central_host,
+                                       ArtDetector* det_host, const uint64_t* peer_bufs, int32_t rank, int32_t world) {
+  if (!c || !src) return fail(ART_E_INVALID, "NULL argument");
+  if (src->kind < 0 || src->kind > 2)
+    return fail(ART_E_INVALID, "kind must be 0 (point source), 1 (plane wave) or 2 (extended source)");
+  if (src->kind == 2 && (src->n_point_sources < 1 || src->rays_per_source < 1 ||
+                         src->n_point_sources * src->rays_per_source != src->n_total))
+    return fail(ART_E_INVALID, "extended source: n_total must equal n_point_sources * rays_per_source");
+  if (src->n_total < 1 || src->first < 0 || src->count < 0 || src->stride < 1 ||
+      (src->count > 0 && src->first + (src->count - 1) * src->stride >= src->n_total))
+    return fail(ART_E_INVALID, "bad index range");
+  if (peer_bufs && (world < 1 || world > ART_PEER_MAX_RANKS || rank < 0 || rank >= world))
+    return fail(ART_E_INVALID, "rank / world out of range");
+  ART_CUDA(cudaSetDevice(c->device));
+  int32_t rc = ensure_workspace(c, (size_t)src->count);
+  if (rc) return rc;
+  HostWorkspace& w = c->ws;
+  if (!w.src_state) ART_CUDA(cudaMalloc(&w.src_state, sizeof(double) * SRC_STATE_LEN));
+  if (manual_det) *pinned_det_in(w) = *manual_det;  // the graph reads the caller's detector from pinned memory
+
+  // The sequence is a dozen short dependent launches: the second call with the same arguments captures it in a
+  // CUDA graph (the first one runs eagerly and sets every function attribute), later calls replay the graph.
+  // The key holds everything the launches depend on.
+  std::string key(reinterpret_cast<const char*>(src), sizeof(ArtSourceDesc));
+  {
+    const uint64_t extra[6] = {(uint64_t)flags, 0, manual_det ? 1u : 0u, (uint64_t)(uintptr_t)peer_bufs,
+                               (uint64_t)(uint32_t)rank << 32 | (uint32_t)world, (uint64_t)w.cap_n};
+    key.append(reinterpret_cast<const char*>(extra), sizeof(extra));
+    key.append(reinterpret_cast<const char*>(&distance), sizeof(distance));
+    if (peer_bufs) key.append(reinterpret_cast<const char*>(peer_bufs), sizeof(uint64_t) * world);
+  }
+  static const bool no_graph = std::getenv("ART_B200_NO_GRAPH") != nullptr;
+  int exchanges = 0;
+  if (!no_graph && w.src_graph && key == w.src_key) {
+    ART_CUDA(cudaGraphLaunch(w.src_graph, w.stream));
+    exchanges = w.src_exchanges;
+  } else if (!no_graph && key == w.src_last_key) {
+    if (w.src_graph) {
+      cudaGraphExecDestroy(w.src_graph);
+      w.src_graph = nullptr;
+      w.src_key.clear();
+    }
+    cudaGraph_t graph = nullptr;
+    ART_CUDA(cudaStreamBeginCapture(w.stream, cudaStreamCaptureModeThreadLocal));
+    rc = run_source_enqueue(c, src, flags, distance, manual_det != nullptr, peer_bufs, rank, world, &exchanges);
+    cudaError_t e = cudaStreamEndCapture(w.stream, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) return fail(ART_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&w.src_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      w.src_graph = nullptr;
+      return fail(ART_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    }
+    w.src_key = key;
+    w.src_exchanges = exchanges;
+    ART_CUDA(cudaGraphLaunch(w.src_graph, w.stream));
+  } else {
+    rc = run_source_enqueue(c, src, flags, distance, manual_det != nullptr, peer_bufs, rank, world, &exchanges);
+    if (rc) return rc;
+  }
+  w.src_last_key = key;
+  return statistics_finish(c, moments_host, central_host, det_host, peer_bufs != nullptr, exchanges);
 }
 
 // RayTracingCalculation for a host caller: host columns in, the bundle after every element (and / or

@@ -336,7 +336,7 @@ __device__ __forceinline__ void store_bundle(const BundleDev& O, long long at, b
 // the register budget per thread follows: 65536 / (2 BT)).  Measured on B200 (profiles/r02_summary.md): the
 // lock-step pair of the defect-free chains fits 128 registers without spilling, the Zernike recurrences need ~168.
 #ifndef ART_BT_QUADRIC
-#define ART_BT_QUADRIC 256
+#define ART_BT_QUADRIC 320
 #endif
 #ifndef ART_BT_TOROID
 #define ART_BT_TOROID 256
@@ -543,12 +543,12 @@ __global__ void __launch_bounds__(trace_block_threads(HAS_DEF, SURFS), HAS_DEF ?
     // lab-frame bundle after an inner element is materialised only when the caller wants the history.
     if constexpr (PACK) {
       RayT<D2> pr = pack_rays(r[0], r[N - 1]);
+      to_element_frame(sE[0], pr, eorg0);
       for (int k = 0; k < a.n_elements; ++k) {
         const bool inc_here = WANT_INC && (k == last || a.has_hist);
         const bool inner = k != last;
         if (any(pr.alive))
-          apply_element<WANT_INC, HAS_DEF, SURFS, D2>(sE[k], pr, sZ, sZoff, ignore_defects, inc_here, a.maps,
-                                                      k == 0 ? eorg0 : nullptr, k != 0, inner);
+          apply_element<WANT_INC, HAS_DEF, SURFS, D2>(sE[k], pr, sZ, sZoff, ignore_defects, inc_here, a.maps, inner);
         if (a.has_hist) {
           if (inner) {
             RayT<D2> lab;
@@ -562,14 +562,15 @@ __global__ void __launch_bounds__(trace_block_threads(HAS_DEF, SURFS), HAS_DEF ?
       }
       unpack_rays(pr, r[0], r[N - 1]);
     } else {
+#pragma unroll
+      for (int q = 0; q < N; ++q) to_element_frame(sE[0], r[q], eorg0);
       for (int k = 0; k < a.n_elements; ++k) {
         const bool inc_here = WANT_INC && (k == last || a.has_hist);
         const bool inner = k != last;
 #pragma unroll
         for (int q = 0; q < N; ++q)
           if (r[q].alive)
-            apply_element<WANT_INC, HAS_DEF, SURFS, double>(sE[k], r[q], sZ, sZoff, ignore_defects, inc_here, a.maps,
-                                                            k == 0 ? eorg0 : nullptr, k != 0, inner);
+            apply_element<WANT_INC, HAS_DEF, SURFS, double>(sE[k], r[q], sZ, sZoff, ignore_defects, inc_here, a.maps, inner);
         if (a.has_hist) {
           if (inner) {
             Ray lab[N];
@@ -839,7 +840,7 @@ constexpr int DB_COL_BYTES = DB_TILE * 8;
 constexpr int DB_STAGE_BYTES = STAGE_COLS * DB_COL_BYTES + DB_TILE;   // 8 columns + flags
 constexpr int DB_SMEM_BYTES = DB_STAGES * DB_STAGE_BYTES;
 #ifndef ART_DB_GROUP
-#define ART_DB_GROUP 4      // tiles whose alive flags the producer warp reads ahead in one go
+#define ART_DB_GROUP 8      // tiles whose alive flags the producer warp reads ahead in one go
 #endif
 constexpr int DB_GROUP = ART_DB_GROUP;
 static_assert(DB_STAGE_BYTES % 16 == 0 && DB_TILE % 16 == 0, "stages and flag rows stay 16-byte aligned");
@@ -1392,6 +1393,9 @@ __global__ void merge_moments_kernel(const double* __restrict__ rows, int n_rank
 // flag first).
 // Buffer of one rank (identical layout on all ranks, ART_PEER_BUFFER_BYTES(world)):
 //   double payload[2][world][PEER_MAX_DOUBLES];  u64 flags[world];  u64 epoch;  u64 status;
+//   u64 stats[ART_PEER_STATS]: exchanges counted, ns spent waiting for the peers' flags (spin), ns in the kernel --
+//   accumulated by thread 0 from %globaltimer; what a timeline would show (skew between the ranks vs the cost of
+//   the exchange itself), read back with art_peer_stats
 // ---------------------------------------------------------------------------------------------
 constexpr int PEER_MAX_DOUBLES = ART_PEER_MAX_VARIANTS * ART_MOMENTS_LEN;
 struct PeerArgs {
@@ -1424,7 +1428,9 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
     return reinterpret_cast<unsigned long long*>(base(owner) + (size_t)2 * a.world * PEER_MAX_DOUBLES);
   };
   unsigned long long* const mine = words(a.rank);  // flags[world], epoch, status
+  unsigned long long t_enter = 0ull, t_wait0 = 0ull, t_wait1 = 0ull;
   if (tid == 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_enter));
     sEpoch = mine[a.world] + 1ull;
     mine[a.world] = sEpoch;
     sFail = 0;
@@ -1440,6 +1446,7 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
   __threadfence_system();
   __syncthreads();
   // 2. publish, then wait for everybody
+  if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_wait0));
   if (tid < a.world) {
     st_release_sys(words(tid) + a.rank, epoch);
     unsigned long long polls = 0;
@@ -1452,6 +1459,7 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
     }
   }
   __syncthreads();
+  if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_wait1));
   if (sFail) {
     if (tid == 0) mine[a.world + 1] = epoch;  // status: the epoch that timed out
     return;
@@ -1468,6 +1476,14 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
     __syncthreads();
     for (int v = tid; v < a.n_variants; v += blockDim.x)
       autoplace_row(a.rows + (size_t)v * ART_CENTRAL_LEN, a.distance, a.det_out + v);
+  }
+  if (tid == 0) {
+    unsigned long long t_exit;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_exit));
+    unsigned long long* stats = mine + a.world + 2;
+    stats[0] += 1ull;
+    stats[1] += t_wait1 - t_wait0;
+    stats[2] += t_exit - t_enter;
   }
 }
 
@@ -1543,6 +1559,8 @@ struct SourceArgs {
   double* partials;  // null, or [block][PLEN_TRACE] rows in the central-sum layout: sum of the directions
                      // (ART_C_SUX..SUZ) and the ray count (ART_C_N) -- what FindCentralRay needs for the axis
                      // of ApplyGaussianIntensityToRayList (ART/ModuleSource.py:244)
+  double* origin_out;        // null, or where the one origin of a point source goes: origin_out[q * origin_stride]
+  long long origin_stride;   // (the trace kernel reads it as in.px[0], in.py[0], in.pz[0])
 };
 // sin and cos of a Vogel angle x = golden * k (0 <= x < 2^28 pi/2, i.e. k < 1.7e8) without the slow path
 // the library takes above 1e5 (Payne-Hanek, local memory): three-constant Cody-Waite reduction
@@ -1572,6 +1590,7 @@ __device__ __forceinline__ void vogel_sincos(double x, double& sn, double& cs) {
 __global__ void __launch_bounds__(TPB) source_kernel(const SourceArgs a) {
   const double golden = 3.141592653589793 * (3.0 - sqrt(5.0));
   double su[3] = {0.0, 0.0, 0.0}, cnt = 0.0;
+  if (a.origin_out && blockIdx.x == 0 && threadIdx.x < 3) a.origin_out[threadIdx.x * a.origin_stride] = a.origin[threadIdx.x];
   const bool fast = a.n_total < (1LL << 27);  // beyond that the reduction above is not exact: library sincos
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.count;
        j += (long long)gridDim.x * blockDim.x) {
@@ -1601,11 +1620,12 @@ __global__ void __launch_bounds__(TPB) source_kernel(const SourceArgs a) {
       py = a.rot[3] * xs + a.rot[4] * ys + a.origin[1];
       pz = a.rot[6] * xs + a.rot[7] * ys + a.origin[2];
     } else if (a.kind == 0) {
-      const double inv = frsqrt(fma(x, x, fma(y, y, 1.0)));
-      const double vx = x * inv, vy = y * inv, vz = inv;
-      ux = a.rot[0] * vx + a.rot[1] * vy + a.rot[2] * vz;
-      uy = a.rot[3] * vx + a.rot[4] * vy + a.rot[5] * vz;
-      uz = a.rot[6] * vx + a.rot[7] * vy + a.rot[8] * vz;
+      // normalise(rot (x, y, 1)): the reference normalises (x, y, 1), rotates and normalises again
+      // (ART/ModuleSource.py:23-81, Ray.vector setter); a rotation keeps the length, so one normalisation of the
+      // rotated vector is the same direction to rounding
+      ux = fma(a.rot[0], x, fma(a.rot[1], y, a.rot[2]));
+      uy = fma(a.rot[3], x, fma(a.rot[4], y, a.rot[5]));
+      uz = fma(a.rot[6], x, fma(a.rot[7], y, a.rot[8]));
       px = a.origin[0]; py = a.origin[1]; pz = a.origin[2];
     } else {
       px = a.rot[0] * x + a.rot[1] * y + a.origin[0];

@@ -277,6 +277,9 @@ ART_HD T tor_newton(const RayT<T>& r, T t, TorEval<T> e, double R, double r2, do
 #ifndef ART_QUARTIC_PRE
 #define ART_QUARTIC_PRE 1
 #endif
+#ifndef ART_QUARTIC_STEPS
+#define ART_QUARTIC_STEPS 2   // leading unchecked Newton steps taken on the quartic form
+#endif
 // The expanded quartic of the reference (ART/ModuleMirror.py:450-465) as P(t) = A^2 - 4 R^2 s with
 // s = x^2 + z^2, A = s + y^2 + R^2 - r^2:  P = F * (A + 2 R rho), the second factor positive and nearly
 // constant, so Newton on P takes (almost) the steps of Newton on F -- without the reciprocal square root
@@ -320,12 +323,15 @@ ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>
     e0.dF = sel(fine, e0.dF, e1.dF);
   }
 #if ART_QUARTIC_PRE && ART_NEWTON_PRE == 2
-  // two leading Newton steps on the quartic, then the checked iteration on F
+  // ART_QUARTIC_STEPS leading Newton steps on the quartic, then the checked iteration on F
   M ok = mand(act, e0.dF > 0.0);
   t0 = t0 - e0.F * fast_rcp(e0.dF);
-  e0 = tor_eval_quartic(r, t0, E.sp[3], E.sp[4]);
-  ok = mand(ok, e0.dF > 0.0);
-  t0 = t0 - e0.F * fast_rcp(e0.dF);
+#pragma unroll
+  for (int q = 1; q < ART_QUARTIC_STEPS; ++q) {
+    e0 = tor_eval_quartic(r, t0, E.sp[3], E.sp[4]);
+    ok = mand(ok, e0.dF > 0.0);
+    t0 = t0 - e0.F * fast_rcp(e0.dF);
+  }
   const T tb = tor_newton<+1, 0>(r, t0, tor_eval(r, t0, R, r2), R, r2, rr, ok);
 #else
   const T tb = tor_newton<+1, ART_NEWTON_PRE>(r, t0, e0, R, r2, rr, act);
@@ -546,14 +552,36 @@ ART_HD T unit_angle(T ax, T ay, T az, T bx, T by, T bz) {
 enum { SURFS_ANY = 0, SURFS_TOROID = 1, SURFS_QUADRIC = 2 };
 
 // ---------------------------------------------------------------------------------------------
-// one element acting on one ray (pair): ART/ModuleProcessing.py:284-309 (frame in, optic, frame out).
+// lab -> element frame, ART/ModuleProcessing.py:289-295: p_e = R (p - pos) + centre, u_e = R u, in place.
+// eorg: the origin shared by all rays (point source), already in this element's frame.
+// ---------------------------------------------------------------------------------------------
+template <class T>
+ART_HD void to_element_frame(const ElemDev& E, RayT<T>& r, const double* __restrict__ eorg = nullptr) {
+  T px, py, pz;
+  if (eorg) {
+    px = splat<T>(eorg[0]); py = splat<T>(eorg[1]); pz = splat<T>(eorg[2]);
+  } else {
+    const T dx = r.px - E.pos[0], dy = r.py - E.pos[1], dz = r.pz - E.pos[2];
+    px = mfma(E.rot[0], dx, mfma(E.rot[1], dy, mfma(E.rot[2], dz, E.ctr[0])));
+    py = mfma(E.rot[3], dx, mfma(E.rot[4], dy, mfma(E.rot[5], dz, E.ctr[1])));
+    pz = mfma(E.rot[6], dx, mfma(E.rot[7], dy, mfma(E.rot[8], dz, E.ctr[2])));
+  }
+  const T ux = mfma(E.rot[0], r.ux, mfma(E.rot[1], r.uy, E.rot[2] * r.uz));
+  const T uy = mfma(E.rot[3], r.ux, mfma(E.rot[4], r.uy, E.rot[5] * r.uz));
+  const T uz = mfma(E.rot[6], r.ux, mfma(E.rot[7], r.uy, E.rot[8] * r.uz));
+  r.px = px; r.py = py; r.pz = pz;
+  r.ux = ux; r.uy = uy; r.uz = uz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one element acting on one ray (pair) that is ALREADY in the element's frame: the optic of
+// ART/ModuleProcessing.py:298-301 and the frame change that follows, in place.
 //
 // The reference takes every ray back to the lab frame after each element and into the next element's frame
 // right afterwards (:306-309 then :289-295 of the next loop trip).  Between two elements the chain here hands
 // the ray over DIRECTLY: p' = M h + b, u' = M o with M = R_next R^T and b = R_next (pos - pos_next - R^T ctr)
 // + ctr_next composed once per element pair on the host (link_elements, art_lowering.h) -- one affine map
 // instead of two, 18 FMAs less per ray and element boundary.
-//   in_elem   r.p / r.u are already in THIS element's frame (handed over by the previous element)
 //   out_next  hand the ray over in the NEXT element's frame (E.nrot / E.noff); otherwise r leaves in the lab frame
 // The lab-frame bundle after an inner element (the per-element history the reference API returns) is obtained
 // from the handed-over ray with frame_to_lab(next element).
@@ -561,29 +589,10 @@ enum { SURFS_ANY = 0, SURFS_TOROID = 1, SURFS_QUADRIC = 2 };
 template <bool WANT_INC, bool HAS_DEF, int SURFS, class T>
 ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict__ ztab,
                           const int* __restrict__ zoff, bool ignore_defects, bool inc_here,
-                          const MapDev* __restrict__ maps = nullptr,
-                          const double* __restrict__ eorg = nullptr, bool in_elem = false, bool out_next = false) {
+                          const MapDev* __restrict__ maps, bool out_next) {
   typedef typename MaskOf<T>::type M;
   const M act = r.alive;
-  // lab -> element frame (:289-295): p_e = R (p - pos) + centre, u_e = R u
-  // eorg: the origin shared by all rays (point source), already in this element's frame
-  RayT<T> e;
-  if (in_elem) {
-    e.px = r.px; e.py = r.py; e.pz = r.pz;
-    e.ux = r.ux; e.uy = r.uy; e.uz = r.uz;
-  } else {
-    if (eorg) {
-      e.px = splat<T>(eorg[0]); e.py = splat<T>(eorg[1]); e.pz = splat<T>(eorg[2]);
-    } else {
-      const T dx = r.px - E.pos[0], dy = r.py - E.pos[1], dz = r.pz - E.pos[2];
-      e.px = mfma(E.rot[0], dx, mfma(E.rot[1], dy, mfma(E.rot[2], dz, E.ctr[0])));
-      e.py = mfma(E.rot[3], dx, mfma(E.rot[4], dy, mfma(E.rot[5], dz, E.ctr[1])));
-      e.pz = mfma(E.rot[6], dx, mfma(E.rot[7], dy, mfma(E.rot[8], dz, E.ctr[2])));
-    }
-    e.ux = mfma(E.rot[0], r.ux, mfma(E.rot[1], r.uy, E.rot[2] * r.uz));
-    e.uy = mfma(E.rot[3], r.ux, mfma(E.rot[4], r.uy, E.rot[5] * r.uz));
-    e.uz = mfma(E.rot[6], r.ux, mfma(E.rot[7], r.uy, E.rot[8] * r.uz));
-  }
+  RayT<T>& e = r;   // the ray in this element's frame; r.p / r.u are overwritten only once h and o are known
   T t;
   const int surf = E.surface;
   if (surf == ART_SURF_PLANE || surf == ART_SURF_MASK) {
@@ -632,10 +641,9 @@ ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict
     return;
   }
   T hx = mfma(t, e.ux, e.px), hy = mfma(t, e.uy, e.py), hz = mfma(t, e.uz, e.pz);
-  T ox = e.ux, oy = e.uy, oz = e.uz;  // outgoing direction, element frame
   T inc = r.inc;
   if (surf == ART_SURF_MASK) {
-    // _TransmitMaskRay, ART/ModuleMask.py:93-108: direction unchanged, incidence vs ez
+    // _TransmitMaskRay, ART/ModuleMask.py:93-108: direction unchanged (r.u stays), incidence vs ez
     if (WANT_INC && inc_here) inc = unit_angle(e.ux, e.uy, e.uz, splat<T>(0.0), splat<T>(0.0), splat<T>(1.0));
   } else {
     T nx, ny, nz;
@@ -684,29 +692,28 @@ ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict
     }
     // _ReflectionMirrorRay, ART/ModuleMirror.py:878-906: u' = u - 2 (n.u) n, incidence = angle(-u, n)
     const T d = mfma(nx, e.ux, mfma(ny, e.uy, nz * e.uz));
-    ox = mfma(-2.0 * d, nx, e.ux); oy = mfma(-2.0 * d, ny, e.uy); oz = mfma(-2.0 * d, nz, e.uz);
+    if (WANT_INC && inc_here) inc = unit_angle(-e.ux, -e.uy, -e.uz, nx, ny, nz);
+    T ox = mfma(-2.0 * d, nx, e.ux), oy = mfma(-2.0 * d, ny, e.uy), oz = mfma(-2.0 * d, nz, e.uz);
     // Ray.vector setter renormalises (ART/ModuleOpticalRay.py:85-90); one Newton step is exact here
     const T sc = mfma(-0.5, mfma(ox, ox, mfma(oy, oy, oz * oz)), 1.5);
-    ox = ox * sc; oy = oy * sc; oz = oz * sc;
-    if (WANT_INC && inc_here) inc = unit_angle(-e.ux, -e.uy, -e.uz, nx, ny, nz);
+    r.ux = ox * sc; r.uy = oy * sc; r.uz = oz * sc;   // the outgoing direction, still in this element's frame
   }
-  const T path = r.path + mabs(t);  // |P - A| with |u| = 1 (ModuleMirror.py:904, ModuleMask.py:100)
-  // element -> lab frame (:306-309): p = R^T (p_e - centre) + pos, u = R^T u_e.
-  // Written unconditionally: a lane that missed is dead from here on and its columns are never read
-  // or stored again, so the old P, U need not stay alive through this function just to be selected back.
+  r.path = r.path + mabs(t);  // |P - A| with |u| = 1 (ModuleMirror.py:904, ModuleMask.py:100)
+  r.inc = inc;
+  r.alive = hit;
+  // Leave the element: lab frame (:306-309: p = R^T (p_e - centre) + pos, u = R^T u_e) after the last element,
+  // else straight into the next element's frame (p' = M h + b, u' = M o).  Written unconditionally: a lane that
+  // missed is dead from here on and its columns are never read or stored again.
+  const T ox = r.ux, oy = r.uy, oz = r.uz;
   if (!out_next) {
     const T dx = hx - E.ctr[0], dy = hy - E.ctr[1], dz = hz - E.ctr[2];
     r.px = mfma(E.rot[0], dx, mfma(E.rot[3], dy, mfma(E.rot[6], dz, E.pos[0])));
     r.py = mfma(E.rot[1], dx, mfma(E.rot[4], dy, mfma(E.rot[7], dz, E.pos[1])));
     r.pz = mfma(E.rot[2], dx, mfma(E.rot[5], dy, mfma(E.rot[8], dz, E.pos[2])));
-    if (!(surf == ART_SURF_MASK && !in_elem)) {
-      // (a mask does not deflect, ART/ModuleMask.py:93-108: when r.u still is the lab-frame direction it stays)
-      r.ux = mfma(E.rot[0], ox, mfma(E.rot[3], oy, E.rot[6] * oz));
-      r.uy = mfma(E.rot[1], ox, mfma(E.rot[4], oy, E.rot[7] * oz));
-      r.uz = mfma(E.rot[2], ox, mfma(E.rot[5], oy, E.rot[8] * oz));
-    }
+    r.ux = mfma(E.rot[0], ox, mfma(E.rot[3], oy, E.rot[6] * oz));
+    r.uy = mfma(E.rot[1], ox, mfma(E.rot[4], oy, E.rot[7] * oz));
+    r.uz = mfma(E.rot[2], ox, mfma(E.rot[5], oy, E.rot[8] * oz));
   } else {
-    // straight into the next element's frame: p' = M h + b, u' = M o
     r.px = mfma(E.nrot[0], hx, mfma(E.nrot[1], hy, mfma(E.nrot[2], hz, E.noff[0])));
     r.py = mfma(E.nrot[3], hx, mfma(E.nrot[4], hy, mfma(E.nrot[5], hz, E.noff[1])));
     r.pz = mfma(E.nrot[6], hx, mfma(E.nrot[7], hy, mfma(E.nrot[8], hz, E.noff[2])));
@@ -714,9 +721,6 @@ ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict
     r.uy = mfma(E.nrot[3], ox, mfma(E.nrot[4], oy, E.nrot[5] * oz));
     r.uz = mfma(E.nrot[6], ox, mfma(E.nrot[7], oy, E.nrot[8] * oz));
   }
-  r.path = path;
-  r.inc = inc;
-  r.alive = hit;
 }
 
 // A ray that sits in element E's frame (handed over by the previous element) expressed in the lab frame:

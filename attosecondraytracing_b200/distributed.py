@@ -153,6 +153,18 @@ class PeerExchange:
         return int(out.value)
 
 
+    def stats(self, reset=False):
+        """{"exchanges", "wait_us", "kernel_us"}: per-exchange averages on THIS rank since the last reset -- time
+        spent waiting for the peers' flags (rank skew + NVLink round trip) and inside the exchange kernel
+        (art_peer_stats; synchronises the stream)."""
+        import ctypes as C
+        out = (C.c_uint64 * _cabi.PEER_STATS)()
+        _cabi.check(_cabi.lib().art_peer_stats(self._ptrs, self.rank, self.world, out, 1 if reset else 0,
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        n = int(out[0])
+        return {"exchanges": n, "wait_us": (out[1] / n / 1e3) if n else 0.0, "kernel_us": (out[2] / n / 1e3) if n else 0.0}
+
+
 def merge_moments(rows):
     """Host-side merge of moments rows from several shards (sequence of (24,) arrays / tensors)."""
     rows = torch.stack([torch.as_tensor(r, dtype=torch.float64) for r in rows])

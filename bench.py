@@ -429,14 +429,32 @@ def measure_bundle(ctx, name, steps, warmup, rays=0, main=False, histograms=Fals
     step()  # one eager step to count this step's launches
     launches_per_step = lib.art_launch_count() - launches0
     ctx.barrier()
+    if peer is not None:
+        peer.stats(reset=True)
     ev0.record()
     for _ in range(steps):
         final, central, det, mom = run_step()
     ev1.record()
     ctx.barrier()
     ms_total = ev0.elapsed_time(ev1)
-    if peer is not None and peer.status() != 0:
-        raise RuntimeError("peer-memory exchange timed out (a rank did not arrive)")
+    breakdown = None
+    if peer is not None:
+        if peer.status() != 0:
+            raise RuntimeError("peer-memory exchange timed out (a rank did not arrive)")
+        # what a timeline of the step would show: per exchange, how long each rank waited for the others' flags
+        # (skew between the ranks + the NVLink round trip) and how long the exchange kernel ran
+        st = peer.stats()
+        mine = torch.tensor([st["wait_us"], st["kernel_us"]], dtype=torch.float64, device=dev)
+        allr = torch.empty((world, 2), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.cpu().numpy()
+        breakdown = {"exchanges_per_step": st["exchanges"] / steps,
+                     "wait_for_peers_us": {"min_rank": float(allr[:, 0].min()), "mean": float(allr[:, 0].mean()),
+                                           "max_rank": float(allr[:, 0].max())},
+                     "exchange_kernel_us": {"min_rank": float(allr[:, 1].min()), "mean": float(allr[:, 1].mean()),
+                                            "max_rank": float(allr[:, 1].max())},
+                     "note": "per exchange, %globaltimer inside peer_exchange_kernel; the rank that arrives last waits "
+                             "only the NVLink round trip (min_rank), the others also the skew between the ranks"}
 
     # the dominant kernel alone, CUDA events on the launching stream.  want_central=False only skips the
     # separate fold launch: trace_kernel itself always reduces the central sums, so this IS the step's K1.
@@ -469,6 +487,8 @@ def measure_bundle(ctx, name, steps, warmup, rays=0, main=False, histograms=Fals
     }
     if histograms:
         res["histograms"] = "64x64 spot + 128 delay bins per step, int64 all-reduce"
+    if breakdown is not None:
+        res["multi_gpu_breakdown"] = breakdown
 
     if main:
         # ---- end to end, the reference's real host input: the source DESCRIPTION (SourceProperties) in,
@@ -739,7 +759,8 @@ def run_b200(args):
             "gpu_launches": main_res["gpu_launches"], "cuda_graph": main_res["cuda_graph"],
             "clocks": main_res["clocks"], "interactions_per_step": main_res["interactions_per_step"],
         }
-        for k in ("e2e_host_columns", "survivors_rank0", "result", "result_variant0_rank0", "histograms"):
+        for k in ("e2e_host_columns", "survivors_rank0", "result", "result_variant0_rank0", "histograms",
+                  "multi_gpu_breakdown"):
             if k in main_res:
                 line[k] = main_res[k]
         if world > 1:

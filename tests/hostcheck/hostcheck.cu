@@ -59,11 +59,10 @@ extern "C" int hc_trace(const ArtElementDesc* els, int n_el, const ArtZernikeDes
     r.alive = true;
     // the trace kernel's element loop: inner elements hand the ray over in the next element's frame and
     // the lab-frame bundle of the history is recovered with frame_to_lab
+    to_element_frame(E[0], r);
     for (int k = 0; k < n_el; ++k) {
       const bool inner = k + 1 < n_el;
-      if (r.alive)
-        apply_element<true, true, SURFS_ANY, double>(E[k], r, ztab.data(), zoff.data(), ign, true, maps.data(), nullptr,
-                                                     k != 0, inner);
+      if (r.alive) apply_element<true, true, SURFS_ANY, double>(E[k], r, ztab.data(), zoff.data(), ign, true, maps.data(), inner);
       Ray w = r;
       if (inner) frame_to_lab(E[k + 1], r, w);
       const long long o = (long long)k * n + i;

@@ -93,10 +93,32 @@ def main():
     rows = [torch.empty(_cabi.MOMENTS_LEN, dtype=torch.float64, device=dev) for _ in range(world)]
     dist.all_gather(rows, torch.from_numpy(mom).to(dev))
     assert all(torch.equal(r, rows[0]) for r in rows), "ranks disagree on the whole-bundle moments"
+    # the same from the source DESCRIPTION: every rank generates its own round-robin share on the device, the axis /
+    # extent of the intensity profile are combined over the ranks inside the call (art_run_source_host)
+    import attosecondraytracing_b200.ModuleSource as msrc
+    n_src = gd["src_P"].shape[0]
+    desc = msrc.source_descriptor(dict(gd.spec["source"]), first=rank, stride=world)
+    mom2, cen2, det2 = chain.run_source(desc, gd.spec["detector_distance"], ignore_defects=gd.ignore_defects, peer=peer)
+    s2 = engine.summary_from_moments(mom2, cen2)
+    for key in ("SpotSizeSD", "SpotSizeSD_w", "ETransmission"):
+        assert abs(s2[key] - gd[key]) <= 1e-9, (key, s2[key], float(gd[key]))
+    assert abs(s2["DurationSD"] - gd["DurationSD"]) <= 1e-5 and abs(s2["DurationSD_w"] - gd["DurationSD_w"]) <= 1e-5
+    assert s2["n_rays"] == gd.out(gd.n_elements - 1)["num"].size
+    # a rank with an EMPTY shard still takes part in the exchanges (rank 0 holds everything, the others nothing)
+    if rank == 0:
+        host0 = RayBundle.from_numpy(gd["src_P"], gd["src_U"], intensity=gd["src_I"], device="cpu")
+    else:
+        host0 = RayBundle.from_numpy(gd["src_P"][:0], gd["src_U"][:0], intensity=gd["src_I"][:0], device="cpu")
+    mom3, cen3, _ = chain.run_host(host0, gd.spec["detector_distance"], ignore_defects=gd.ignore_defects, peer=peer)
+    s3 = engine.summary_from_moments(mom3, cen3)
+    assert abs(s3["SpotSizeSD"] - gd["SpotSizeSD"]) <= 1e-9 and s3["n_rays"] == s2["n_rays"]
+    st = peer.stats()
+    assert st["exchanges"] > 0 and st["kernel_us"] > 0
     chain.close()
     dist.barrier()
     if rank == 0:
-        print("peer exchange ok on %d ranks" % world, flush=True)
+        print("peer exchange ok on %d ranks (exchange kernel %.1f us, of which %.1f us waiting for the peers, "
+              "averaged over %d exchanges on rank 0)" % (world, st["kernel_us"], st["wait_us"], st["exchanges"]), flush=True)
     dist.destroy_process_group()
 
 

@@ -196,6 +196,21 @@ def test_source_descriptor_entry_point(name):
     assert abs(s["DurationSD_w"] - g["DurationSD_w"]) <= DELAY_TOL_FS
     assert abs(s["ETransmission"] - g["ETransmission"]) <= 1e-9
     assert np.max(np.abs(np.array(det.centre[:]) - g["det_centre"])) <= point_tol(name)
+    # the second identical call captures the launch sequence in a CUDA graph, later ones replay it: same numbers
+    for _ in range(3):
+        mom_r, cen_r, det_r = chain.run_source(desc, g.spec["detector_distance"], ignore_defects=g.ignore_defects)
+        assert np.array_equal(mom_r, mom) and np.array_equal(cen_r, cen)
+        assert np.array_equal(np.array(det_r.centre[:]), np.array(det.centre[:]))
+    # ... also with the caller's detector, whose content may change between replays
+    md1, cd1, _ = chain.run_source(desc, g.spec["detector_distance"], ignore_defects=g.ignore_defects, manual_det=det)
+    md1, cd1, _ = chain.run_source(desc, g.spec["detector_distance"], ignore_defects=g.ignore_defects, manual_det=det)
+    assert np.array_equal(md1, mom)
+    import copy as _copy
+    det_shift = _copy.copy(det)
+    for i in range(3):
+        det_shift.centre[i] = det.centre[i] + 5.0 * det.cvec[i]
+    md2, _, _ = chain.run_source(desc, g.spec["detector_distance"], ignore_defects=g.ignore_defects, manual_det=det_shift)
+    assert not np.array_equal(md2, mom) and md2[0] == mom[0]
     # a strided share of the same bundle agrees with the host-column path on the same rays
     desc2 = msrc.source_descriptor(dict(g.spec["source"]), first=1, stride=3)
     m2, c2, _ = chain.run_source(desc2, g.spec["detector_distance"], ignore_defects=g.ignore_defects)

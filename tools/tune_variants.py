@@ -99,16 +99,28 @@ def main():
     libs.append(os.path.join(ROOT, "attosecondraytracing_b200", "libart_b200.so"))
     runs = [(lib, {}) for lib in libs]
     runs.append((libs[-1], {"ART_B200_DET_LEGACY": "1"}))  # A/B: the LDGSTS detector kernel instead of the bulk-copy one
-    for lib, extra in runs:
-        env = dict(os.environ, ART_B200_LIB=lib, **extra)
-        try:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=env, capture_output=True,
-                                 text=True, timeout=300)
-            line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
-            msg = line[0][7:] if line else "FAILED " + out.stderr[-400:]
-        except subprocess.TimeoutExpired:
-            msg = "TIMEOUT"
-        print(os.path.basename(lib), " ".join(f"{k}={v}" for k, v in extra.items()), msg, flush=True)
+    # process-to-process variation on a shared box is a few per cent: every build runs REPS times, interleaved with
+    # the others, and the fastest time of each entry is kept
+    reps = int(os.environ.get("TUNE_REPS", "2"))
+    best = {}
+    for _ in range(reps):
+        for lib, extra in runs:
+            key = os.path.basename(lib) + " " + " ".join(f"{k}={v}" for k, v in extra.items())
+            env = dict(os.environ, ART_B200_LIB=lib, **extra)
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=env, capture_output=True,
+                                     text=True, timeout=300)
+                line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
+                if not line:
+                    best[key] = "FAILED " + out.stderr[-400:]
+                    continue
+                res = json.loads(line[0][7:])
+                cur = best.get(key)
+                best[key] = res if not isinstance(cur, dict) else {k: min(v, cur[k]) for k, v in res.items()}
+            except subprocess.TimeoutExpired:
+                best[key] = "TIMEOUT"
+    for key, res in best.items():
+        print(key, json.dumps(res) if isinstance(res, dict) else res, flush=True)
 
 
 if __name__ == "__main__":
