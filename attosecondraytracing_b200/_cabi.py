@@ -37,6 +37,7 @@ MOMENT_MAX = [M_XMAX, M_YMAX, M_DMAX, M_TMAX]
 TRACE_IGNORE_DEFECTS = 1
 TRACE_NO_INCIDENCE = 2
 TRACE_UNIFORM_POINT = 4
+TRACE_NO_FOLD = 8
 
 c_double_p = C.POINTER(C.c_double)
 c_u8_p = C.POINTER(C.c_uint8)
@@ -149,6 +150,8 @@ _SIGNATURES = {
                                            C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
     "art_peer_exchange": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_double, C.c_void_p, C.c_void_p]),
+    "art_peer_exchange_fold": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "art_peer_status": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_void_p]),
     "art_peer_stats": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_int32,
                                    C.c_void_p]),

@@ -72,6 +72,8 @@ struct ArtChain {
   int surfs = 0;                 // SURFS_* class of the chain's surfaces
   double* d_partials = nullptr;
   size_t partial_rows = 0;
+  int unfolded_rows = 0;         // partial rows a NO_FOLD launch left for art_peer_exchange_fold (0: none)
+  int unfolded_kind = -1;        // 0: central rows (PLEN_TRACE), 1: moments rows (PLEN_DET)
   double* d_central = nullptr;   // n_variants x ART_CENTRAL_LEN scratch (sweep, host run)
   double* d_moments = nullptr;   // n_variants x ART_MOMENTS_LEN scratch
   ArtDetector* d_det = nullptr;  // n_variants scratch
@@ -432,7 +434,11 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
     if (want_inc) ART_TRACE_LAUNCH(true, false);
     else ART_TRACE_LAUNCH(false, false);
     ART_LAUNCHED();
-    if (central_out && chunk_blocks == 0) {
+    if ((flags & ART_TRACE_NO_FOLD) && chunk_blocks == 0) {
+      if (n_variants != 1) return fail(ART_E_INVALID, "ART_TRACE_NO_FOLD is for one variant");
+      c->unfolded_rows = bpv;
+      c->unfolded_kind = 0;
+    } else if (central_out && chunk_blocks == 0) {
       // place_det: fold the central sums and place the variant's detector in the same launch
       fold_kernel<<<n_variants, TPB, 0, st>>>(c->d_partials, bpv, place_det ? 3 : 0, central_out, nullptr,
                                               place_distance, place_det);
@@ -500,7 +506,9 @@ static int32_t global_scratch(size_t rows, void* stream, double** out) {
 extern "C" int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bundle, int32_t n_variants,
                                         const ArtDetector* det, double* x_out, double* y_out, double* l_out,
                                         double* moments_out, void* stream) {
-  if (!bundle || !det || !moments_out || n_variants < 1) return fail(ART_E_INVALID, "bad argument");
+  if (!bundle || !det || n_variants < 1) return fail(ART_E_INVALID, "bad argument");
+  if (!moments_out && (!chain || n_variants != 1))
+    return fail(ART_E_INVALID, "moments_out may be NULL only with a chain and one variant (art_peer_exchange_fold)");
   ArtChain tmp;  // launch-shape defaults when no chain lends its scratch
   if (!chain) {
     // no chain has opted this device in to the kernel's shared-memory size yet
@@ -558,12 +566,22 @@ extern "C" int32_t art_detector_moments(ArtChain* chain, const ArtBundleView* bu
       return fail(ART_E_INVALID, "n_variants exceeds the chain's variant count");
     detector_bulk_kernel<<<dim3((unsigned)bulk_bpv, n_variants), DB_THREADS, DB_SMEM_BYTES, st>>>(a);
     ART_LAUNCHED();
+    if (!moments_out) {
+      chain->unfolded_rows = (int)bulk_bpv;
+      chain->unfolded_kind = 1;
+      return ART_OK;
+    }
     fold_kernel<<<n_variants, TPB, 0, st>>>(chain->d_partials, (int)bulk_bpv, 2, nullptr, moments_out);
     ART_LAUNCHED();
     return ART_OK;
   }
   detector_kernel<<<dim3(bpv, n_variants), TPB, DET_STAGE_BYTES, st>>>(a);
   ART_LAUNCHED();
+  if (!moments_out) {
+    chain->unfolded_rows = bpv;
+    chain->unfolded_kind = 1;
+    return ART_OK;
+  }
   fold_kernel<<<n_variants, TPB, 0, st>>>(chain->d_partials, bpv, 2, nullptr, moments_out);
   ART_LAUNCHED();
   return ART_OK;
@@ -659,9 +677,9 @@ extern "C" int32_t art_moments_merge(const double* rows, int32_t n_ranks, int32_
   return ART_OK;
 }
 
-extern "C" int32_t art_peer_exchange(const uint64_t* peer_bufs, int32_t rank, int32_t world, int32_t kind,
-                                     int32_t n_variants, double* rows, double distance, ArtDetector* det_out,
-                                     void* stream) {
+static int32_t peer_exchange_impl(const uint64_t* peer_bufs, int32_t rank, int32_t world, int32_t kind,
+                                  int32_t n_variants, double* rows, double distance, ArtDetector* det_out,
+                                  void* stream, const double* partials, int n_partials) {
   if (!peer_bufs || !rows) return fail(ART_E_INVALID, "NULL argument");
   if (world < 1 || world > ART_PEER_MAX_RANKS || rank < 0 || rank >= world)
     return fail(ART_E_INVALID, "rank / world out of range");
@@ -680,9 +698,32 @@ extern "C" int32_t art_peer_exchange(const uint64_t* peer_bufs, int32_t rank, in
   a.distance = distance;
   a.det_out = kind == 0 ? det_out : nullptr;
   a.spin_limit = 50000000ull;  // x (64 ns sleep + a system-scope load) ~ 10 s
+  a.partials = partials;
+  a.n_partials = n_partials;
   peer_exchange_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
   ART_LAUNCHED();
   return ART_OK;
+}
+
+extern "C" int32_t art_peer_exchange(const uint64_t* peer_bufs, int32_t rank, int32_t world, int32_t kind,
+                                     int32_t n_variants, double* rows, double distance, ArtDetector* det_out,
+                                     void* stream) {
+  return peer_exchange_impl(peer_bufs, rank, world, kind, n_variants, rows, distance, det_out, stream, nullptr, 0);
+}
+
+extern "C" int32_t art_peer_exchange_fold(ArtChain* chain, const uint64_t* peer_bufs, int32_t rank, int32_t world,
+                                          int32_t kind, double* rows, double distance, ArtDetector* det_out,
+                                          void* stream) {
+  if (!chain) return fail(ART_E_INVALID, "chain is NULL");
+  if (kind != 0 && kind != 1) return fail(ART_E_INVALID, "kind must be 0 (central) or 1 (moments)");
+  if (chain->unfolded_rows < 1 || chain->unfolded_kind != kind)
+    return fail(ART_E_INVALID, "the chain holds no unfolded rows of this kind (art_trace with ART_TRACE_NO_FOLD / "
+                               "art_detector_moments with moments_out == NULL must be the chain's last launch)");
+  const int n_partials = chain->unfolded_rows;
+  chain->unfolded_rows = 0;
+  chain->unfolded_kind = -1;
+  return peer_exchange_impl(peer_bufs, rank, world, kind, 1, rows, distance, det_out, stream, chain->d_partials,
+                            n_partials);
 }
 
 extern "C" int32_t art_peer_status(const uint64_t* peer_bufs, int32_t rank, int32_t world, uint64_t* status_out,
@@ -756,7 +797,12 @@ extern "C" int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t fi
   const bool no_points = !bundle->px && !bundle->py && !bundle->pz;  // point source kept as a uniform origin
   if (!(no_points && kind == 0 && bundle->ux && bundle->uy && bundle->uz)) {
     if (const char* why = check_columns(bundle, true)) return fail(ART_E_INVALID, std::string("bundle: ") + why);
+  } else if (!aligned16(bundle->ux) || !aligned16(bundle->uy) || !aligned16(bundle->uz) ||
+             (bundle->path && !aligned16(bundle->path))) {
+    return fail(ART_E_INVALID, "bundle: ray columns must be 16-byte aligned");
   }
+  if (bundle->alive && (reinterpret_cast<uintptr_t>(bundle->alive) & 1))
+    return fail(ART_E_INVALID, "bundle: the alive flags must be 2-byte aligned");
   SourceArgs a;
   a.kind = kind;
   a.n_total = n_total;
@@ -774,7 +820,7 @@ extern "C" int32_t art_source_generate(int32_t kind, int64_t n_total, int64_t fi
   a.partials = nullptr;
   a.origin_out = nullptr;
   a.origin_stride = 0;
-  long long bx = (count + TPB - 1) / TPB;
+  long long bx = ((count + 1) / 2 + TPB - 1) / TPB;  // two rays per thread
   if (bx < 1) bx = 1;
   if (bx > 148 * 16) bx = 148 * 16;
   source_kernel<<<(unsigned)bx, TPB, 0, (cudaStream_t)stream>>>(a);
@@ -1109,7 +1155,7 @@ static int32_t run_source_enqueue(ArtChain* c, const ArtSourceDesc* src, uint32_
     a.origin_out = col(0);  // the one origin of a point source: written by the generator into col(0..2)[0]
     a.origin_stride = (long long)cap;
   }
-  long long bx = ((long long)n + TPB - 1) / TPB;
+  long long bx = (((long long)n + 1) / 2 + TPB - 1) / TPB;  // two rays per thread
   if (bx < 1) bx = 1;
   if (bx > (long long)c->sm_count * 8) bx = (long long)c->sm_count * 8;
   a.partials = weighted ? c->d_partials : nullptr;

@@ -1408,6 +1408,9 @@ struct PeerArgs {
   double distance;     // kind 0 with det_out
   ArtDetector* det_out;
   unsigned long long spin_limit;  // polls before giving up (status word set, rows left unreduced)
+  const double* partials;  // null, or the per-block partial rows of the trace / detector kernel that ran just
+  int n_partials;          // before (one variant): folded into `rows` here, in fold_kernel's fixed order, instead
+                           // of by a fold launch of its own
 };
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -1423,6 +1426,40 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
   const int tid = threadIdx.x;
   const int rlen = a.kind == 0 ? ART_CENTRAL_LEN : (a.kind == 1 ? ART_MOMENTS_LEN : 2);
   const int len = a.n_variants * rlen;
+  if (a.partials) {
+    // second reduction stage of the kernel that ran before (what fold_kernel modes 0 / 2 do), one variant:
+    // thread t folds rows t, t + 256, ..., then a shuffle tree and the warps in order -- a fixed order
+    __shared__ double sFold[8 * ART_MOMENTS_LEN];
+    const int lane = tid & 31, warp = tid >> 5;
+    double acc[ART_MOMENTS_LEN];
+#pragma unroll
+    for (int j = 0; j < ART_MOMENTS_LEN; ++j) {
+      const int op = (a.kind == 1 && j < rlen) ? moment_op(j) : 0;
+      acc[j] = op == 0 ? 0.0 : (op == 1 ? CUDART_INF : -CUDART_INF);
+    }
+    for (int b = tid; b < a.n_partials; b += 256) {
+      const double* prow = a.partials + (size_t)b * rlen;
+#pragma unroll
+      for (int j = 0; j < ART_MOMENTS_LEN; ++j)
+        if (j < rlen) acc[j] = red_any(a.kind == 1 ? moment_op(j) : 0, acc[j], prow[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < ART_MOMENTS_LEN; ++j) {
+      if (j >= rlen) break;
+      const int op = a.kind == 1 ? moment_op(j) : 0;
+      double x = acc[j];
+      for (int o = 16; o > 0; o >>= 1) x = red_any(op, x, __shfl_xor_sync(0xffffffffu, x, o));
+      if (lane == 0) sFold[warp * rlen + j] = x;
+    }
+    __syncthreads();
+    if (tid < rlen) {
+      const int op = a.kind == 1 ? moment_op(tid) : 0;
+      double x = sFold[tid];
+      for (int w = 1; w < 8; ++w) x = red_any(op, x, sFold[w * rlen + tid]);
+      a.rows[tid] = x;
+    }
+    __syncthreads();   // a.rows is read by all threads below (same block: visible after the barrier)
+  }
   auto base = [&](int owner) { return reinterpret_cast<double*>(a.bufs[owner]); };
   auto words = [&](int owner) {
     return reinterpret_cast<unsigned long long*>(base(owner) + (size_t)2 * a.world * PEER_MAX_DOUBLES);
@@ -1443,7 +1480,9 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
     double* dst = base(p) + half + (size_t)a.rank * PEER_MAX_DOUBLES;
     for (int j = tid; j < len; j += blockDim.x) dst[j] = a.rows[j];
   }
-  __threadfence_system();
+  // No system-wide fence here: the barrier orders every thread's row stores before the publishing threads, and
+  // their st.release.sys is cumulative, so a peer that acquires the flag observes the whole row (PTX memory model:
+  // causality through bar.sync + release at system scope).  The fence cost ~2 us per exchange.
   __syncthreads();
   // 2. publish, then wait for everybody
   if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_wait0));
@@ -1587,60 +1626,86 @@ __device__ __forceinline__ void vogel_sincos(double x, double& sn, double& cs) {
   cs = ((q + 1) & 2) ? -b : b;
 }
 
+// one ray of the bundle: local index j -> spiral index a.first + j a.stride
+struct SourceRay {
+  double px, py, pz, ux, uy, uz;
+};
+__device__ __forceinline__ SourceRay source_ray(const SourceArgs& a, long long j, bool fast, double golden) {
+  const long long idx = a.first + j * a.stride;
+  // the Vogel point that shapes the direction (kinds 0, 2) or the position (kind 1)
+  const double k = (double)(a.kind == 2 ? idx % a.per : idx);
+  const double kn = (double)(a.kind == 2 ? a.per : a.n_total);
+  const double rad = fsqrt(fdiv(k, kn)) * a.rho;
+  double s, c;
+  if (fast) vogel_sincos(golden * k, s, c);
+  else sincos(golden * k, &s, &c);
+  const double x = c * rad, y = s * rad;
+  SourceRay o;
+  if (a.kind == 2) {
+    const double ks = (double)(idx / a.per);
+    const double rs = fsqrt(fdiv(ks, (double)a.n_ps)) * a.ps_radius;
+    double ss, cs;
+    if (fast) vogel_sincos(golden * ks, ss, cs);
+    else sincos(golden * ks, &ss, &cs);
+    const double xs = cs * rs, ys = ss * rs;
+    const double inv = frsqrt(fma(x, x, fma(y, y, 1.0)));
+    const double vx = x * inv, vy = y * inv, vz = inv;
+    o.ux = a.rot[0] * vx + a.rot[1] * vy + a.rot[2] * vz;
+    o.uy = a.rot[3] * vx + a.rot[4] * vy + a.rot[5] * vz;
+    o.uz = a.rot[6] * vx + a.rot[7] * vy + a.rot[8] * vz;
+    o.px = a.rot[0] * xs + a.rot[1] * ys + a.origin[0];
+    o.py = a.rot[3] * xs + a.rot[4] * ys + a.origin[1];
+    o.pz = a.rot[6] * xs + a.rot[7] * ys + a.origin[2];
+  } else if (a.kind == 0) {
+    // normalise(rot (x, y, 1)): the reference normalises (x, y, 1), rotates and normalises again
+    // (ART/ModuleSource.py:23-81, Ray.vector setter); a rotation keeps the length, so one normalisation of the
+    // rotated vector is the same direction to rounding
+    o.ux = fma(a.rot[0], x, fma(a.rot[1], y, a.rot[2]));
+    o.uy = fma(a.rot[3], x, fma(a.rot[4], y, a.rot[5]));
+    o.uz = fma(a.rot[6], x, fma(a.rot[7], y, a.rot[8]));
+    o.px = a.origin[0]; o.py = a.origin[1]; o.pz = a.origin[2];
+  } else {
+    o.px = a.rot[0] * x + a.rot[1] * y + a.origin[0];
+    o.py = a.rot[3] * x + a.rot[4] * y + a.origin[1];
+    o.pz = a.rot[6] * x + a.rot[7] * y + a.origin[2];
+    o.ux = a.rot[2]; o.uy = a.rot[5]; o.uz = a.rot[8];
+  }
+  const double un = frsqrt(fma(o.ux, o.ux, fma(o.uy, o.uy, o.uz * o.uz)));
+  o.ux *= un; o.uy *= un; o.uz *= un;
+  return o;
+}
+
+// Two adjacent rays per thread and trip: two independent FP64 chains (the kernel is bound by the latency of its
+// square roots / reciprocal square roots / polynomials, not by the store bandwidth) and 128-bit column stores.
 __global__ void __launch_bounds__(TPB) source_kernel(const SourceArgs a) {
   const double golden = 3.141592653589793 * (3.0 - sqrt(5.0));
   double su[3] = {0.0, 0.0, 0.0}, cnt = 0.0;
   if (a.origin_out && blockIdx.x == 0 && threadIdx.x < 3) a.origin_out[threadIdx.x * a.origin_stride] = a.origin[threadIdx.x];
   const bool fast = a.n_total < (1LL << 27);  // beyond that the reduction above is not exact: library sincos
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.count;
-       j += (long long)gridDim.x * blockDim.x) {
-    const long long idx = a.first + j * a.stride;
-    // the Vogel point that shapes the direction (kinds 0, 2) or the position (kind 1)
-    const double k = (double)(a.kind == 2 ? idx % a.per : idx);
-    const double kn = (double)(a.kind == 2 ? a.per : a.n_total);
-    const double rad = fsqrt(fdiv(k, kn)) * a.rho;
-    double s, c;
-    if (fast) vogel_sincos(golden * k, s, c);
-    else sincos(golden * k, &s, &c);
-    const double x = c * rad, y = s * rad;
-    double px, py, pz, ux, uy, uz;
-    if (a.kind == 2) {
-      const double ks = (double)(idx / a.per);
-      const double rs = fsqrt(fdiv(ks, (double)a.n_ps)) * a.ps_radius;
-      double ss, cs;
-      if (fast) vogel_sincos(golden * ks, ss, cs);
-      else sincos(golden * ks, &ss, &cs);
-      const double xs = cs * rs, ys = ss * rs;
-      const double inv = frsqrt(fma(x, x, fma(y, y, 1.0)));
-      const double vx = x * inv, vy = y * inv, vz = inv;
-      ux = a.rot[0] * vx + a.rot[1] * vy + a.rot[2] * vz;
-      uy = a.rot[3] * vx + a.rot[4] * vy + a.rot[5] * vz;
-      uz = a.rot[6] * vx + a.rot[7] * vy + a.rot[8] * vz;
-      px = a.rot[0] * xs + a.rot[1] * ys + a.origin[0];
-      py = a.rot[3] * xs + a.rot[4] * ys + a.origin[1];
-      pz = a.rot[6] * xs + a.rot[7] * ys + a.origin[2];
-    } else if (a.kind == 0) {
-      // normalise(rot (x, y, 1)): the reference normalises (x, y, 1), rotates and normalises again
-      // (ART/ModuleSource.py:23-81, Ray.vector setter); a rotation keeps the length, so one normalisation of the
-      // rotated vector is the same direction to rounding
-      ux = fma(a.rot[0], x, fma(a.rot[1], y, a.rot[2]));
-      uy = fma(a.rot[3], x, fma(a.rot[4], y, a.rot[5]));
-      uz = fma(a.rot[6], x, fma(a.rot[7], y, a.rot[8]));
-      px = a.origin[0]; py = a.origin[1]; pz = a.origin[2];
+  const long long npairs = (a.count + 1) >> 1;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npairs;
+       p += (long long)gridDim.x * blockDim.x) {
+    const long long j = p << 1;
+    const bool two = j + 1 < a.count;
+    const SourceRay r0 = source_ray(a, j, fast, golden);
+    const SourceRay r1 = source_ray(a, two ? j + 1 : j, fast, golden);
+    if (two) {
+#define ART_SRC_ST2(colp, f) *reinterpret_cast<double2*>(colp + j) = make_double2(r0.f, r1.f);
+      if (a.b.px) { ART_SRC_ST2(a.b.px, px) ART_SRC_ST2(a.b.py, py) ART_SRC_ST2(a.b.pz, pz) }
+      ART_SRC_ST2(a.b.ux, ux) ART_SRC_ST2(a.b.uy, uy) ART_SRC_ST2(a.b.uz, uz)
+#undef ART_SRC_ST2
+      if (a.b.path) *reinterpret_cast<double2*>(a.b.path + j) = make_double2(0.0, 0.0);
+      if (a.b.alive) *reinterpret_cast<uchar2*>(a.b.alive + j) = make_uchar2(1, 1);
+      su[0] += r0.ux + r1.ux; su[1] += r0.uy + r1.uy; su[2] += r0.uz + r1.uz;
+      cnt += 2.0;
     } else {
-      px = a.rot[0] * x + a.rot[1] * y + a.origin[0];
-      py = a.rot[3] * x + a.rot[4] * y + a.origin[1];
-      pz = a.rot[6] * x + a.rot[7] * y + a.origin[2];
-      ux = a.rot[2]; uy = a.rot[5]; uz = a.rot[8];
+      if (a.b.px) { a.b.px[j] = r0.px; a.b.py[j] = r0.py; a.b.pz[j] = r0.pz; }
+      a.b.ux[j] = r0.ux; a.b.uy[j] = r0.uy; a.b.uz[j] = r0.uz;
+      if (a.b.path) a.b.path[j] = 0.0;
+      if (a.b.alive) a.b.alive[j] = 1;
+      su[0] += r0.ux; su[1] += r0.uy; su[2] += r0.uz;
+      cnt += 1.0;
     }
-    const double un = frsqrt(fma(ux, ux, fma(uy, uy, uz * uz)));
-    ux *= un; uy *= un; uz *= un;
-    if (a.b.px) { a.b.px[j] = px; a.b.py[j] = py; a.b.pz[j] = pz; }
-    a.b.ux[j] = ux; a.b.uy[j] = uy; a.b.uz[j] = uz;
-    su[0] += ux; su[1] += uy; su[2] += uz;
-    cnt += 1.0;
-    if (a.b.path) a.b.path[j] = 0.0;
-    if (a.b.alive) a.b.alive[j] = 1;
   }
   if (a.partials) {  // launched with TPB threads per block in that case
     __shared__ double sRed[NWARP * PLEN_TRACE];

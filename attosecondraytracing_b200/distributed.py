@@ -124,25 +124,34 @@ class PeerExchange:
             return None
         return cls(buf, handle, rank, world)
 
-    def _call(self, kind, rows, distance, det):
+    def _call(self, kind, rows, distance, det, chain=None):
         import ctypes as C
         if not rows.is_contiguous() or rows.dtype != torch.float64:
             raise ValueError("rows must be a contiguous float64 tensor")
         nv = rows.shape[0]
-        _cabi.check(_cabi.lib().art_peer_exchange(
-            self._ptrs, self.rank, self.world, kind, nv, C.c_void_p(rows.data_ptr()), float(distance),
-            C.c_void_p(det.data_ptr()) if det is not None else None,
-            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        dp = C.c_void_p(det.data_ptr()) if det is not None else None
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if chain is not None:
+            if nv != 1:
+                raise ValueError("folding inside the exchange is for one variant")
+            _cabi.check(_cabi.lib().art_peer_exchange_fold(chain._handle, self._ptrs, self.rank, self.world, kind,
+                                                           C.c_void_p(rows.data_ptr()), float(distance), dp, st))
+        else:
+            _cabi.check(_cabi.lib().art_peer_exchange(self._ptrs, self.rank, self.world, kind, nv,
+                                                      C.c_void_p(rows.data_ptr()), float(distance), dp, st))
         return rows
 
-    def all_reduce_central(self, central, distance=0.0, det=None):
+    def all_reduce_central(self, central, distance=0.0, det=None, chain=None):
         """Sum the central rows (n_variants x 10) over the ranks in place; with `det` (n_variants x 23) also
-        place every variant's detector at `distance` (Detector.autoplace) in the same kernel."""
-        return self._call(0, central, distance, det)
+        place every variant's detector at `distance` (Detector.autoplace) in the same kernel.
+        chain: the DeviceChain whose last call was trace(..., fold=False): its per-block rows are folded into
+        `central` inside the exchange kernel (art_peer_exchange_fold) -- no fold launch of its own."""
+        return self._call(0, central, distance, det, chain)
 
-    def all_reduce_moments(self, moments):
-        """Merge the moments rows (n_variants x 24) over the ranks in place (sums / minima / maxima)."""
-        return self._call(1, moments, 0.0, None)
+    def all_reduce_moments(self, moments, chain=None):
+        """Merge the moments rows (n_variants x 24) over the ranks in place (sums / minima / maxima).
+        chain: the DeviceChain whose last call was moments(..., fold=False)."""
+        return self._call(1, moments, 0.0, None, chain)
 
     def status(self):
         """0, or the epoch of an exchange in which a peer did not arrive (synchronises the stream)."""

@@ -87,15 +87,17 @@ class DeviceChain:
         return self._new_out(bundle, n_variants, want_incidence)
 
     def trace(self, bundle, ignore_defects=True, history=False, want_incidence=True, want_central=True,
-              variant_first=0, n_variants=None, store_final=True, out=None, central=None):
+              variant_first=0, n_variants=None, store_final=True, out=None, central=None, fold=True):
         """Trace `bundle` through the chain.  Returns (bundles, central):
         bundles = list of RayBundle after each element (history=True) or [final bundle];
         for several variants the rows of variant v are [v*n, (v+1)*n).  central = tensor
-        (n_variants, 10) of the central-ray sums, or None."""
+        (n_variants, 10) of the central-ray sums, or None.
+        fold=False (one variant, multi-GPU): the central sums stay as per-block rows in the chain's scratch and
+        `central` is NOT written -- PeerExchange.all_reduce_central(..., chain=self) folds them inside the exchange."""
         self._check_bundle(bundle)
         nv = self.n_variants - variant_first if n_variants is None else n_variants
         flags = ((_cabi.TRACE_IGNORE_DEFECTS if ignore_defects else 0) | (0 if want_incidence else _cabi.TRACE_NO_INCIDENCE)
-                 | bundle.trace_flags())
+                 | bundle.trace_flags() | (0 if fold else _cabi.TRACE_NO_FOLD))
         outs = []
         hist_arr = None
         final_view = None
@@ -150,12 +152,16 @@ class DeviceChain:
             _cabi.check(_cabi.lib().art_detector_autoplace(_ptr(central), float(distance), nv, _ptr(det), _stream()))
         return det
 
-    def moments(self, bundle, det, intensity=None, want_points=False, out=None):
-        """Detector moments of a stored bundle (n_variants x n rows).  Returns (moments, x, y, l)."""
+    def moments(self, bundle, det, intensity=None, want_points=False, out=None, fold=True):
+        """Detector moments of a stored bundle (n_variants x n rows).  Returns (moments, x, y, l).
+        fold=False (one variant, multi-GPU): the rows stay unfolded in the chain's scratch (moments is None) for
+        PeerExchange.all_reduce_moments(..., chain=self)."""
         self._check_bundle(bundle)
         bundle = bundle.materialize()  # the detector kernel reads per-ray points
         nv = det.shape[0]
-        mom = out if out is not None else torch.empty((nv, _cabi.MOMENTS_LEN), dtype=torch.float64, device=self.device)
+        mom = None
+        if fold:
+            mom = out if out is not None else torch.empty((nv, _cabi.MOMENTS_LEN), dtype=torch.float64, device=self.device)
         x = y = l = None
         if want_points:
             x = torch.full((bundle.n,), float("nan"), dtype=torch.float64, device=self.device)

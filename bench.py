@@ -392,16 +392,18 @@ def measure_bundle(ctx, name, steps, warmup, rays=0, main=False, histograms=Fals
     hist_b = torch.empty((_cabi.hist_len(64, 64, 128),), dtype=torch.int64, device=dev) if histograms else None
 
     def step():
-        chain.trace(src, ignore_defects=ign, history=False, want_incidence=True, out=out, central=central_b)
         if peer is not None:
-            peer.all_reduce_central(central_b, distance, det_b)   # sum over ranks + autoplace, one kernel
+            # the per-block rows of the trace / detector kernel are folded INSIDE the exchange kernels:
+            # four launches per step (trace, exchange + autoplace, detector, exchange)
+            chain.trace(src, ignore_defects=ign, history=False, want_incidence=True, out=out, central=central_b, fold=False)
+            peer.all_reduce_central(central_b, distance, det_b, chain=chain)
+            chain.moments(out, det_b, intensity=inten, fold=False)
+            peer.all_reduce_moments(mom_b, chain=chain)
         else:
+            chain.trace(src, ignore_defects=ign, history=False, want_incidence=True, out=out, central=central_b)
             ad.all_reduce_central(central_b)
             chain.autoplace(central_b, distance, det=det_b)
-        chain.moments(out, det_b, intensity=inten, out=mom_b)
-        if peer is not None:
-            peer.all_reduce_moments(mom_b)
-        else:
+            chain.moments(out, det_b, intensity=inten, out=mom_b)
             ad.all_reduce_moments(mom_b, gather_buffer=gather_b)
         if hist_b is not None:  # SpotDiagram / DelayGraph bins over the merged extents, exact int64 SUM
             chain.histogram(out, det_b, mom_b, bins=(64, 64), delay_bins=128, intensity=inten, out=hist_b)

@@ -182,6 +182,11 @@ enum {
                                        all rays (a point source, ART/ModuleSource.py:54: every ray starts
                                        at S): 24 B/ray less to move and to read                         */
 
+#define ART_TRACE_NO_FOLD 8u        /* art_trace: leave the central sums as per-block partial rows in the chain's
+                                       scratch (central_out is not written); art_peer_exchange_fold reduces
+                                       them inside the exchange kernel -- one launch fewer per step on a
+                                       multi-GPU run.  One variant only.                                    */
+
 typedef struct ArtChain ArtChain;
 
 int32_t art_version(void);
@@ -253,7 +258,8 @@ int32_t art_detector_make(const double centre[3], const double normal[3], const 
  *   det      device, n_variants detectors.
  *   x_out, y_out, l_out  NULL or device columns (n_variants x n): in-plane coordinates relative
  *            to Detector.centre and total optical path length L (mm) of each alive ray.
- *   moments_out  device, n_variants x ART_MOMENTS_LEN.
+ *   moments_out  device, n_variants x ART_MOMENTS_LEN; NULL (with a chain, one variant): the per-block rows are
+ *            left unfolded in the chain's scratch for art_peer_exchange_fold.
  *   chain    lends its reduction scratch (a chain serves one stream at a time); NULL: a
  *            per-device scratch inside the library is used (allocated on first use / growth).
  */
@@ -326,6 +332,15 @@ int32_t art_moments_merge(const double* rows, int32_t n_ranks, int32_t n_variant
   ((int64_t)8 * ((int64_t)2 * (world) * ART_PEER_MAX_VARIANTS * ART_MOMENTS_LEN + (world) + 2 + ART_PEER_STATS))
 int32_t art_peer_exchange(const uint64_t* peer_bufs, int32_t rank, int32_t world, int32_t kind, int32_t n_variants,
                           double* rows, double distance, ArtDetector* det_out, void* stream);
+/*
+ * art_peer_exchange for ONE variant whose rows have not been folded yet: `chain` ran art_trace with
+ * ART_TRACE_NO_FOLD (kind 0) or art_detector_moments with moments_out == NULL (kind 1) as its last launch on
+ * this stream; the exchange kernel first folds the chain's per-block partial rows into `rows` (the arithmetic and
+ * order of the stand-alone fold) and then proceeds as art_peer_exchange.  Saves the fold launch in front of
+ * each of the two exchanges of a multi-GPU step.
+ */
+int32_t art_peer_exchange_fold(ArtChain* chain, const uint64_t* peer_bufs, int32_t rank, int32_t world, int32_t kind,
+                               double* rows, double distance, ArtDetector* det_out, void* stream);
 /* Synchronises the stream and returns the status word of this rank's buffer in *status_out. */
 int32_t art_peer_status(const uint64_t* peer_bufs, int32_t rank, int32_t world, uint64_t* status_out, void* stream);
 /* Synchronises the stream and copies the ART_PEER_STATS counters of this rank's buffer to stats_out: number of

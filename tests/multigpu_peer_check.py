@@ -93,6 +93,29 @@ def main():
     rows = [torch.empty(_cabi.MOMENTS_LEN, dtype=torch.float64, device=dev) for _ in range(world)]
     dist.all_gather(rows, torch.from_numpy(mom).to(dev))
     assert all(torch.equal(r, rows[0]) for r in rows), "ranks disagree on the whole-bundle moments"
+    # the exchange that folds the per-block rows itself == fold launch + plain exchange (another, equally fixed,
+    # summation order: equal to rounding; extents exactly)
+    from attosecondraytracing_b200.ModuleOpticalRay import RayBundle as _RB
+    dsrc = _RB.from_numpy(gd["src_P"][sel], gd["src_U"][sel], intensity=gd["src_I"][sel], device=dev)
+    dist_ = gd.spec["detector_distance"]
+    outs_a, cen_a = chain.trace(dsrc, ignore_defects=gd.ignore_defects, history=False)
+    det_a = torch.empty((1, _cabi.DETECTOR_DOUBLES), dtype=torch.float64, device=dev)
+    peer.all_reduce_central(cen_a, dist_, det_a)
+    mom_a, _, _, _ = chain.moments(outs_a[0], det_a, intensity=dsrc.col("intensity"))
+    peer.all_reduce_moments(mom_a)
+    cen_b = torch.empty_like(cen_a)
+    det_b = torch.empty_like(det_a)
+    mom_b = torch.empty_like(mom_a)
+    outs_b, _ = chain.trace(dsrc, ignore_defects=gd.ignore_defects, history=False, central=cen_b, fold=False)
+    peer.all_reduce_central(cen_b, dist_, det_b, chain=chain)
+    chain.moments(outs_b[0], det_b, intensity=dsrc.col("intensity"), fold=False)
+    peer.all_reduce_moments(mom_b, chain=chain)
+    torch.cuda.synchronize()
+    assert torch.allclose(cen_a, cen_b, rtol=1e-13, atol=0) and torch.allclose(det_a, det_b, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(mom_a[:, :14], mom_b[:, :14], rtol=1e-11, atol=1e-12) and torch.equal(mom_a[:, 14:21], mom_b[:, 14:21])
+    rows_b = [torch.empty_like(mom_b) for _ in range(world)]
+    dist.all_gather(rows_b, mom_b)
+    assert all(torch.equal(r, rows_b[0]) for r in rows_b), "ranks disagree after the folding exchange"
     # the same from the source DESCRIPTION: every rank generates its own round-robin share on the device, the axis /
     # extent of the intensity profile are combined over the ranks inside the call (art_run_source_host)
     import attosecondraytracing_b200.ModuleSource as msrc
