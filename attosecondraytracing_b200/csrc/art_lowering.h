@@ -148,7 +148,7 @@ inline std::string lower_gridmap(const ArtGridMapDesc& g, MapDev& m) {
 // Zernike table of one defect in the layout zernike_eval (art_device.cuh) walks:
 //   [0] radius, [1] max order N (the reference: max n over the keys, at least 2,
 //   ART/ModuleDefects.py:151-154 + ART/recursive_zernike_generator.py:37-38), then for l = 0..N and
-//   k = 0..(N-l)/2 the record {alpha, beta, gamma, c_cos, c_sin}:
+//   k = 0..(N-l)/2 the record {alpha, beta, gamma, c_cos, c_sin, pad}:
 //   Q_k^l(s) = (alpha s + beta) Q_{k-1}^l(s) - gamma Q_{k-2}^l(s), Q_0 = 1, where
 //   rho^l Q_k^l(rho^2) is the radial Zernike polynomial R_{l+2k}^l(rho) = (-1)^k rho^l P_k^{(l,0)}(1 - 2 rho^2);
 //   the three-term recurrence is Jacobi's.  The reference key (n, m) is the polynomial
@@ -192,6 +192,7 @@ inline std::string build_zernike_table(const ArtZernikeDesc& z, std::vector<doub
       out.push_back((double)gamma);
       out.push_back(get(n, (n + l) / 2));
       out.push_back(l > 0 ? get(n, (n - l) / 2) : 0.0);
+      out.push_back(0.0);  // pad: six doubles per record = three aligned 16-byte loads (zernike_record)
     }
   }
   return std::string();

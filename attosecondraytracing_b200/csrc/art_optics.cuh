@@ -380,11 +380,34 @@ ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>
 // Q_k^l(s) = R_{l+2k}^l(rho)/rho^l = (-1)^k P_k^{(l,0)}(1-2s)  (Jacobi), advanced in k by a
 // three-term recurrence -> O(1) registers per ray for any order.  Table (host-built, smem):
 //   zt[0] = radius R (= Support._CircumCirc()), zt[1] = max order N, then for l = 0..N,
-//   k = 0..(N-l)/2: {alpha, beta, gamma, c_cos, c_sin} with
+//   k = 0..(N-l)/2: {alpha, beta, gamma, c_cos, c_sin, pad} with
 //   Q_k = (alpha s + beta) Q_{k-1} - gamma Q_{k-2};  c_cos / c_sin = coefficients of the reference
 //   keys (n, (n+l)/2) / (n, (n-l)/2), n = l + 2k.
 // Returns value and Cartesian gradient (already divided by R where the reference does).
 // ---------------------------------------------------------------------------------------------
+// One table record per (l, k): {alpha, beta, gamma, c_cos, c_sin, pad} -- six doubles, so that every record is
+// three aligned 16-byte loads from the shared-memory table.
+struct ZRec {
+  double al, be, ga, cc, cs;
+};
+ART_HD ZRec zernike_record(const double* __restrict__ rec) {
+#ifdef __CUDA_ARCH__
+  const double2* q = reinterpret_cast<const double2*>(rec);
+  const double2 a = q[0], b = q[1], c = q[2];
+  return {a.x, a.y, b.x, b.y, c.x};
+#else
+  return {rec[0], rec[1], rec[2], rec[3], rec[4]};
+#endif
+}
+constexpr int ZREC = 6;  // doubles per record
+// Unrolling of the radial recurrence.  Measured on cfg4 (10^7 rays, order 20, profiles/r02_summary.md): 1: 0.445,
+// 2: 0.422, 4: 0.418 ms.  One flat loop over all records with a block-start mark per record (no nested loops) was
+// tried as well and is slower (0.512 ms: a uniform but unpredictable branch per record, and spills).
+#ifndef ART_ZUNROLL
+#define ART_ZUNROLL 4
+#endif
+constexpr int ZUNROLL = ART_ZUNROLL;
+
 template <bool WANT_VALUE, bool WANT_GRAD, class T>
 ART_HD void zernike_eval(const double* __restrict__ zt, T X, T Y, T& val, T& gx, T& gy) {
   const double Rz = zt[0];
@@ -398,24 +421,26 @@ ART_HD void zernike_eval(const double* __restrict__ zt, T X, T Y, T& val, T& gx,
   for (int l = 0; l <= N; ++l) {
     const int K = (N - l) >> 1;
     T Q = splat<T>(1.0), Qp = splat<T>(0.0), dQ = splat<T>(0.0), dQp = splat<T>(0.0);
-    T A = splat<T>(rec[3]), B = splat<T>(rec[4]), dA = splat<T>(0.0), dB = splat<T>(0.0);
-    rec += 5;
+    const ZRec r0 = zernike_record(rec);
+    T A = splat<T>(r0.cc), B = splat<T>(r0.cs), dA = splat<T>(0.0), dB = splat<T>(0.0);
+    rec += ZREC;
+#pragma unroll(ZUNROLL)
     for (int k = 1; k <= K; ++k) {
-      const double al = rec[0], be = rec[1], ga = rec[2], cc = rec[3], cs = rec[4];
-      rec += 5;
-      const T lin = mfma(al, s, be);
-      const T Qn = mfma(lin, Q, -ga * Qp);
+      const ZRec z = zernike_record(rec);
+      rec += ZREC;
+      const T lin = mfma(z.al, s, z.be);
+      const T Qn = mfma(lin, Q, -z.ga * Qp);
       if (WANT_GRAD) {
-        const T dQn = mfma(al, Q, mfma(lin, dQ, -ga * dQp));
+        const T dQn = mfma(z.al, Q, mfma(lin, dQ, -z.ga * dQp));
         dQp = dQ;
         dQ = dQn;
-        dA = mfma(cc, dQn, dA);
-        dB = mfma(cs, dQn, dB);
+        dA = mfma(z.cc, dQn, dA);
+        dB = mfma(z.cs, dQn, dB);
       }
       Qp = Q;
       Q = Qn;
-      A = mfma(cc, Qn, A);
-      B = mfma(cs, Qn, B);
+      A = mfma(z.cc, Qn, A);
+      B = mfma(z.cs, Qn, B);
     }
     if (WANT_VALUE) v = mfma(A, Cl, mfma(B, Sl, v));
     if (WANT_GRAD) {

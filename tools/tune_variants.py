@@ -23,7 +23,7 @@ def worker():
     from attosecondraytracing_b200 import engine
     import attosecondraytracing_b200.ModuleSource as msrc
     res = {}
-    for wl, nrays in (("cfg2", 10_000_000), ("cfg3", 12_500_000), ("cfg5", 4_000_000), ("cfg4", 2_000_000)):
+    for wl, nrays in (("cfg2", 10_000_000), ("cfg3", 12_500_000), ("cfg5", 4_000_000), ("cfg4", 10_000_000)):
         w = bench.load_workload(wl)
         oes = bench.build_chain_elements(w)
         sp = bench.source_properties(w, nrays)
