@@ -410,7 +410,7 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
   a.wstate = wstate;
   a.wcoef = wcoef;
   if (wstate && !in->intensity) return fail(ART_E_INVALID, "internal: computed weights need an intensity column");
-  const size_t sm = c->smem_bytes + (det ? (size_t)smem_moments_bytes(bt) : (size_t)stage_bytes(bt));
+  const size_t sm = c->smem_bytes + (det ? (size_t)smem_moments_bytes(bt) : (size_t)stage_bytes(bt, uniform_point));
   // Zernike chains run the general kernel; defect-free chains one specialised for their surface class
 #define ART_TRACE_LAUNCH2(INC, DET, UPT)                                                                      \
   do {                                                                                                       \

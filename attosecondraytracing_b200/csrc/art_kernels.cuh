@@ -254,7 +254,11 @@ __device__ __forceinline__ void moments_finish(ACC& m) {
 // the source columns is hidden behind the FP64 work without costing registers.  Slots are private
 // to the issuing thread: cp.async.wait_group is the only synchronisation needed.
 constexpr int STAGE_COLS = 8;  // px py pz ux uy uz intensity path
-constexpr int stage_bytes(int bt) { return 2 * STAGE_COLS * bt * 16; }
+// slots of the trace kernel's two input stages: directions, intensity, path -- and the three point columns only
+// when the bundle has them (a point source shares one origin: five slots instead of eight, which is what lets two
+// 320-thread blocks of a quadric chain stay resident per SM)
+__host__ __device__ constexpr int trace_stage_cols(bool upt) { return upt ? 5 : 8; }
+__host__ __device__ constexpr int stage_bytes(int bt, bool upt = false) { return 2 * trace_stage_cols(upt) * bt * 16; }
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
@@ -438,15 +442,16 @@ __global__ void __launch_bounds__(trace_block_threads(HAS_DEF, SURFS), HAS_DEF ?
   if constexpr (WITH_DET) moments_init(m);
 
   double2* const sStage = reinterpret_cast<double2*>(smem_raw + a.stage_smem_offset) + threadIdx.x;
+  constexpr int NSC = trace_stage_cols(UPT);  // slots: 0-2 direction, 3 intensity, 4 path, 5-7 point
   auto stage_issue = [&](int stage, long long it) {
     const long long ii = it * 2;
-    double2* b = sStage + stage * STAGE_COLS * BT;
+    double2* b = sStage + stage * NSC * BT;
+    cp_async16(b + 0 * BT, a.in.ux + ii); cp_async16(b + 1 * BT, a.in.uy + ii); cp_async16(b + 2 * BT, a.in.uz + ii);
+    if (load_w) cp_async16(b + 3 * BT, a.in.inten + ii);
+    if (a.in.path) cp_async16(b + 4 * BT, a.in.path + ii);
     if (!UPT) {
-      cp_async16(b + 0 * BT, a.in.px + ii); cp_async16(b + 1 * BT, a.in.py + ii); cp_async16(b + 2 * BT, a.in.pz + ii);
+      cp_async16(b + 5 * BT, a.in.px + ii); cp_async16(b + 6 * BT, a.in.py + ii); cp_async16(b + 7 * BT, a.in.pz + ii);
     }
-    cp_async16(b + 3 * BT, a.in.ux + ii); cp_async16(b + 4 * BT, a.in.uy + ii); cp_async16(b + 5 * BT, a.in.uz + ii);
-    if (load_w) cp_async16(b + 6 * BT, a.in.inten + ii);
-    if (a.in.path) cp_async16(b + 7 * BT, a.in.path + ii);
     cp_async_commit();
   };
   const long long stride = (long long)gridDim.x * BT;
@@ -465,20 +470,20 @@ __global__ void __launch_bounds__(trace_block_threads(HAS_DEF, SURFS), HAS_DEF ?
     if (staged) {
       if (staged_next) cp_async_wait<1>();
       else cp_async_wait<0>();
-      const double2* b = sStage + stage * STAGE_COLS * BT;
+      const double2* b = sStage + stage * NSC * BT;
       double2 v;
       if (UPT) {  // point source: one origin for all rays (re-read per pair: an L1 hit, no live registers)
         r[0].px = r[N - 1].px = a.in.px[0]; r[0].py = r[N - 1].py = a.in.py[0]; r[0].pz = r[N - 1].pz = a.in.pz[0];
       } else {
-        v = b[0 * BT]; r[0].px = v.x; r[N - 1].px = v.y;
-        v = b[1 * BT]; r[0].py = v.x; r[N - 1].py = v.y;
-        v = b[2 * BT]; r[0].pz = v.x; r[N - 1].pz = v.y;
+        v = b[5 * BT]; r[0].px = v.x; r[N - 1].px = v.y;
+        v = b[6 * BT]; r[0].py = v.x; r[N - 1].py = v.y;
+        v = b[7 * BT]; r[0].pz = v.x; r[N - 1].pz = v.y;
       }
-      v = b[3 * BT]; r[0].ux = v.x; r[N - 1].ux = v.y;
-      v = b[4 * BT]; r[0].uy = v.x; r[N - 1].uy = v.y;
-      v = b[5 * BT]; r[0].uz = v.x; r[N - 1].uz = v.y;
-      if (load_w) { v = b[6 * BT]; w[0] = v.x; w[N - 1] = v.y; } else { w[0] = w[N - 1] = 1.0; }
-      if (a.in.path) { v = b[7 * BT]; r[0].path = v.x; r[N - 1].path = v.y; } else { r[0].path = r[N - 1].path = 0.0; }
+      v = b[0 * BT]; r[0].ux = v.x; r[N - 1].ux = v.y;
+      v = b[1 * BT]; r[0].uy = v.x; r[N - 1].uy = v.y;
+      v = b[2 * BT]; r[0].uz = v.x; r[N - 1].uz = v.y;
+      if (load_w) { v = b[3 * BT]; w[0] = v.x; w[N - 1] = v.y; } else { w[0] = w[N - 1] = 1.0; }
+      if (a.in.path) { v = b[4 * BT]; r[0].path = v.x; r[N - 1].path = v.y; } else { r[0].path = r[N - 1].path = 0.0; }
     } else {
       double t[N];
 #define ART_LD(colp, field)                      \

@@ -35,6 +35,27 @@ def shard_strided(n, rank, world):
     return rank, max(0, (n - rank + world - 1) // world), world
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin the calling process to the CPUs that are local to GPU `device_index` (NVML's ideal CPU affinity), so that
+    pinned host staging allocated afterwards is first-touched on the GPU's own NUMA node: on a two-socket 8-GPU box
+    eight ranks uploading ray columns at once otherwise share one socket's memory controllers.  Returns the number
+    of CPUs bound to, or 0 when NVML is unavailable (nothing changes then)."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        cpus = [c for c in cpus if c < n_cpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def is_distributed(group=None):
     return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 

@@ -531,6 +531,8 @@ def measure_bundle(ctx, name, steps, warmup, rays=0, main=False, histograms=Fals
             "d2h_bytes_per_step": 8 * (_cabi.MOMENTS_LEN + _cabi.CENTRAL_LEN + _cabi.DETECTOR_DOUBLES),
             "steps": hc_steps, "ms_per_step": 1e3 * t_hc / hc_steps,
             "h2d_gbs_per_gpu": h2d * hc_steps / t_hc / 1e9,
+            "numa": (f"each rank bound to the {ctx.numa_cpus} CPUs local to its GPU before pinning its staging"
+                     if ctx.numa_cpus else "no CPU binding"),
             "api": "art_run_host" + ("" if peer is None else "_sharded") + " (ctypes): pinned host ray columns in "
                    "(8 PCIe chunks overlapped with the trace), moments/central/detector out"}
         del host
@@ -698,9 +700,12 @@ def run_b200(args):
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host staging (the pinned ray columns of e2e_host_columns) should live on the GPU's own NUMA node
+    numa_cpus = ad.bind_to_gpu_numa(local) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = Ctx()
+    ctx.numa_cpus = numa_cpus
     ctx.args, ctx.rank, ctx.world, ctx.local, ctx.dev = args, rank, world, local, dev
     ctx.lib = _cabi.lib()
     # multi-GPU: the two exchanges run inside one kernel each over peer memory (NVLink); NCCL when

@@ -54,6 +54,19 @@ def worker():
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         res[f"{wl}_det_ms"] = round(float(np.median(ts)), 4)
+        # the statistics-only alternative: no stored bundle, two traces (central pass + fused detector pass)
+        for _ in range(2):
+            chain.sweep(src, w["scene_spec"]["detector_distance"])
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(8):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            chain.sweep(src, w["scene_spec"]["detector_distance"])
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        res[f"{wl}_two_trace_stats_ms"] = round(float(np.median(ts)), 4)
         if wl == "cfg3":  # descriptor-driven end-to-end call (K0 + trace + detector), wall clock
             import time
             desc = msrc.source_descriptor(sp)
