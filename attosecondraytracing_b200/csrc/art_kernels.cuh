@@ -987,10 +987,14 @@ __global__ void __launch_bounds__(DB_THREADS, ART_DB_MINB) detector_bulk_kernel(
   } else {
     // ---- consumer warps: thread c owns DB_PAIRS pairs of adjacent rays of every tile ---------------------
     const int c = threadIdx.x - 32;
+    bool lost = false;
     int stage = 0;
     unsigned phase = 0;
     for (;;) {
-      if (!mbar_wait(smem_addr(&sFull[stage]), phase)) break;
+      if (!mbar_wait(smem_addr(&sFull[stage]), phase)) {
+        lost = true;  // a lost arrival: poison the row below rather than return plausible partial sums
+        break;
+      }
       const long long tile = sTile[stage];
       if (tile < 0) break;
       const unsigned char* st = smem_raw + (size_t)stage * DB_STAGE_BYTES;
@@ -1036,6 +1040,7 @@ __global__ void __launch_bounds__(DB_THREADS, ART_DB_MINB) detector_bulk_kernel(
         detector_pair(a, sDet, at, r, w, al, m);
       }
     }
+    if (lost) m[ART_M_N] = CUDART_NAN;
   }
   moments_finish(m);
   block_reduce_row<PLEN_DET, DB_THREADS>(m, [](int j) { return moment_op(j); }, sRed,
@@ -1611,18 +1616,24 @@ struct SourceArgs {
 // pi/2 = C1 + C2 + C3 with 25-bit C1, C2 (n C1 and n C2 are exact for the quadrant count n < 2^28) followed by the
 // fdlibm kernel polynomials on [-pi/4, pi/4].  Largest deviation from libm over k < 4e8: 2.2e-16 (1 ulp of 1),
 // checked on the host with the same arithmetic.
+// (the constants are constant-bank operands of the FMAs: as 64-bit immediates each use cost two UMOVs, 32 of the
+// generator's 180 instructions per ray)
+__constant__ double c_vogel[16] = {
+    0.63661977236758138,      // 2 / pi
+    0x1.921fb50000000p+0, 0x1.110b460000000p-26, 0x1.1a62633145c07p-54,  // pi/2 in three pieces
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,   // sin: S6 .. S1
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,  // cos: C6 .. C1
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
 __device__ __forceinline__ void vogel_sincos(double x, double& sn, double& cs) {
-  const double n = rint(x * 0.63661977236758138);
-  double r = fma(-n, 0x1.921fb50000000p+0, x);
-  r = fma(-n, 0x1.110b460000000p-26, r);
-  r = fma(-n, 0x1.1a62633145c07p-54, r);
+  const double* k = c_vogel;
+  const double n = rint(x * k[0]);
+  double r = fma(-n, k[1], x);
+  r = fma(-n, k[2], r);
+  r = fma(-n, k[3], r);
   const double z = r * r;
-  const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08),
-                                             2.75573137070700676789e-06), -1.98412698298579493134e-04),
-                               8.33333333332248946124e-03), -1.66666666666666324348e-01);
-  const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09),
-                                             -2.75573143513906633035e-07), 2.48015872894767294178e-05),
-                               -1.38888888888741095749e-03), 4.16666666666666019037e-02);
+  const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, k[4], k[5]), k[6]), k[7]), k[8]), k[9]);
+  const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, k[10], k[11]), k[12]), k[13]), k[14]), k[15]);
   const double s0 = fma(r * z, ps, r);
   const double c0 = fma(z * z, pc, fma(-0.5, z, 1.0));
   const long long q = (long long)n;
