@@ -134,10 +134,16 @@ ART_HD void unpack_rays(const RayT<D2>& r, Ray& p, Ray& q) {
 //   RECT_RECT_HOLE   ap = {|X/2|, |Y/2|, |hX/2|, |hY/2|, cx, cy}
 // NaN coordinates compare false, as in numpy.
 // ---------------------------------------------------------------------------------------------
-template <class T>
+#ifndef ART_SKIP_SOFF
+#define ART_SKIP_SOFF 1
+#endif
+// OFFSET = false: the caller knows soff = 0 (every surface but the parabola and the ellipsoid, art_lowering.h)
+template <bool OFFSET = true, class T>
 ART_HD typename MaskOf<T>::type in_support(const ElemDev& E, T x, T y) {
-  x = x - E.soff[0];
-  y = y - E.soff[1];
+  if (OFFSET || !ART_SKIP_SOFF) {
+    x = x - E.soff[0];
+    y = y - E.soff[1];
+  }
   switch (E.support) {
     case ART_SUPP_ROUND:
       return mfma(x, x, y * y) <= E.ap[0];
@@ -242,6 +248,21 @@ ART_HD TorEval<T> tor_eval(const RayT<T>& r, T t, double R, double r2) {
 // PRE leading steps are taken without the convergence test (the start is known to need them: from
 // the tangent plane a ray needs three evaluations); only their slope signs are accumulated.  They are
 // taken by every lane alike, so a ray's result still never depends on its partner.
+#ifndef ART_PEEL_NEWTON
+#define ART_PEEL_NEWTON 1   // first checked step outside the loop: the common case converges on it
+#endif
+template <int DIR, class T>
+ART_HD void tor_newton_step(const TorEval<T>& e, T& t, T& result, typename MaskOf<T>::type& todo, double scale) {
+  typedef typename MaskOf<T>::type M;
+  const T slope = DIR > 0 ? e.dF : -e.dF;
+  const M good = slope > 0.0;
+  const T dt = e.F * fast_rcp(e.dF);
+  const T tn = t - dt;
+  const M conv = mand(good, dt * dt <= 2e-16 * (mabs(tn) + scale) * slope);
+  result = sel(mand(todo, conv), tn, result);
+  todo = mand(todo, mand(good, mnot(conv)));
+  t = sel(todo, tn, t);
+}
 template <int DIR, int PRE, class T>
 ART_HD T tor_newton(const RayT<T>& r, T t, TorEval<T> e, double R, double r2, double scale,
                     typename MaskOf<T>::type active) {
@@ -254,17 +275,18 @@ ART_HD T tor_newton(const RayT<T>& r, T t, TorEval<T> e, double R, double r2, do
     t = t - e.F * fast_rcp(e.dF);
     e = tor_eval(r, t, R, r2);
   }
+#if ART_PEEL_NEWTON
+  tor_newton_step<DIR>(e, t, result, todo, scale);
+  for (int it = 1; it < 64 && any(todo); ++it) {
+    e = tor_eval(r, t, R, r2);
+    tor_newton_step<DIR>(e, t, result, todo, scale);
+  }
+#else
   for (int it = 0; it < 64 && any(todo); ++it) {
-    const T slope = DIR > 0 ? e.dF : -e.dF;
-    const M good = slope > 0.0;
-    const T dt = e.F * fast_rcp(e.dF);
-    const T tn = t - dt;
-    const M conv = mand(good, dt * dt <= 2e-16 * (mabs(tn) + scale) * slope);
-    result = sel(mand(todo, conv), tn, result);
-    todo = mand(todo, mand(good, mnot(conv)));
-    t = sel(todo, tn, t);
+    tor_newton_step<DIR>(e, t, result, todo, scale);
     if (any(todo)) e = tor_eval(r, t, R, r2);
   }
+#endif
   return result;
 }
 
@@ -276,6 +298,12 @@ ART_HD T tor_newton(const RayT<T>& r, T t, TorEval<T> e, double R, double r2, do
 #endif
 #ifndef ART_QUARTIC_PRE
 #define ART_QUARTIC_PRE 1
+#endif
+#ifndef ART_GRADIENT_REFLECT
+#define ART_GRADIENT_REFLECT 1
+#endif
+#ifndef ART_T0_RCP
+#define ART_T0_RCP 1
 #endif
 #ifndef ART_QUARTIC_STEPS
 #define ART_QUARTIC_STEPS 2   // leading unchecked Newton steps taken on the quartic form
@@ -303,7 +331,11 @@ ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>
   typedef typename MaskOf<T>::type M;
   const double R = E.sp[0], rr = E.sp[1], r2 = E.sp[2];
   // start for the right root: the tangent plane z = -(R+r) lies outside the solid
+#if ART_T0_RCP
+  T t0 = (-(R + rr) - r.pz) * fast_rcp(r.uz);  // a START value: 2^-46 is plenty (uz = 0 -> NaN -> the fallback start)
+#else
   T t0 = fdiv(-(R + rr) - r.pz, r.uz);
+#endif
 #if ART_QUARTIC_PRE && ART_NEWTON_PRE == 2
   TorEval<T> e0 = tor_eval_quartic(r, t0, E.sp[3], E.sp[4]);
 #else
@@ -340,7 +372,7 @@ ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>
   M cb = tb > 1e-12;
   {
     const T x = mfma(tb, r.ux, r.px), y = mfma(tb, r.uy, r.py), z = mfma(tb, r.uz, r.pz);
-    cb = mand(mand(cb, z < -R), in_support(E, x, y));
+    cb = mand(mand(cb, z < -R), in_support<false>(E, x, y));
   }
   // A second, nearer root exists only when the origin lies OUTSIDE the solid (F(0) > 0).  Sign of F(0)
   // without the square root: with A = x^2 + y^2 + z^2 + R^2 - r^2 the origin is inside iff y^2 <= r^2 and
@@ -366,7 +398,7 @@ ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>
   M ca = mand(need, ta > 1e-12);
   {
     const T x = mfma(ta, r.ux, r.px), y = mfma(ta, r.uy, r.py), z = mfma(ta, r.uz, r.pz);
-    ca = mand(mand(ca, z < -R), in_support(E, x, y));
+    ca = mand(mand(ca, z < -R), in_support<false>(E, x, y));
   }
   // one candidate -> it, two -> the nearer (ta <= tb)
   const T t = sel(ca, ta, sel(cb, tb, ART_NAN));
@@ -489,11 +521,11 @@ ART_HD void gridmap_eval(const MapDev& M, D2 X, D2 Y, D2& a, D2& b) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// surface normal, `get_normal` of each mirror class (unit vector)
+// surface normal, `get_normal` of each mirror class: surface_gradient gives its direction (any length),
+// surface_normal the unit vector
 // ---------------------------------------------------------------------------------------------
 template <class T>
-ART_HD void surface_normal(const ElemDev& E, T x, T y, T z, T& nx, T& ny, T& nz) {
-  T gx, gy, gz;
+ART_HD void surface_gradient(const ElemDev& E, T x, T y, T z, T& gx, T& gy, T& gz) {
   switch (E.surface) {
     case ART_SURF_SPHERICAL:  // ART/ModuleMirror.py:180-183
       gx = -x; gy = -y; gz = -z;
@@ -515,8 +547,17 @@ ART_HD void surface_normal(const ElemDev& E, T x, T y, T z, T& nx, T& ny, T& nz)
       gx = splat<T>(0.0); gy = -y; gz = -z;
       break;
     default:  // plane, mask: :84-87
-      nx = splat<T>(0.0); ny = splat<T>(0.0); nz = splat<T>(1.0);
-      return;
+      gx = splat<T>(0.0); gy = splat<T>(0.0); gz = splat<T>(1.0);
+      break;
+  }
+}
+template <class T>
+ART_HD void surface_normal(const ElemDev& E, T x, T y, T z, T& nx, T& ny, T& nz) {
+  T gx, gy, gz;
+  surface_gradient(E, x, y, z, gx, gy, gz);
+  if (E.surface == ART_SURF_PLANE || E.surface == ART_SURF_MASK) {
+    nx = gx; ny = gy; nz = gz;
+    return;
   }
   const T inv = frsqrt(mfma(gx, gx, mfma(gy, gy, gz * gz)));
   nx = gx * inv; ny = gy * inv; nz = gz * inv;
@@ -625,7 +666,7 @@ ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict
     // ART/ModuleMask.py:51-61: passes iff t > 0 and NOT on the support
     t = fdiv(-e.pz, e.uz);
     const T x = mfma(t, e.ux, e.px), y = mfma(t, e.uy, e.py);
-    M ok = in_support(E, x, y);
+    M ok = in_support<false>(E, x, y);
     if (surf == ART_SURF_MASK) ok = mnot(ok);
     t = sel(mand(t > 0.0, ok), t, ART_NAN);
   } else if (SURFS != SURFS_QUADRIC && surf == ART_SURF_TOROIDAL) {
@@ -671,57 +712,71 @@ ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict
     // _TransmitMaskRay, ART/ModuleMask.py:93-108: direction unchanged (r.u stays), incidence vs ez
     if (WANT_INC && inc_here) inc = unit_angle(e.ux, e.uy, e.uz, splat<T>(0.0), splat<T>(0.0), splat<T>(1.0));
   } else {
-    T nx, ny, nz;
-    surface_normal(E, hx, hy, hz, nx, ny, nz);
-    if (HAS_DEF && (E.n_defects > 0 || E.n_maps > 0)) {
-      // DeformedMirror._get_intersection, ART/ModuleMirror.py:969-980:
-      //   h = sum offsets(P - C); alpha = angle(-u, n_base(P)); P -= u h / cos(alpha)
-      T h = splat<T>(0.0);
-      for (int d = 0; d < E.n_defects; ++d) {
-        T v, g0, g1;
-        zernike_eval<true, false>(ztab + zoff[E.first_defect + d], hx - E.ctr[0], hy - E.ctr[1], v, g0, g1);
-        h = h + v;
-      }
-      for (int d = 0; d < E.n_maps; ++d) {
-        T v, unused;
-        gridmap_eval<0>(maps[E.first_map + d], hx - E.ctr[0], hy - E.ctr[1], v, unused);
-        h = h + v;
-      }
-      const T cosa = -mfma(nx, e.ux, mfma(ny, e.uy, nz * e.uz));
-      const T sh = fdiv(h, cosa);
-      t = t - sh;
-      hx = mfma(-sh, e.ux, hx); hy = mfma(-sh, e.uy, hy); hz = mfma(-sh, e.uz, hz);
-      surface_normal(E, hx, hy, hz, nx, ny, nz);  // the reflection uses get_normal(shifted point)
-      if (!ignore_defects) {
-        // DeformedMirror.get_normal + normal_add, ART/ModuleMirror.py:952-961, ModuleGeometry.py:394-407:
-        // slopes add; the result is (-gx, -gy, 1) normalised
-        const T inz = fdiv(1.0, nz);
-        T sx = -(nx * inz), sy = -(ny * inz);
+    const bool deformed = HAS_DEF && (E.n_defects > 0 || E.n_maps > 0);
+    if (ART_GRADIENT_REFLECT && !deformed) {
+      // _ReflectionMirrorRay, ART/ModuleMirror.py:878-906 with the normal left unnormalised: u' = u - 2 (g.u)/(g.g) g
+      // and angle(-u, g) are both independent of |g| -- no reciprocal square root, no renormalisation (the
+      // reflection keeps |u| to rounding; Ray.vector's renormalisation, ART/ModuleOpticalRay.py:85-90, moves the
+      // last bit only)
+      T gx, gy, gz;
+      surface_gradient(E, hx, hy, hz, gx, gy, gz);
+      const T d = mfma(gx, e.ux, mfma(gy, e.uy, gz * e.uz));
+      if (WANT_INC && inc_here) inc = unit_angle(-e.ux, -e.uy, -e.uz, gx, gy, gz);
+      const T k = fdiv(-2.0 * d, mfma(gx, gx, mfma(gy, gy, gz * gz)));
+      r.ux = mfma(k, gx, e.ux); r.uy = mfma(k, gy, e.uy); r.uz = mfma(k, gz, e.uz);
+    } else {
+      T nx, ny, nz;
+      surface_normal(E, hx, hy, hz, nx, ny, nz);
+      if (HAS_DEF && (E.n_defects > 0 || E.n_maps > 0)) {
+        // DeformedMirror._get_intersection, ART/ModuleMirror.py:969-980:
+        //   h = sum offsets(P - C); alpha = angle(-u, n_base(P)); P -= u h / cos(alpha)
+        T h = splat<T>(0.0);
         for (int d = 0; d < E.n_defects; ++d) {
           T v, g0, g1;
-          zernike_eval<false, true>(ztab + zoff[E.first_defect + d], hx - E.ctr[0], hy - E.ctr[1], v, g0, g1);
-          sx = sx + g0;
-          sy = sy + g1;
+          zernike_eval<true, false>(ztab + zoff[E.first_defect + d], hx - E.ctr[0], hy - E.ctr[1], v, g0, g1);
+          h = h + v;
         }
         for (int d = 0; d < E.n_maps; ++d) {
-          // MeasuredMap / Fourrier.get_normal returns (+dX, +dY, 1)/norm (ART/ModuleDefects.py:52-58,119-129),
-          // so normal_add's slope -n_x/n_z is MINUS the interpolated derivative
-          T g0, g1;
-          gridmap_eval<1>(maps[E.first_map + d], hx - E.ctr[0], hy - E.ctr[1], g0, g1);
-          sx = sx - g0;
-          sy = sy - g1;
+          T v, unused;
+          gridmap_eval<0>(maps[E.first_map + d], hx - E.ctr[0], hy - E.ctr[1], v, unused);
+          h = h + v;
         }
-        const T inv = frsqrt(mfma(sx, sx, mfma(sy, sy, 1.0)));
-        nx = -(sx * inv); ny = -(sy * inv); nz = inv;
+        const T cosa = -mfma(nx, e.ux, mfma(ny, e.uy, nz * e.uz));
+        const T sh = fdiv(h, cosa);
+        t = t - sh;
+        hx = mfma(-sh, e.ux, hx); hy = mfma(-sh, e.uy, hy); hz = mfma(-sh, e.uz, hz);
+        surface_normal(E, hx, hy, hz, nx, ny, nz);  // the reflection uses get_normal(shifted point)
+        if (!ignore_defects) {
+          // DeformedMirror.get_normal + normal_add, ART/ModuleMirror.py:952-961, ModuleGeometry.py:394-407:
+          // slopes add; the result is (-gx, -gy, 1) normalised
+          const T inz = fdiv(1.0, nz);
+          T sx = -(nx * inz), sy = -(ny * inz);
+          for (int d = 0; d < E.n_defects; ++d) {
+            T v, g0, g1;
+            zernike_eval<false, true>(ztab + zoff[E.first_defect + d], hx - E.ctr[0], hy - E.ctr[1], v, g0, g1);
+            sx = sx + g0;
+            sy = sy + g1;
+          }
+          for (int d = 0; d < E.n_maps; ++d) {
+            // MeasuredMap / Fourrier.get_normal returns (+dX, +dY, 1)/norm (ART/ModuleDefects.py:52-58,119-129),
+            // so normal_add's slope -n_x/n_z is MINUS the interpolated derivative
+            T g0, g1;
+            gridmap_eval<1>(maps[E.first_map + d], hx - E.ctr[0], hy - E.ctr[1], g0, g1);
+            sx = sx - g0;
+            sy = sy - g1;
+          }
+          const T inv = frsqrt(mfma(sx, sx, mfma(sy, sy, 1.0)));
+          nx = -(sx * inv); ny = -(sy * inv); nz = inv;
+        }
       }
+      // _ReflectionMirrorRay, ART/ModuleMirror.py:878-906: u' = u - 2 (n.u) n, incidence = angle(-u, n)
+      const T d = mfma(nx, e.ux, mfma(ny, e.uy, nz * e.uz));
+      if (WANT_INC && inc_here) inc = unit_angle(-e.ux, -e.uy, -e.uz, nx, ny, nz);
+      T ox = mfma(-2.0 * d, nx, e.ux), oy = mfma(-2.0 * d, ny, e.uy), oz = mfma(-2.0 * d, nz, e.uz);
+      // Ray.vector setter renormalises (ART/ModuleOpticalRay.py:85-90); one Newton step is exact here
+      const T sc = mfma(-0.5, mfma(ox, ox, mfma(oy, oy, oz * oz)), 1.5);
+      r.ux = ox * sc; r.uy = oy * sc; r.uz = oz * sc;   // the outgoing direction, still in this element's frame
     }
-    // _ReflectionMirrorRay, ART/ModuleMirror.py:878-906: u' = u - 2 (n.u) n, incidence = angle(-u, n)
-    const T d = mfma(nx, e.ux, mfma(ny, e.uy, nz * e.uz));
-    if (WANT_INC && inc_here) inc = unit_angle(-e.ux, -e.uy, -e.uz, nx, ny, nz);
-    T ox = mfma(-2.0 * d, nx, e.ux), oy = mfma(-2.0 * d, ny, e.uy), oz = mfma(-2.0 * d, nz, e.uz);
-    // Ray.vector setter renormalises (ART/ModuleOpticalRay.py:85-90); one Newton step is exact here
-    const T sc = mfma(-0.5, mfma(ox, ox, mfma(oy, oy, oz * oz)), 1.5);
-    r.ux = ox * sc; r.uy = oy * sc; r.uz = oz * sc;   // the outgoing direction, still in this element's frame
   }
   r.path = r.path + mabs(t);  // |P - A| with |u| = 1 (ModuleMirror.py:904, ModuleMask.py:100)
   r.inc = inc;
