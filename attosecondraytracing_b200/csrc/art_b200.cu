@@ -349,6 +349,9 @@ static int32_t launch_trace(ArtChain* c, int variant_first, int n_variants, cons
   if (variant_first < 0 || n_variants < 1 || variant_first + n_variants > c->n_variants)
     return fail(ART_E_INVALID, "variant range outside the chain's variants");
   if (in->n < 0) return fail(ART_E_INVALID, "negative ray count");
+  // the trace kernel indexes the rays of one variant with 32 bits (ART_INDEX32, art_kernels.cuh); 180 GB of HBM
+  // hold fewer than 2^32 rays (48 B per source ray)
+  if (in->n >= (int64_t)0xFFFFFFFEll) return fail(ART_E_INVALID, "more than 2^32 - 2 rays in one bundle");
   const bool uniform_point = (flags & ART_TRACE_UNIFORM_POINT) != 0;
   if (const char* why = check_columns(in, true, uniform_point))
     return fail(ART_E_INVALID, std::string("input bundle: ") + why);
