@@ -109,7 +109,7 @@ PEER_STATS = 4            # ART_PEER_STATS
 
 def peer_buffer_bytes(world):
     """ART_PEER_BUFFER_BYTES of the header."""
-    return 8 * (2 * world * PEER_MAX_VARIANTS * MOMENTS_LEN + world + 2 + PEER_STATS)
+    return 16 * (2 * world * PEER_MAX_VARIANTS * MOMENTS_LEN) + 8 * (world + 2 + PEER_STATS)
 
 
 def hist_len(nx, ny, nt):

@@ -700,7 +700,7 @@ static int32_t peer_exchange_impl(const uint64_t* peer_bufs, int32_t rank, int32
   a.rows = rows;
   a.distance = distance;
   a.det_out = kind == 0 ? det_out : nullptr;
-  a.spin_limit = 50000000ull;  // x (64 ns sleep + a system-scope load) ~ 10 s
+  a.spin_limit = 10000000ull;  // polling rounds of ~1 us each (system-scope loads of the pending cells): ~10 s
   a.partials = partials;
   a.n_partials = n_partials;
   peer_exchange_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
@@ -729,11 +729,15 @@ extern "C" int32_t art_peer_exchange_fold(ArtChain* chain, const uint64_t* peer_
                             n_partials);
 }
 
+// the u64 words behind the 16-byte cells of an exchange buffer (peer_exchange_kernel, art_kernels.cuh)
+static inline uint64_t* peer_words(uint64_t buf, int world) {
+  return reinterpret_cast<uint64_t*>(buf + (uint64_t)16 * 2 * (uint64_t)world * PEER_MAX_DOUBLES);
+}
+
 extern "C" int32_t art_peer_status(const uint64_t* peer_bufs, int32_t rank, int32_t world, uint64_t* status_out,
                                    void* stream) {
   if (!peer_bufs || !status_out || world < 1 || rank < 0 || rank >= world) return fail(ART_E_INVALID, "bad argument");
-  const double* base = reinterpret_cast<const double*>(peer_bufs[rank]);
-  const uint64_t* words = reinterpret_cast<const uint64_t*>(base + (size_t)2 * world * PEER_MAX_DOUBLES);
+  const uint64_t* words = peer_words(peer_bufs[rank], world);
   ART_CUDA(cudaMemcpyAsync(status_out, words + world + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   ART_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return ART_OK;
@@ -742,8 +746,7 @@ extern "C" int32_t art_peer_status(const uint64_t* peer_bufs, int32_t rank, int3
 extern "C" int32_t art_peer_stats(const uint64_t* peer_bufs, int32_t rank, int32_t world, uint64_t* stats_out,
                                   int32_t reset, void* stream) {
   if (!peer_bufs || !stats_out || world < 1 || rank < 0 || rank >= world) return fail(ART_E_INVALID, "bad argument");
-  double* base = reinterpret_cast<double*>(peer_bufs[rank]);
-  uint64_t* words = reinterpret_cast<uint64_t*>(base + (size_t)2 * world * PEER_MAX_DOUBLES);
+  uint64_t* words = peer_words(peer_bufs[rank], world);
   cudaStream_t st = (cudaStream_t)stream;
   ART_CUDA(cudaMemcpyAsync(stats_out, words + world + 2, ART_PEER_STATS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   if (reset) ART_CUDA(cudaMemsetAsync(words + world + 2, 0, ART_PEER_STATS * sizeof(uint64_t), st));
@@ -960,8 +963,7 @@ static int32_t statistics_enqueue(ArtChain* c, const ArtBundleView* dout_p, size
   ART_CUDA(cudaMemcpyAsync(pd, c->d_det, sizeof(ArtDetector), cudaMemcpyDeviceToHost, st));
   if (peer_bufs) {
     uint64_t* pw = reinterpret_cast<uint64_t*>(pd + 1);  // {epoch, status} of this rank's exchange buffer
-    const double* base = reinterpret_cast<const double*>(peer_bufs[rank]);
-    const uint64_t* words = reinterpret_cast<const uint64_t*>(base + (size_t)2 * world * PEER_MAX_DOUBLES);
+    const uint64_t* words = peer_words(peer_bufs[rank], world);
     ART_CUDA(cudaMemcpyAsync(pw, words + world, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   }
   if (out_final_host && n) {

@@ -1451,18 +1451,20 @@ __global__ void merge_moments_kernel(const double* __restrict__ rows, int n_rank
 
 // ---------------------------------------------------------------------------------------------
 // Multi-GPU exchange of the small per-detector rows over PEER MEMORY (NVLink / NVSwitch) inside one
-// kernel: every rank stores its row into slot [rank] of EVERY rank's exchange buffer (remote stores),
-// publishes its epoch in the peers' flag words (release at system scope), waits until the flags of all
-// ranks in its OWN buffer have reached the epoch (acquire) and reduces the rows in rank order -- the same
-// arithmetic on every rank, so every rank places the identical detector.  Replaces an NCCL all-reduce /
-// all-gather of 80-200 bytes (latency-bound, ~15 us each) and the kernel that followed it (autoplace /
-// merge).  The epoch lives in device memory and is advanced by the kernel itself, so the step including
-// the exchange can be captured in a CUDA graph.  Payload slots are double-buffered by epoch parity: a rank
-// that is one exchange ahead writes the other half and cannot be two ahead (it would need this rank's next
-// flag first).
-// Buffer of one rank (identical layout on all ranks, ART_PEER_BUFFER_BYTES(world)):
-//   double payload[2][world][PEER_MAX_DOUBLES];  u64 flags[world];  u64 epoch;  u64 status;
-//   u64 stats[ART_PEER_STATS]: exchanges counted, ns spent waiting for the peers' flags (spin), ns in the kernel --
+// kernel: every rank stores its row into slot [rank] of EVERY rank's exchange buffer (remote stores) and
+// reduces the rows that arrive in its OWN buffer in rank order -- the same arithmetic on every rank, so every
+// rank places the identical detector.  Replaces an NCCL all-reduce / all-gather of 80-200 bytes
+// (latency-bound, ~15 us each) and the kernel that followed it (autoplace / merge).
+// Flag-in-data protocol (NCCL's LL): a payload double travels as one 16-byte cell {lo32, epoch32, hi32, epoch32};
+// each 8-byte half is written atomically, so a cell whose two epochs equal the current one IS the value -- no
+// separate flag, no system-scope release / acquire (the fenced version of this kernel spent 2.5 us of every
+// exchange waiting for its own remote stores to be acknowledged before it could publish a flag).
+// The epoch lives in device memory and is advanced by the kernel itself, so the step including the exchange can
+// be captured in a CUDA graph.  Cells are double-buffered by epoch parity: a rank that is one exchange ahead
+// writes the other half and cannot be two ahead (it needs this rank's next row first).
+// Buffer of one rank (identical layout on all ranks, ART_PEER_BUFFER_BYTES(world), zeroed before first use):
+//   uint4 cell[2][world][PEER_MAX_DOUBLES];  u64 reserved[world];  u64 epoch;  u64 status;
+//   u64 stats[ART_PEER_STATS]: exchanges counted, ns spent polling for the peers' cells, ns in the kernel --
 //   accumulated by thread 0 from %globaltimer; what a timeline would show (skew between the ranks vs the cost of
 //   the exchange itself), read back with art_peer_stats
 // ---------------------------------------------------------------------------------------------
@@ -1529,11 +1531,12 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
     }
     __syncthreads();   // a.rows is read by all threads below (same block: visible after the barrier)
   }
-  auto base = [&](int owner) { return reinterpret_cast<double*>(a.bufs[owner]); };
+  // every payload double travels as a 16-byte cell {lo32, epoch32, hi32, epoch32}
+  auto cells = [&](int owner) { return reinterpret_cast<uint4*>(a.bufs[owner]); };
   auto words = [&](int owner) {
-    return reinterpret_cast<unsigned long long*>(base(owner) + (size_t)2 * a.world * PEER_MAX_DOUBLES);
+    return reinterpret_cast<unsigned long long*>(cells(owner) + (size_t)2 * a.world * PEER_MAX_DOUBLES);
   };
-  unsigned long long* const mine = words(a.rank);  // flags[world], epoch, status
+  unsigned long long* const mine = words(a.rank);  // [0, world): unused (flags of the fenced protocol), epoch, status
   unsigned long long t_enter = 0ull, t_wait0 = 0ull, t_wait1 = 0ull;
   if (tid == 0) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_enter));
@@ -1543,27 +1546,55 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
   }
   __syncthreads();
   const unsigned long long epoch = sEpoch;
+  const unsigned ep = (unsigned)epoch;   // never 0 within 2^32 exchanges: the buffers start zeroed
   const size_t half = (size_t)(epoch & 1ull) * a.world * PEER_MAX_DOUBLES;
-  // 1. my row into my slot of every rank's buffer (remote stores over NVLink; the local one is a plain store)
-  for (int p = 0; p < a.world; ++p) {
-    double* dst = base(p) + half + (size_t)a.rank * PEER_MAX_DOUBLES;
-    for (int j = tid; j < len; j += blockDim.x) dst[j] = a.rows[j];
+  // 1. my row into my slot of every rank's buffer: one 16-byte store per double and peer.  The epoch rides in both
+  // 8-byte halves of the cell (each half is written atomically), so the receiver needs no flag, no fence and no
+  // acquire: a cell whose two epochs match IS the value (the protocol of NCCL's LL path).
+  for (int idx = tid; idx < a.world * len; idx += blockDim.x) {
+    const int p = idx / len, j = idx - p * len;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(a.rows[j]);
+    uint4* dst = cells(p) + half + (size_t)a.rank * PEER_MAX_DOUBLES + j;
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"((unsigned)bits), "r"(ep),
+                 "r"((unsigned)(bits >> 32)), "r"(ep)
+                 : "memory");
   }
-  // No system-wide fence here: the barrier orders every thread's row stores before the publishing threads, and
-  // their st.release.sys is cumulative, so a peer that acquires the flag observes the whole row (PTX memory model:
-  // causality through bar.sync + release at system scope).  The fence cost ~2 us per exchange.
-  __syncthreads();
-  // 2. publish, then wait for everybody
+  __syncthreads();   // a.rows is overwritten below
   if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_wait0));
-  if (tid < a.world) {
-    st_release_sys(words(tid) + a.rank, epoch);
+  // 2. + 3. thread j polls cell j of every rank in its OWN buffer and reduces them in rank order -- the same
+  // arithmetic on every rank, so every rank places the identical detector
+  for (int j = tid; j < len; j += blockDim.x) {
+    const int op = a.kind == 0 ? 0 : (a.kind == 1 ? moment_op(j % ART_MOMENTS_LEN) : 2);
+    const uint4* src = cells(a.rank) + half + j;
+    double val[ART_PEER_MAX_RANKS];
+    unsigned pending = a.world >= 32 ? 0xffffffffu : ((1u << a.world) - 1u);
     unsigned long long polls = 0;
-    while (ld_acquire_sys(mine + tid) < epoch) {
-      if (++polls > a.spin_limit) {
+    while (pending) {
+#pragma unroll
+      for (int r = 0; r < ART_PEER_MAX_RANKS; ++r) {
+        if (r < a.world && (pending >> r & 1u)) {
+          uint4 c;
+          asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
+                       : "l"(src + (size_t)r * PEER_MAX_DOUBLES)
+                       : "memory");
+          if (c.y == ep && c.w == ep) {
+            val[r] = __longlong_as_double((long long)((unsigned long long)c.z << 32 | c.x));
+            pending &= ~(1u << r);
+          }
+        }
+      }
+      if (pending && ++polls > a.spin_limit) {
         sFail = 1;
         break;
       }
-      __nanosleep(64);
+    }
+    if (!pending) {
+      double x = val[0];
+#pragma unroll
+      for (int r = 1; r < ART_PEER_MAX_RANKS; ++r)
+        if (r < a.world) x = red_any(op, x, val[r]);
+      a.rows[j] = x;
     }
   }
   __syncthreads();
@@ -1572,16 +1603,7 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
     if (tid == 0) mine[a.world + 1] = epoch;  // status: the epoch that timed out
     return;
   }
-  // 3. the same reduction in rank order on every rank (ld.global.cg: the slots are written by peers)
-  for (int j = tid; j < len; j += blockDim.x) {
-    const int op = a.kind == 0 ? 0 : (a.kind == 1 ? moment_op(j % ART_MOMENTS_LEN) : 2);
-    const double* src = base(a.rank) + half + j;
-    double x = __ldcg(src);
-    for (int r = 1; r < a.world; ++r) x = red_any(op, x, __ldcg(src + (size_t)r * PEER_MAX_DOUBLES));
-    a.rows[j] = x;
-  }
   if (a.kind == 0 && a.det_out) {
-    __syncthreads();
     for (int v = tid; v < a.n_variants; v += blockDim.x)
       autoplace_row(a.rows + (size_t)v * ART_CENTRAL_LEN, a.distance, a.det_out + v);
   }

@@ -327,9 +327,10 @@ int32_t art_moments_merge(const double* rows, int32_t n_ranks, int32_t n_variant
  */
 #define ART_PEER_MAX_RANKS 16
 #define ART_PEER_MAX_VARIANTS 64
-#define ART_PEER_STATS 4 /* exchanges, ns waiting for the peers' flags, ns inside the kernel, reserved */
-#define ART_PEER_BUFFER_BYTES(world) \
-  ((int64_t)8 * ((int64_t)2 * (world) * ART_PEER_MAX_VARIANTS * ART_MOMENTS_LEN + (world) + 2 + ART_PEER_STATS))
+#define ART_PEER_STATS 4 /* exchanges, ns polling for the peers' rows, ns inside the kernel, reserved */
+#define ART_PEER_BUFFER_BYTES(world)                                                       \
+  ((int64_t)16 * ((int64_t)2 * (world) * ART_PEER_MAX_VARIANTS * ART_MOMENTS_LEN) + \
+   (int64_t)8 * ((world) + 2 + ART_PEER_STATS))
 int32_t art_peer_exchange(const uint64_t* peer_bufs, int32_t rank, int32_t world, int32_t kind, int32_t n_variants,
                           double* rows, double distance, ArtDetector* det_out, void* stream);
 /*
@@ -344,8 +345,7 @@ int32_t art_peer_exchange_fold(ArtChain* chain, const uint64_t* peer_bufs, int32
 /* Synchronises the stream and returns the status word of this rank's buffer in *status_out. */
 int32_t art_peer_status(const uint64_t* peer_bufs, int32_t rank, int32_t world, uint64_t* status_out, void* stream);
 /* Synchronises the stream and copies the ART_PEER_STATS counters of this rank's buffer to stats_out: number of
- * exchanges, nanoseconds spent waiting for the peers' flags (the skew between the ranks plus the NVLink round
- * trip) and nanoseconds inside the exchange kernel, accumulated since the buffer was zeroed -- the breakdown a
+ * exchanges, nanoseconds spent polling for the peers' rows (the skew between the ranks plus the NVLink latency) and nanoseconds inside the exchange kernel, accumulated since the buffer was zeroed -- the breakdown a
  * timeline of the multi-GPU step would show.  With reset != 0 the counters are zeroed afterwards. */
 int32_t art_peer_stats(const uint64_t* peer_bufs, int32_t rank, int32_t world, uint64_t* stats_out, int32_t reset,
                        void* stream);
