@@ -367,10 +367,10 @@ __device__ __forceinline__ void store_bundle(const BundleDev& O, I at, bool vec,
 #define ART_BT_QUADRIC 320
 #endif
 #ifndef ART_BT_TOROID
-#define ART_BT_TOROID 256
+#define ART_BT_TOROID 320   // 96 registers without spills since the gradient reflection: 20 warps per SM
 #endif
 #ifndef ART_BT_ANY
-#define ART_BT_ANY 256
+#define ART_BT_ANY 320
 #endif
 #ifndef ART_BT_DEF
 #define ART_BT_DEF 192
@@ -1570,18 +1570,24 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
     unsigned pending = a.world >= 32 ? 0xffffffffu : ((1u << a.world) - 1u);
     unsigned long long polls = 0;
     while (pending) {
+      // one polling round: the loads of all pending cells are issued back to back (one L2 / NVLink-ingress latency
+      // for the round, not one per rank), then examined
+      uint4 c[ART_PEER_MAX_RANKS];
 #pragma unroll
       for (int r = 0; r < ART_PEER_MAX_RANKS; ++r) {
-        if (r < a.world && (pending >> r & 1u)) {
-          uint4 c;
-          asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
-                       : "l"(src + (size_t)r * PEER_MAX_DOUBLES)
-                       : "memory");
-          if (c.y == ep && c.w == ep) {
-            val[r] = __longlong_as_double((long long)((unsigned long long)c.z << 32 | c.x));
-            pending &= ~(1u << r);
-          }
+        // unconditional (slots beyond the world re-read slot 0): predicated loads end up in one register quad and
+        // serialise
+        const uint4* cell = src + (size_t)(r < a.world ? r : 0) * PEER_MAX_DOUBLES;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(c[r].x), "=r"(c[r].y), "=r"(c[r].z), "=r"(c[r].w)
+                     : "l"(cell)
+                     : "memory");
+      }
+#pragma unroll
+      for (int r = 0; r < ART_PEER_MAX_RANKS; ++r) {
+        if (r < a.world && (pending >> r & 1u) && c[r].y == ep && c[r].w == ep) {
+          val[r] = __longlong_as_double((long long)((unsigned long long)c[r].z << 32 | c[r].x));
+          pending &= ~(1u << r);
         }
       }
       if (pending && ++polls > a.spin_limit) {
