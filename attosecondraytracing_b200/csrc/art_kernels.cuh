@@ -1575,12 +1575,11 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
       uint4 c[ART_PEER_MAX_RANKS];
 #pragma unroll
       for (int r = 0; r < ART_PEER_MAX_RANKS; ++r) {
-        // unconditional (slots beyond the world re-read slot 0): predicated loads end up in one register quad and
-        // serialise
-        const uint4* cell = src + (size_t)(r < a.world ? r : 0) * PEER_MAX_DOUBLES;
+        // every rank's cell, pending or not: loads predicated per thread end up in one register quad and serialise
+        if (r >= a.world) break;
         asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(c[r].x), "=r"(c[r].y), "=r"(c[r].z), "=r"(c[r].w)
-                     : "l"(cell)
+                     : "l"(src + (size_t)r * PEER_MAX_DOUBLES)
                      : "memory");
       }
 #pragma unroll
