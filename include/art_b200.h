@@ -229,7 +229,8 @@ int32_t art_chain_destroy(ArtChain* chain);
  *   central_out NULL, or device pointer to n_variants x ART_CENTRAL_LEN doubles receiving the
  *               sums over the surviving final rays that FindCentralRay needs
  *               (ART/ModuleProcessing.py:464-482), reduced in a fixed order (deterministic).
- * One fused kernel launch; every element of the chain is applied per ray in registers.
+ * One fused kernel launch; every element of the chain is applied per ray in registers.  in->n < 2^32 - 2
+ * (the kernel indexes the rays of one variant with 32 bits; ART_E_INVALID otherwise).
  */
 int32_t art_trace(ArtChain* chain, int32_t variant_first, int32_t n_variants, const ArtBundleView* in,
                   const ArtBundleView* out_final, const ArtBundleView* out_history, uint32_t flags,
@@ -345,7 +346,8 @@ int32_t art_peer_exchange_fold(ArtChain* chain, const uint64_t* peer_bufs, int32
 /* Synchronises the stream and returns the status word of this rank's buffer in *status_out. */
 int32_t art_peer_status(const uint64_t* peer_bufs, int32_t rank, int32_t world, uint64_t* status_out, void* stream);
 /* Synchronises the stream and copies the ART_PEER_STATS counters of this rank's buffer to stats_out: number of
- * exchanges, nanoseconds spent polling for the peers' rows (the skew between the ranks plus the NVLink latency) and nanoseconds inside the exchange kernel, accumulated since the buffer was zeroed -- the breakdown a
+ * exchanges, nanoseconds spent polling for the peers' rows (the skew between the ranks plus the NVLink latency)
+ * and nanoseconds inside the exchange kernel, accumulated since the buffer was zeroed -- the breakdown a
  * timeline of the multi-GPU step would show.  With reset != 0 the counters are zeroed afterwards. */
 int32_t art_peer_stats(const uint64_t* peer_bufs, int32_t rank, int32_t world, uint64_t* stats_out, int32_t reset,
                        void* stream);
