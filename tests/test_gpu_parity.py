@@ -259,6 +259,16 @@ def test_edge_cases_empty_ragged_and_all_blocked():
         assert h1["spot_count"].sum() == 1 and h1["spot_count"][0, 0] == 1 and h1["delay_count"][0] == 1
     with pytest.raises(Exception):
         chain.histogram(outs[0], det, mom, bins=(0, 8), delay_bins=16)
+    # a bundle claiming 2^32 rays is refused before any launch (the trace kernel indexes a variant's rays with 32 bits)
+    import ctypes as C
+    import torch
+    from attosecondraytracing_b200 import _cabi
+    vin = RayBundle.from_numpy(P[:4], U[:4], device="cuda").view()
+    vin.n = 1 << 32
+    central = torch.zeros((1, _cabi.CENTRAL_LEN), dtype=torch.float64, device="cuda")
+    rc = _cabi.lib().art_trace(chain._handle, 0, 1, C.byref(vin), None, None, _cabi.TRACE_IGNORE_DEFECTS,
+                               C.c_void_p(central.data_ptr()), None)
+    assert rc != 0 and rc != _cabi.E_PEER_TIMEOUT and b"2^32" in _cabi.lib().art_last_error()
     chain.close()
 
 
