@@ -100,6 +100,57 @@ void run_mix() {
   cudaFree(out);
 }
 
+// issue-port test with FULL-RATE companions: per DFMA, NA independent FFMA (FP32 pipe, 32 lanes/clk per sub-partition:
+// one issue cycle each).  If an FP64 instruction held the issue port for one cycle only, a group of 1 DFMA + NA FFMA
+// would take max(2, 1 + NA) clocks; if it holds it for both cycles of its 16-lane pipe, 2 + NA.
+template <int NA>
+__global__ void __launch_bounds__(256) mixalu(double* out, int iters, double a, double b, double c, float fb, float fc) {
+  double x[CHAINS];
+  float f[CHAINS][4];
+#pragma unroll
+  for (int j = 0; j < CHAINS; ++j) {
+    x[j] = a + threadIdx.x + j;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f[j][q] = (float)(threadIdx.x * (q + 1) + j);
+  }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < CHAINS; ++j) {
+      x[j] = fma(x[j], b, c);
+#pragma unroll
+      for (int q = 0; q < NA; ++q) f[j][q] = fmaf(f[j][q], fb, fc);
+    }
+  }
+  double s = 0;
+  float t = 0;
+#pragma unroll
+  for (int j = 0; j < CHAINS; ++j) { s += x[j]; t += f[j][0] + f[j][1] + f[j][2] + f[j][3]; }
+  if (s == 123.456 || t == 12345.f) out[0] = s + t;
+}
+template <int NA>
+void run_mixalu() {
+  int sms = 0, khz = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+  double* out;
+  cudaMalloc(&out, 8);
+  const int iters = 20000, threads = 256, bps = 2;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  mixalu<NA><<<sms * bps, threads>>>(out, 100, 1.0, 0.999999, 1e-9, 0.999f, 1e-3f);
+  cudaEventRecord(e0);
+  mixalu<NA><<<sms * bps, threads>>>(out, iters, 1.0, 0.999999, 1e-9, 0.999f, 1e-3f);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double clocks = ms * 1e-3 * khz * 1e3;
+  const double groups = (double)sms * bps * (threads / 32) * (double)iters * CHAINS;
+  printf("1 DFMA + %d FFMA: %.2f clk per group per SMSP (one-cycle issue port: %d, two-cycle: %d)\n", NA,
+         clocks * sms * 4 / groups, 1 + NA > 2 ? 1 + NA : 2, 2 + NA);
+  cudaFree(out);
+}
+
 // dependent-issue latency: NCH independent DFMA chains per thread, W warps per SM sub-partition
 template <int NCH>
 __global__ void __launch_bounds__(1024) lat(double* out, int iters, double a, double b, double c) {
@@ -140,6 +191,7 @@ void run_lat(int warps_per_smsp) {
 
 int main() {
   run_mix<0>(); run_mix<1>(); run_mix<2>(); run_mix<3>();
+  run_mixalu<0>(); run_mixalu<1>(); run_mixalu<2>(); run_mixalu<3>(); run_mixalu<4>();
   run_lat<1>(1); run_lat<2>(1); run_lat<4>(1); run_lat<8>(1);
   run_lat<1>(3); run_lat<2>(3); run_lat<4>(3);
   run_lat<1>(4); run_lat<2>(4); run_lat<2>(6); run_lat<2>(8);
