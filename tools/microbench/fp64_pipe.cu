@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) k(double* out, int iters, double a, doubl
       if (KIND == 2) x[j] = x[j] + y[j];                                    // DADD
       if (KIND == 3) x[j] = fma(x[j], p, q);                                // DFMA, 2 shared operands
       if (KIND == 4) { x[j] = fma(x[j], y[j], y[(j + 1) % CHAINS]); y[j] = x[j] > p ? y[j] : q; }  // DFMA + DSETP + 2 FSEL
-      if (KIND == 5) { x[j] = fma(x[j], y[j], y[(j + 1) % CHAINS]); x[j] = x[j] * y[j]; x[j] = x[j] + q; }  // mix
+      if (KIND == 5) { x[j] = fma(x[j], y[j], y[(j + 1) % CHAINS]); x[j] = __dadd_rn(__dmul_rn(x[j], y[j]), q); }  // mix (no contraction)
     }
   }
   double s = 0;
