@@ -362,7 +362,8 @@ __device__ __forceinline__ void store_bundle(const BundleDev& O, I at, bool vec,
 
 // Threads per block of a trace kernel instantiation, by what the chain contains (two blocks per SM are resident;
 // the register budget per thread follows: 65536 / (2 BT)).  Measured on B200 (profiles/r02_summary.md): the
-// lock-step pair of the defect-free chains fits 128 registers without spilling, the Zernike recurrences need ~168.
+// lock-step pair of the defect-free chains fits 96 registers without spilling (320 x 2 = 20 warps per SM), the Zernike
+// recurrences need ~168 (192 x 2).
 #ifndef ART_BT_QUADRIC
 #define ART_BT_QUADRIC 320
 #endif
