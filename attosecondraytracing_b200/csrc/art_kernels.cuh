@@ -589,15 +589,16 @@ __global__ void __launch_bounds__(trace_block_threads(HAS_DEF, SURFS), HAS_DEF ?
     if constexpr (PACK) {
       RayT<D2> pr = pack_rays(r[0], r[N - 1]);
       to_element_frame(sE[0], pr, eorg0);
-      for (int k = 0; k < a.n_elements; ++k) {
+      const ElemDev* E = sE;   // walked by pointer: no index arithmetic per element
+      for (int k = 0; k < a.n_elements; ++k, ++E) {
         const bool inc_here = WANT_INC && (k == last || a.has_hist);
         const bool inner = k != last;
         if (any(pr.alive))
-          apply_element<WANT_INC, HAS_DEF, SURFS, D2>(sE[k], pr, sZ, sZoff, ignore_defects, inc_here, a.maps, inner);
+          apply_element<WANT_INC, HAS_DEF, SURFS, D2>(*E, pr, sZ, sZoff, ignore_defects, inc_here, a.maps, inner);
         if (a.has_hist) {
           if (inner) {
             RayT<D2> lab;
-            frame_to_lab(sE[k + 1], pr, lab);
+            frame_to_lab(E[1], pr, lab);
             unpack_rays(lab, r[0], r[N - 1]);
           } else {
             unpack_rays(pr, r[0], r[N - 1]);

@@ -88,6 +88,12 @@ template <>
 ART_HD double splat<double>(double x) { return x; }
 template <>
 ART_HD D2 splat<D2>(double x) { return {x, x}; }
+template <class T>
+ART_HD typename MaskOf<T>::type splat_mask(bool x);
+template <>
+ART_HD bool splat_mask<double>(bool x) { return x; }
+template <>
+ART_HD B2 splat_mask<D2>(bool x) { return {x, x}; }
 
 // 1/d to ~2^-46: MUFU.RCP64H seed (2^-23) + one Newton step.  Only used for Newton CORRECTIONS of the
 // root search, which are self-correcting; the converged root does not depend on the step's last bits.
@@ -189,7 +195,7 @@ ART_HD void solve_quadratic(T a, T b, T c, T& t1, T& t2) {
 // A root that is not positive for either lane (the far root of a ray that starts inside a sphere, ...)
 // skips its hit-point evaluation altogether.
 template <bool SIDE_Z_NEG, class T>
-ART_HD T pick_candidate(const ElemDev& E, const RayT<T>& r, T t1, T t2, double zlim) {
+ART_HD T pick_candidate(const ElemDev& E, const RayT<T>& r, T t1, T t2, double zlim, typename MaskOf<T>::type& valid) {
   typedef typename MaskOf<T>::type M;
   M c1 = t1 > 1e-12, c2 = t2 > 1e-12;
   if (any(c1)) {
@@ -204,7 +210,8 @@ ART_HD T pick_candidate(const ElemDev& E, const RayT<T>& r, T t1, T t2, double z
   }
   // t2 wins when it is a candidate and either t1 is none or t2 is nearer
   const M use2 = mand(c2, mor(mnot(c1), t2 < t1));
-  return sel(use2, t2, sel(c1, t1, ART_NAN));
+  valid = mor(use2, c1);   // the hit distance of a lane without a candidate is meaningless (the caller masks it)
+  return sel(use2, t2, t1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -327,7 +334,8 @@ ART_HD TorEval<T> tor_eval_quartic(const RayT<T>& r, T t, double c, double R2) {
 }
 
 template <class T>
-ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>::type act) {
+ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>::type act,
+                          typename MaskOf<T>::type& valid) {
   typedef typename MaskOf<T>::type M;
   const double R = E.sp[0], rr = E.sp[1], r2 = E.sp[2];
   // start for the right root: the tangent plane z = -(R+r) lies outside the solid
@@ -388,7 +396,10 @@ ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>
     maybe_out = mand(act, mnot(mand(in_y, in_rho)));
   }
 #endif
-  if (!any(maybe_out)) return sel(cb, tb, ART_NAN);
+  if (!any(maybe_out)) {
+    valid = cb;
+    return tb;
+  }
   const TorEval<T> o = tor_eval(r, splat<T>(0.0), R, r2);
   const M outside = mand(maybe_out, o.F > 0.0);    // origin outside the solid: a second, nearer root may exist
   const M away = mand(outside, mnot(o.dF < 0.0));  // ... but not if we move away from the solid
@@ -401,8 +412,8 @@ ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>
     ca = mand(mand(ca, z < -R), in_support<false>(E, x, y));
   }
   // one candidate -> it, two -> the nearer (ta <= tb)
-  const T t = sel(ca, ta, sel(cb, tb, ART_NAN));
-  return sel(away, ART_NAN, t);
+  valid = mand(mor(ca, cb), mnot(away));
+  return sel(ca, ta, tb);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -660,6 +671,7 @@ ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict
   const M act = r.alive;
   RayT<T>& e = r;   // the ray in this element's frame; r.p / r.u are overwritten only once h and o are known
   T t;
+  M valid;
   const int surf = E.surface;
   if (surf == ART_SURF_PLANE || surf == ART_SURF_MASK) {
     // ART/ModuleMirror.py:73-82: t > 0 (no epsilon) and on the support;
@@ -668,9 +680,9 @@ ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict
     const T x = mfma(t, e.ux, e.px), y = mfma(t, e.uy, e.py);
     M ok = in_support<false>(E, x, y);
     if (surf == ART_SURF_MASK) ok = mnot(ok);
-    t = sel(mand(t > 0.0, ok), t, ART_NAN);
+    valid = mand(t > 0.0, ok);
   } else if (SURFS != SURFS_QUADRIC && surf == ART_SURF_TOROIDAL) {
-    t = intersect_toroid(E, e, act);
+    t = intersect_toroid(E, e, act, valid);
   } else if (SURFS != SURFS_TOROID) {
     T a, b, c;
     bool side = true;
@@ -696,12 +708,14 @@ ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict
     }
     T t1, t2;
     solve_quadratic(a, b, c, t1, t2);
-    t = side ? pick_candidate<true>(E, e, t1, t2, 0.0) : pick_candidate<false>(E, e, t1, t2, 0.0);
+    t = side ? pick_candidate<true>(E, e, t1, t2, 0.0, valid) : pick_candidate<false>(E, e, t1, t2, 0.0, valid);
   } else {
     t = splat<T>(ART_NAN);
+    valid = splat_mask<T>(false);
   }
-  // miss: the reference drops the ray (ModuleMirror.py:932, ModuleMask.py:132)
-  const M hit = mand(act, t == t);
+  // miss: the reference drops the ray (ModuleMirror.py:932, ModuleMask.py:132).  Validity travels as a lane mask, not
+  // as a NaN in t: no selects to poison t and no FP64 compare to read the poison back.
+  const M hit = mand(act, valid);
   if (!any(hit)) {
     r.alive = hit;
     return;
