@@ -453,6 +453,7 @@ __global__ void __launch_bounds__(trace_block_threads(HAS_DEF, SURFS), HAS_DEF ?
     __syncthreads();
   }
   const bool load_w = a.in.inten != nullptr && a.wstate == nullptr;
+  const unsigned char* const in_alive = a.in.alive;
 
   const bool ignore_defects = (a.flags & ART_TRACE_IGNORE_DEFECTS) != 0;
   const long long n = a.n;
@@ -553,8 +554,12 @@ __global__ void __launch_bounds__(trace_block_threads(HAS_DEF, SURFS), HAS_DEF ?
 #pragma unroll
     for (int q = 0; q < N; ++q) {
       r[q].alive = (q == 0) || two;
-      if (a.in.alive && r[q].alive) r[q].alive = a.in.alive[i + q] != 0;
       r[q].inc = ART_NAN;
+    }
+    if (in_alive) {   // kernel-uniform: a branch around the flag loads, not predicated-off instructions for every ray
+#pragma unroll
+      for (int q = 0; q < N; ++q)
+        if (r[q].alive) r[q].alive = in_alive[i + q] != 0;
     }
     if (a.wstate) {
 #pragma unroll

@@ -259,22 +259,24 @@ ART_HD TorEval<T> tor_eval(const RayT<T>& r, T t, double R, double r2) {
 #define ART_PEEL_NEWTON 1   // first checked step outside the loop: the common case converges on it
 #endif
 template <int DIR, class T>
-ART_HD void tor_newton_step(const TorEval<T>& e, T& t, T& result, typename MaskOf<T>::type& todo, double scale) {
+ART_HD void tor_newton_step(const TorEval<T>& e, T& t, typename MaskOf<T>::type& done, typename MaskOf<T>::type& todo,
+                            double scale) {
   typedef typename MaskOf<T>::type M;
   const T slope = DIR > 0 ? e.dF : -e.dF;
   const M good = slope > 0.0;
   const T dt = e.F * fast_rcp(e.dF);
   const T tn = t - dt;
   const M conv = mand(good, dt * dt <= 2e-16 * (mabs(tn) + scale) * slope);
-  result = sel(mand(todo, conv), tn, result);
+  t = sel(todo, tn, t);   // every lane still iterating moves; one that converges with this step keeps tn for good
+  done = mor(done, mand(todo, conv));
   todo = mand(todo, mand(good, mnot(conv)));
-  t = sel(todo, tn, t);
 }
+// Returns t; `done` = the lanes whose iteration converged (the value of any other lane is meaningless).
 template <int DIR, int PRE, class T>
 ART_HD T tor_newton(const RayT<T>& r, T t, TorEval<T> e, double R, double r2, double scale,
-                    typename MaskOf<T>::type active) {
+                    typename MaskOf<T>::type active, typename MaskOf<T>::type& done) {
   typedef typename MaskOf<T>::type M;
-  T result = splat<T>(ART_NAN);
+  done = splat_mask<T>(false);
   M todo = active;
 #pragma unroll
   for (int p = 0; p < PRE; ++p) {
@@ -283,18 +285,18 @@ ART_HD T tor_newton(const RayT<T>& r, T t, TorEval<T> e, double R, double r2, do
     e = tor_eval(r, t, R, r2);
   }
 #if ART_PEEL_NEWTON
-  tor_newton_step<DIR>(e, t, result, todo, scale);
+  tor_newton_step<DIR>(e, t, done, todo, scale);
   for (int it = 1; it < 64 && any(todo); ++it) {
     e = tor_eval(r, t, R, r2);
-    tor_newton_step<DIR>(e, t, result, todo, scale);
+    tor_newton_step<DIR>(e, t, done, todo, scale);
   }
 #else
   for (int it = 0; it < 64 && any(todo); ++it) {
-    tor_newton_step<DIR>(e, t, result, todo, scale);
+    tor_newton_step<DIR>(e, t, done, todo, scale);
     if (any(todo)) e = tor_eval(r, t, R, r2);
   }
 #endif
-  return result;
+  return t;
 }
 
 #ifndef ART_NEWTON_PRE
@@ -372,12 +374,14 @@ ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>
     ok = mand(ok, e0.dF > 0.0);
     t0 = t0 - e0.F * fast_rcp(e0.dF);
   }
-  const T tb = tor_newton<+1, 0>(r, t0, tor_eval(r, t0, R, r2), R, r2, rr, ok);
+  M vb;
+  const T tb = tor_newton<+1, 0>(r, t0, tor_eval(r, t0, R, r2), R, r2, rr, ok, vb);
 #else
-  const T tb = tor_newton<+1, ART_NEWTON_PRE>(r, t0, e0, R, r2, rr, act);
+  M vb;
+  const T tb = tor_newton<+1, ART_NEWTON_PRE>(r, t0, e0, R, r2, rr, act, vb);
 #endif
   // the far root as a candidate: t > 1e-12, z < -R, on the support (pick_candidate's rule for one root)
-  M cb = tb > 1e-12;
+  M cb = mand(vb, tb > 1e-12);
   {
     const T x = mfma(tb, r.ux, r.px), y = mfma(tb, r.uy, r.py), z = mfma(tb, r.uz, r.pz);
     cb = mand(mand(cb, z < -R), in_support<false>(E, x, y));
@@ -404,9 +408,10 @@ ART_HD T intersect_toroid(const ElemDev& E, const RayT<T>& r, typename MaskOf<T>
   const M outside = mand(maybe_out, o.F > 0.0);    // origin outside the solid: a second, nearer root may exist
   const M away = mand(outside, mnot(o.dF < 0.0));  // ... but not if we move away from the solid
   const M need = mand(outside, mnot(away));
-  T ta = splat<T>(ART_NAN);
-  if (any(need)) ta = tor_newton<-1, 0>(r, splat<T>(0.0), o, R, r2, rr, need);
-  M ca = mand(need, ta > 1e-12);
+  T ta = splat<T>(0.0);
+  M va = splat_mask<T>(false);
+  if (any(need)) ta = tor_newton<-1, 0>(r, splat<T>(0.0), o, R, r2, rr, need, va);
+  M ca = mand(mand(need, va), ta > 1e-12);
   {
     const T x = mfma(ta, r.ux, r.px), y = mfma(ta, r.uy, r.py), z = mfma(ta, r.uz, r.pz);
     ca = mand(mand(ca, z < -R), in_support<false>(E, x, y));
