@@ -150,25 +150,22 @@ ART_HD typename MaskOf<T>::type in_support(const ElemDev& E, T x, T y) {
     x = x - E.soff[0];
     y = y - E.soff[1];
   }
-  switch (E.support) {
-    case ART_SUPP_ROUND:
-      return mfma(x, x, y * y) <= E.ap[0];
-    case ART_SUPP_ROUND_HOLE: {
-      const T hx = x - E.ap[2], hy = y - E.ap[3];
-      return mand(mfma(x, x, y * y) <= E.ap[0], mnot(mfma(hx, hx, hy * hy) <= E.ap[1]));
-    }
-    case ART_SUPP_RECT:
-      return mand(mabs(x) <= E.ap[0], mabs(y) <= E.ap[1]);
-    case ART_SUPP_RECT_HOLE: {
-      const T hx = x - E.ap[3], hy = y - E.ap[4];
-      return mand(mand(mabs(x) <= E.ap[0], mabs(y) <= E.ap[1]), mnot(mfma(hx, hx, hy * hy) <= E.ap[2]));
-    }
-    default: {  // ART_SUPP_RECT_RECT_HOLE
-      const T hx = x - E.ap[4], hy = y - E.ap[5];
-      return mand(mand(mabs(x) <= E.ap[0], mabs(y) <= E.ap[1]),
-                  mnot(mand(mabs(hx) <= E.ap[2], mabs(hy) <= E.ap[3])));
-    }
+  // Two binary, warp-uniform decisions (outline round / rectangular, hole or not) instead of a five-way switch: the
+  // compiler turns a switch -- and an if-chain over the kind -- into a jump table that costs seven instructions per call.
+  typedef typename MaskOf<T>::type M;
+  const int kind = E.support;
+  M in;
+  if (kind >= ART_SUPP_RECT) in = mand(mabs(x) <= E.ap[0], mabs(y) <= E.ap[1]);
+  else in = mfma(x, x, y * y) <= E.ap[0];
+  if ((kind & 1) == 0 && kind != ART_SUPP_RECT_RECT_HOLE) return in;   // SupportRound, SupportRectangle
+  if (kind == ART_SUPP_RECT_RECT_HOLE) {
+    const T hx = x - E.ap[4], hy = y - E.ap[5];
+    return mand(in, mnot(mand(mabs(hx) <= E.ap[2], mabs(hy) <= E.ap[3])));
   }
+  // round hole: ap = {.., Rh^2, cx, cy} from index 1 (SupportRoundHole) or 2 (SupportRectangleHole)
+  const double* h = E.ap + (kind == ART_SUPP_ROUND_HOLE ? 1 : 2);
+  const T hx = x - h[1], hy = y - h[2];
+  return mand(in, mnot(mfma(hx, hx, hy * hy) <= h[0]));
 }
 
 // ---------------------------------------------------------------------------------------------
