@@ -537,32 +537,33 @@ ART_HD void gridmap_eval(const MapDev& M, D2 X, D2 Y, D2& a, D2& b) {
 // surface normal, `get_normal` of each mirror class: surface_gradient gives its direction (any length),
 // surface_normal the unit vector
 // ---------------------------------------------------------------------------------------------
-template <class T>
+// SURFS (0 any / 1 toroid class / 2 quadric class, the enum further down): the surface kinds a kernel instantiation can
+// meet.  Written as nested two-way decisions on the warp-uniform kind: a five-way switch becomes a jump table.
+template <int SURFS = 0, class T>
 ART_HD void surface_gradient(const ElemDev& E, T x, T y, T z, T& gx, T& gy, T& gz) {
-  switch (E.surface) {
-    case ART_SURF_SPHERICAL:  // ART/ModuleMirror.py:180-183
-      gx = -x; gy = -y; gz = -z;
-      break;
-    case ART_SURF_PARABOLIC:  // :349-355
-      gx = -x; gy = -y; gz = splat<T>(E.sp[0]);
-      break;
-    case ART_SURF_TOROIDAL: {  // :480-498 (common factor 4 dropped)
-      const T S = mfma(x, x, mfma(y, y, z * z));
-      const T a = S + E.sp[3];        // + (R^2 - r^2)
-      const T b = a - 2.0 * E.sp[4];  // - 2 R^2
-      gx = -(x * b); gy = -(y * a); gz = -(z * b);
-      break;
-    }
-    case ART_SURF_ELLIPSOIDAL:  // :685-693
-      gx = -(x * E.sp[2]); gy = -(y * E.sp[3]); gz = -(z * E.sp[3]);
-      break;
-    case ART_SURF_CYLINDRICAL:  // :846-849
-      gx = splat<T>(0.0); gy = -y; gz = -z;
-      break;
-    default:  // plane, mask: :84-87
-      gx = splat<T>(0.0); gy = splat<T>(0.0); gz = splat<T>(1.0);
-      break;
+  const int kind = E.surface;
+  if (SURFS != 2 && kind == ART_SURF_TOROIDAL) {  // ART/ModuleMirror.py:480-498 (common factor 4 dropped)
+    const T S = mfma(x, x, mfma(y, y, z * z));
+    const T a = S + E.sp[3];        // + (R^2 - r^2)
+    const T b = a - 2.0 * E.sp[4];  // - 2 R^2
+    gx = -(x * b); gy = -(y * a); gz = -(z * b);
+    return;
   }
+  if (kind == ART_SURF_PLANE || kind == ART_SURF_MASK || SURFS == 1) {  // :84-87
+    gx = splat<T>(0.0); gy = splat<T>(0.0); gz = splat<T>(1.0);
+    return;
+  }
+  if (kind == ART_SURF_SPHERICAL || kind == ART_SURF_PARABOLIC) {
+    gx = -x; gy = -y;
+    if (kind == ART_SURF_SPHERICAL) gz = -z;     // :180-183
+    else gz = splat<T>(E.sp[0]);                 // :349-355
+    return;
+  }
+  if (kind == ART_SURF_ELLIPSOIDAL) {  // :685-693
+    gx = -(x * E.sp[2]); gy = -(y * E.sp[3]); gz = -(z * E.sp[3]);
+    return;
+  }
+  gx = splat<T>(0.0); gy = -y; gz = -z;  // ART_SURF_CYLINDRICAL :846-849
 }
 template <class T>
 ART_HD void surface_normal(const ElemDev& E, T x, T y, T z, T& nx, T& ny, T& nz) {
@@ -735,7 +736,7 @@ ART_HD void apply_element(const ElemDev& E, RayT<T>& r, const double* __restrict
       // reflection keeps |u| to rounding; Ray.vector's renormalisation, ART/ModuleOpticalRay.py:85-90, moves the
       // last bit only)
       T gx, gy, gz;
-      surface_gradient(E, hx, hy, hz, gx, gy, gz);
+      surface_gradient<SURFS>(E, hx, hy, hz, gx, gy, gz);
       const T d = mfma(gx, e.ux, mfma(gy, e.uy, gz * e.uz));
       if (WANT_INC && inc_here) inc = unit_angle(-e.ux, -e.uy, -e.uz, gx, gy, gz);
       const T k = fdiv(-2.0 * d, mfma(gx, gx, mfma(gy, gy, gz * gz)));
