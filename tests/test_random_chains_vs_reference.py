@@ -2,13 +2,17 @@
 supports) placed by the reference's own OEPlacement at random distances / incidences / plane angles and then
 misaligned at random; a point-source bundle is traced by the reference's RayTracingCalculation and by the device
 code compiled for the host (the kernel's element loop with its fused element-to-element hand-over) on the poses the
-reference produced.  After every element: identical survivors, points within 2e-9 mm, directions within 1e-10, path
-lengths within 2e-9 mm.  Complements the fixed scenes of tests/golden (arbitrary relative poses stress the composed
+reference produced.  After every element the survivor sets are identical; the extended-precision arbiter
+(oracle/art_oracle_ld.py) decides the numbers: the device code stays within 1e-10 mm (points, paths) of it on every
+scene, the reference within 1e-8 mm (its np.roots toroid quartic and lab-frame round trips reach a few 1e-9 mm on
+these 2 m chains).  Complements the fixed scenes of tests/golden (arbitrary relative poses stress the composed
 hand-over map) and tests/test_adversarial_vs_reference.py (single optics, arbitrary rays).
 Runs where a copy of the reference is present (build container: /root/reference; elsewhere oracle/_ref)."""
 import numpy as np
 import pytest
 
+import art_oracle_ld as ld
+import gen_golden
 import hostcheck_util
 import ref_runner
 from attosecondraytracing_b200 import _cabi
@@ -78,6 +82,16 @@ def test_random_chain_matches_the_live_reference(seed):
                                       np.asarray(roe.normal, dtype=np.float64), np.asarray(roe.majoraxis, dtype=np.float64)))
     dev = hostcheck_util.trace(LoweredChain([oes]), src_P, src_U, _cabi.TRACE_IGNORE_DEFECTS)
     kinds = "+".join(s["kind"] for s in scene["optics"])
+    arb = None
+    if ld.available():
+        els = []
+        for spec, roe in zip(scene["optics"], chain.optical_elements):
+            optic = gen_golden.derived_optic(spec, roe.type)
+            optic["support"] = tuple(optic["support"])
+            els.append({"optic": optic, "position": np.asarray(roe.position, dtype=np.float64),
+                        "normal": np.asarray(roe.normal, dtype=np.float64),
+                        "majoraxis": np.asarray(roe.majoraxis, dtype=np.float64)})
+        arb = ld.trace_chain(src_P, src_U, els, ignore_defects=True)
     for k, ref_list in enumerate(out):
         ref_num = np.array([r.number for r in ref_list], dtype=np.int64)
         got = np.nonzero(dev[k]["alive"])[0]
@@ -86,7 +100,14 @@ def test_random_chain_matches_the_live_reference(seed):
             continue
         ref_P = np.array([r.point for r in ref_list]).reshape(-1, 3)
         ref_U = np.array([r.vector for r in ref_list]).reshape(-1, 3)
-        ref_L = np.array([r.path if np.isscalar(r.path) else np.sum(r.path) for r in ref_list], dtype=np.float64)
-        assert np.max(np.abs(dev[k]["P"][got] - ref_P)) <= 2e-9, (seed, kinds, k)
+        ref_L = np.array([np.sum(r.path) for r in ref_list], dtype=np.float64)
+        # the reference against the device code: its own noise is the limit
+        assert np.max(np.abs(dev[k]["P"][got] - ref_P)) <= 1e-8, (seed, kinds, k)
         assert np.max(np.abs(dev[k]["U"][got] - ref_U)) <= 1e-10, (seed, kinds, k)
-        assert np.max(np.abs(dev[k]["path"][got] - ref_L)) <= 2e-9, (seed, kinds, k)
+        assert np.max(np.abs(dev[k]["path"][got] - ref_L)) <= 1e-8, (seed, kinds, k)
+        if arb is not None:
+            assert np.array_equal(arb[k]["number"], ref_num), (seed, kinds, k)
+            d_dev = float(np.max(np.abs(dev[k]["P"][got] - arb[k]["P"])))
+            d_path = float(np.max(np.abs(dev[k]["path"][got] - arb[k]["path"])))
+            assert d_dev <= 1e-10 and d_path <= 2e-10, (seed, kinds, k, d_dev, d_path)
+            assert float(np.max(np.abs(ref_P - arb[k]["P"]))) <= 1e-8, (seed, kinds, k)
