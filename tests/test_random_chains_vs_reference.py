@@ -111,3 +111,72 @@ def test_random_chain_matches_the_live_reference(seed):
             d_path = float(np.max(np.abs(dev[k]["path"][got] - arb[k]["path"])))
             assert d_dev <= 1e-10 and d_path <= 2e-10, (seed, kinds, k, d_dev, d_path)
             assert float(np.max(np.abs(ref_P - arb[k]["P"]))) <= 1e-8, (seed, kinds, k)
+
+
+DEFORMED = [
+    ({"kind": "parabolic", "feff": 400.0, "offaxisangle_deg": 30.0, "support": ["rect", 90, 90]}, (0, 0)),
+    ({"kind": "spherical", "radius_signed": 2500.0, "support": ["round", 40]}, (2, 25)),
+    ({"kind": "plane", "support": ["round", 50]}, (5, 60)),
+    ({"kind": "toroidal", "majorradius": TOR[0], "minorradius": TOR[1], "support": ["rect", 300, 60]}, (70, 82)),
+]
+
+
+def _deformed_scene(seed):
+    """As _scene, with a Zernike-deformed mirror (random order 3..8, random coefficients) somewhere in the chain."""
+    import scenes as sc
+    rng = np.random.default_rng(1000 + seed)
+    scene = _scene(1000 + seed)
+    k = int(rng.integers(len(scene["optics"])))
+    base, inc = DEFORMED[int(rng.integers(len(DEFORMED)))]
+    optic = dict(base)
+    optic["defects"] = [{"kind": "zernike",
+                         "coefficients": sc.zernike_table(int(rng.integers(3, 9)), seed=seed, scale=float(rng.uniform(5e-5, 3e-4)))}]
+    if rng.random() < 0.5:   # two stacked defects
+        optic["defects"].append({"kind": "zernike", "coefficients": [[2, 1, 4e-5], [3, 0, -6e-5], [5, 4, 3e-5]]})
+    scene["optics"][k] = optic
+    scene["incidences"][k] = float(rng.uniform(*inc)) * (1 if rng.random() < 0.5 else -1)
+    scene["source"]["Divergence"] = float(rng.uniform(5e-3, 30e-3))
+    return scene
+
+
+@pytest.mark.parametrize("ignore", [True, False])
+@pytest.mark.parametrize("seed", range(8))
+def test_random_chain_with_zernike_defects(seed, ignore):
+    """Both IgnoreDefects modes of the reference (ART/ModuleMirror.py:945-980) on random chains with a deformed mirror."""
+    R = ref_runner.ref()
+    import load_reference as lr
+    import attosecondraytracing_b200.ModuleOpticalElement as moe
+    scene = _deformed_scene(seed)
+    chain = ref_runner.build_chain(scene)
+    n = scene["source"]["NumberRays"]
+    rays = ref_runner.subset_source_rays(scene, n, np.arange(n))
+    src_P = np.array([r.point for r in rays], dtype=np.float64)
+    src_U = np.array([r.vector for r in rays], dtype=np.float64)
+    with lr.quiet():
+        out = R.mp.RayTracingCalculation(rays, chain.optical_elements, IgnoreDefects=ignore)
+    oes, els = [], []
+    for spec, roe in zip(scene["optics"], chain.optical_elements):
+        pose = [np.asarray(getattr(roe, a), dtype=np.float64) for a in ("position", "normal", "majoraxis")]
+        oes.append(moe.OpticalElement(build_optic(dict(spec, support=tuple(spec["support"]))), *pose))
+        optic = gen_golden.derived_optic(spec, roe.type)
+        optic["support"] = tuple(optic["support"])
+        if optic.get("defects"):
+            for dd in optic["defects"]:
+                dd["coefficients"] = {(int(a), int(b)): c for a, b, c in dd["coefficients"]}
+        els.append({"optic": optic, "position": pose[0], "normal": pose[1], "majoraxis": pose[2]})
+    dev = hostcheck_util.trace(LoweredChain([oes]), src_P, src_U, _cabi.TRACE_IGNORE_DEFECTS if ignore else 0)
+    arb = ld.trace_chain(src_P, src_U, els, ignore_defects=ignore) if ld.available() else None
+    kinds = "+".join(s["kind"] + ("*" if s.get("defects") else "") for s in scene["optics"])
+    for k, ref_list in enumerate(out):
+        ref_num = np.array([r.number for r in ref_list], dtype=np.int64)
+        got = np.nonzero(dev[k]["alive"])[0]
+        assert np.array_equal(got, ref_num), (seed, kinds, k, np.setxor1d(got, ref_num)[:8])
+        if ref_num.size == 0:
+            continue
+        ref_P = np.array([r.point for r in ref_list]).reshape(-1, 3)
+        ref_U = np.array([r.vector for r in ref_list]).reshape(-1, 3)
+        assert np.max(np.abs(dev[k]["P"][got] - ref_P)) <= 1e-8, (seed, kinds, k)
+        assert np.max(np.abs(dev[k]["U"][got] - ref_U)) <= 1e-10, (seed, kinds, k)
+        if arb is not None:
+            assert np.array_equal(arb[k]["number"], ref_num), (seed, kinds, k)
+            assert float(np.max(np.abs(dev[k]["P"][got] - arb[k]["P"]))) <= 1e-10, (seed, kinds, k)
